@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs token-updates/s of the B200 engine on BASELINE.json configs[1] (lda_100k).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--docs D]
+
+A "step" is one full Gibbs sweep (mvtm_sweep) over the rank's shard.  N > 1 is launched by torchrun, one rank per
+GPU; every rank holds a 100 K-document shard (weak scaling), n_wk is replicated and the per-sweep count deltas
+are all-reduced with NCCL inside the timed region.  Rank 0 prints ONE JSON line.
+
+--impl reference times the reference's CPU scheme (oracle/: multithreaded restatement of the Java
+worker/updater/queue design; the Java code itself cannot run, there is no JVM in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gibbs_token_updates_per_sec"
+UNIT = "tokens/s"
+
+
+def b_tok(K, mean_len):
+    """Algorithmic bytes per token update, SURVEY.md 8(d) / BASELINE.md section 3 (single view)."""
+    return 4 * K + 4 + 8 + 16 + 8.0 * K / mean_len
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(workload, sample_docs, steps, warmup, threads):
+    """The reference's multithreaded CPU scheme (oracle restatement) on a bounded sample of the workload."""
+    from mvtopicmodel_b200 import corpus
+    from oracle import oracle as O
+    O.build()
+    K, Vs, views = corpus.generate(workload, docs=sample_docs)
+    o = O.Oracle(K, Vs, views, seed=2026)
+    o.init_assignments()
+    o.rebuild_trees()
+    ntok = sum(o.ntok)
+    for it in range(1, warmup + 1):
+        o.sweep_mt(it, threads)
+    t0 = time.perf_counter()
+    for it in range(warmup + 1, warmup + steps + 1):
+        o.sweep_mt(it, threads)
+    dt = time.perf_counter() - t0
+    assert o.check_invariants() == 0
+    return ntok * steps / dt, dt / steps * 1e3, ntok, K
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="lda_100k")
+    ap.add_argument("--docs", type=int, default=None, help="documents per rank (default: the workload's D)")
+    ap.add_argument("--cpu-sample-docs", type=int, default=25000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from mvtopicmodel_b200 import corpus
+    cfg = corpus.CONFIGS[args.workload]
+    mean_len = sum(v[1] * v[3] for v in cfg["views"]) / max(1, len(cfg["views"]))
+    wl_desc = (f"{args.workload}: BASELINE configs[1] synthetic single-view LDA shape, D={cfg['D']} docs/GPU, "
+               f"V={cfg['views'][0][0]}, K={cfg['K']}, ~{int(cfg['D'] * cfg['views'][0][1] / 1e6)}M tokens/GPU")
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5)); warmup = max(1, min(args.warmup, 1))
+        val, ms, ntok, K = cpu_reference_run(args.workload, args.cpu_sample_docs, steps, warmup, threads)
+        nst, nut = 3 * threads // 4, threads // 4
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+                "data": "synthetic", "config": {"workload": wl_desc, "sample": f"{args.cpu_sample_docs} docs / {ntok} tokens per step"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"first {args.cpu_sample_docs} docs ({ntok} tokens) of {args.workload}, {steps} sweeps; "
+                                           f"{nst} sampler + {nut} updater threads (M:1036-1037); C restatement of the Java scheme, no JVM in this image"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from mvtopicmodel_b200 import Engine
+    from mvtopicmodel_b200.dist import CountExchange, EngineAdapter
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    K, Vs, views = corpus.generate(args.workload, shard=rank, docs=args.docs)
+    M = len(views)
+    D_local = len(views[0][0]) - 1
+    eng = Engine(K, Vs, views, seed=2026, device=local_rank, doc_id_base=rank, doc_id_stride=world)
+    ntok_local = sum(eng.ntok)
+    xch = None
+    if world > 1:
+        xch = CountExchange(EngineAdapter(eng, local_rank))
+        xch.reset()
+    eng.init_assignments()
+    if xch:
+        xch.exchange()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(it):
+        eng.sweep(it)
+        if xch:
+            xch.exchange()
+
+    it = 0
+    for _ in range(args.warmup):
+        it += 1
+        step(it)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, changed = 0.0, 0
+    ev0.record()
+    for _ in range(args.steps):
+        it += 1
+        step(it)
+        st = eng.stats()
+        kern_ms += sum(st["ms_view"])
+        changed += st["changed"]
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist:
+        t = torch.tensor([ms_total, kern_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, kern_ms_max = float(t[0]), float(t[1])
+        n = torch.tensor([ntok_local], device="cuda", dtype=torch.int64)
+        dist.all_reduce(n)
+        ntok_global = int(n[0])
+    else:
+        ntok_global, kern_ms_max = ntok_local, kern_ms
+    viol = eng.check_invariants() if world == 1 else 0
+    value = ntok_global * args.steps / (ms_total * 1e-3)
+
+    # end-to-end: the same sweep through HOST buffers (pinned), H2D + count rebuild + sweep + D2H inside the timing
+    e2e = None
+    if not args.no_e2e:
+        zh = [torch.empty(n, dtype=torch.int32).pin_memory() for n in eng.ntok]
+        zn = [z.numpy() for z in zh]
+        for m in range(M):
+            zn[m][:] = eng.get_assignments(m)
+
+        def e2e_step(i):
+            if xch:
+                for m in range(M):
+                    eng.set_assignments(m, zn[m])          # H2D + local rebuild
+                xch.reset(); xch.exchange()                # local counts -> global counts
+                eng.sweep(i); xch.exchange()
+                for m in range(M):
+                    zn[m][:] = eng.get_assignments(m)      # D2H
+            else:
+                eng.sweep_host(i, zn)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            it += 1
+            e2e_step(it)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(e2e_steps):
+            it += 1
+            e2e_step(it)
+        ev1.record()
+        barrier()
+        e2e_ms = ev0.elapsed_time(ev1)
+        if dist:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+        e2e = {"value": ntok_global * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * ntok_local,
+               "d2h_bytes_per_step": 4 * ntok_local, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+               "call": "mvtm_sweep_host (pinned host z in/out, count rebuild + sweep inside)" if not xch else
+                       "mvtm_set_assignments + delta all-reduce + mvtm_sweep + delta all-reduce + mvtm_get_assignments"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    btok = b_tok(K, mean_len)
+    kern_s = kern_ms_max * 1e-3
+    achieved = btok * ntok_local * args.steps / kern_s / 1e9 if kern_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f32", "data": "synthetic",
+            "config": {"workload": wl_desc, "docs_per_gpu": D_local, "tokens_per_gpu": ntok_local, "K": K, "views": M,
+                       "l2": "inputs larger than L2 (z+words+n_wk = %d MB per sweep vs 126 MB L2), no explicit flush" %
+                             int((8 * ntok_local + 4 * sum(Vs) * eng.row_stride()) / 1e6),
+                       "changed_frac": changed / max(1, ntok_local * args.steps), "invariant_violations": viol},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_sweep_view", "bytes_per_token": btok, "tokens_per_launch": ntok_local,
+                         "avg_launch_ms": kern_ms_max / args.steps / M, "peak_source": peak_src},
+            "e2e": e2e, "gpu_launches": args.steps * M, "clocks": clocks}
+    if xch:
+        line["config"]["allreduce_bytes_per_sweep"] = xch.bytes_per_exchange
+    if world == 1 and not args.no_cpu_baseline:
+        val, ms, ntok_s, _ = cpu_reference_run(args.workload, args.cpu_sample_docs, 3, 1, threads)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"first {args.cpu_sample_docs} docs ({ntok_s} tokens) of {args.workload}, 3 sweeps, "
+                                          f"{3 * threads // 4} sampler + {threads // 4} updater threads"}
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

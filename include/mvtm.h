@@ -1,0 +1,148 @@
+/*
+ * mvtm.h -- C ABI of the B200-native collapsed-Gibbs engine for the multi-view HDP topic model (MViHDP).
+ *
+ * This is the drop-in boundary for ONE path of hmetaxa/MVTopicModel: the per-token sampling done by
+ * FastQMVWVWorkerRunnable and the count updates done by FastQMVWVUpdaterRunnable, as driven by
+ * FastQMVWVParallelTopicModel.addInstances()/estimate().  The reference has no FFI of its own (it is pure
+ * Java); each entry point below names the reference code whose job it takes over.
+ * Reference tags (under /root/reference/src/main/java/org/madgik/):
+ *   W = MVTopicModel/FastQMVWVWorkerRunnable.java     U = MVTopicModel/FastQMVWVUpdaterRunnable.java
+ *   M = MVTopicModel/FastQMVWVParallelTopicModel.java  I = MVTopicModel/FastQMVWVTopicInferencer.java
+ *
+ * Conventions: every function returns 0 on success and a non-zero mvtm_status otherwise, never throws or
+ * aborts; mvtm_last_error() returns a UTF-8 message for the last failure on that handle (or for a failed
+ * mvtm_create when h == NULL).  The caller owns every buffer it passes; inputs are copied.  One caller
+ * thread per handle; one handle drives one GPU.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with MVTM_ERR_CUDA.
+ */
+#ifndef MVTM_H
+#define MVTM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVTM_MAX_VIEWS 8
+#define MVTM_UNASSIGNED (-1)          /* FastQMVWVParallelTopicModel.UNASSIGNED_TOPIC */
+
+typedef enum {
+    MVTM_OK = 0,
+    MVTM_ERR_ARG = 1,        /* bad argument (K/M mismatch, NULL, out of range)             */
+    MVTM_ERR_STATE = 2,      /* call order (e.g. sweep before every view was added)         */
+    MVTM_ERR_CUDA = 3,       /* CUDA runtime failure, including "no device"                 */
+    MVTM_ERR_CORRUPT = 4,    /* negative count / invariant violation detected on the device */
+    MVTM_ERR_LIMIT = 5       /* a size this build does not support (doc-view > 65535 tokens, K > 2048) */
+} mvtm_status;
+
+/* mvtm_config.flags */
+#define MVTM_FLAG_DOC_ORDER   1u   /* work list in plain document order instead of longest-first (tests)     */
+#define MVTM_FLAG_SINGLE_WARP 2u   /* run each view pass with one warp: fully sequential, deterministic (tests) */
+
+typedef struct mvtm_config {
+    int32_t num_topics;              /* K, M:183 numTopics                                                   */
+    int32_t num_views;               /* M, M:183 numModalities                                               */
+    int64_t num_docs;                /* documents held by THIS handle (its shard)                            */
+    const int32_t *vocab_sizes;      /* V_m = alphabet[m].size(), M:413                                      */
+    uint64_t seed;                   /* Philox key (M:403-408 randomSeed)                                    */
+    int32_t device;                  /* CUDA device ordinal                                                  */
+    uint32_t flags;
+    int64_t doc_id_base;             /* global id of local document d is doc_id_base + d * doc_id_stride;     */
+    int64_t doc_id_stride;           /*   it keys the RNG, so a sharded run draws what the unsharded one does */
+    int32_t warps_per_cta;           /* 0 = auto                                                             */
+    int32_t ring_depth;              /* n_wk rows in flight per warp (TMA ring), 0 = auto                    */
+    int32_t max_ctas;                /* 0 = one persistent CTA per SM; smaller values bound the number of documents
+                                        sampled concurrently (the asynchrony the reference bounds by numThreads, M:1036) */
+} mvtm_config;
+
+typedef struct mvtm_sweep_stats {
+    int64_t tokens;                  /* token updates performed by the last sweep (all views)                */
+    int64_t changed;                 /* tokens whose topic changed (= deltas of W:587-589)                   */
+    int64_t new_topic;               /* draws from the new-topic bucket (W:523 newMassCnt)                   */
+    double ms_total;                 /* device time of the last sweep, CUDA events                           */
+    double ms_view[MVTM_MAX_VIEWS];  /* device time of each view's sampling kernel                           */
+    int32_t kernel_launches;         /* kernels launched by the last sweep                                   */
+} mvtm_sweep_stats;
+
+typedef struct mvtm_handle mvtm_handle;
+
+/* Lifecycle.  Replaces the constructor M:183-247 + initSpace M:575-598 (device allocation). */
+int mvtm_create(const mvtm_config *cfg, mvtm_handle **out);
+int mvtm_destroy(mvtm_handle *h);
+const char *mvtm_last_error(const mvtm_handle *h);
+
+/* Corpus.  Replaces the per-view document collection of addInstances M:410-463: view m as a doc-aligned
+ * CSR (doc_off has num_docs+1 entries; a document that lacks view m has an empty range).  `present`
+ * (nullable, num_docs bytes) marks documents that own an Assignments[m] object even if it is empty
+ * (only the log-likelihood quirk Q18 looks at it). */
+int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, const int32_t *word_id, const uint8_t *present);
+
+/* Initial assignments.  mvtm_init_assignments = the random initialisation M:465-515 followed by
+ * buildInitialTypeTopicCounts M:600-652; mvtm_set_assignments imports z (state restore, M:534-573) and
+ * rebuilds the view's counts. */
+int mvtm_init_assignments(mvtm_handle *h);
+int mvtm_set_assignments(mvtm_handle *h, int32_t m, const int32_t *z);
+
+/* Hyper-parameters as the worker/updater constructors receive them (W:80-150, U:78-147).  Any pointer may
+ * be NULL (= keep).  alpha is M x (K+1) row-major (slot K = new-topic prior), p_a/p_b are M x M;
+ * inactive = inActiveTopicIndex (M:95) as a list, n_inactive < 0 = keep.  Defaults after create are the
+ * driver's: alpha 0.1, alphaSum 0.1*K, beta 0.01, betaSum beta*V, gamma 1, p_a 0.2, p_b 1, no inactive topics. */
+int mvtm_set_hyper(mvtm_handle *h, const double *alpha, const double *alpha_sum, const double *beta,
+                   const double *beta_sum, const double *gamma, const double *p_a, const double *p_b,
+                   const int32_t *inactive, int32_t n_inactive);
+int mvtm_get_hyper(mvtm_handle *h, double *alpha, double *alpha_sum, int32_t *inactive, int32_t *n_inactive);
+
+/* One Gibbs sweep over every view = one iteration of estimate()'s loop body M:1213-1239: the work of all
+ * FastQMVWVWorkerRunnable.run (W:186-233, W:301-597) and FastQMVWVUpdaterRunnable.run (U:164-297) threads up to
+ * the barrier.  update_global = 0 freezes n_wk / n_k (the inferencer's nut = 0 mode, I:211-256).  Blocking. */
+int mvtm_sweep(mvtm_handle *h, int32_t iteration, int32_t update_global);
+
+/* The same sweep through HOST buffers: uploads z (one array per view, caller memory, pinned or pageable),
+ * rebuilds the counts from it, sweeps, and downloads the new z into the same arrays.  This is the call a
+ * stateless host (a JVM holding topicSequence arrays) makes; bench.py's e2e number times it. */
+int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout);
+
+/* Readers.  z: LabelSequence.getFeatures() of every doc concatenated in CSR order; n_wk: typeTopicCounts[m]
+ * as V_m x K row-major by word (M:584); n_k: tokensPerTopic[m]. */
+int mvtm_get_assignments(mvtm_handle *h, int32_t m, int32_t *z_out);
+int mvtm_get_counts(mvtm_handle *h, int32_t m, int32_t *n_wk_out, int32_t *n_k_out);
+
+/* topicDocCounts[m][t][c] (U:220-232, M:647-649), recomputed from the assignments: K x (max_len+1) ints,
+ * bin c = number of documents in which topic t holds exactly c tokens of view m.  *max_len_out receives the
+ * longest document of the view; call with hist_out == NULL to query it. */
+int mvtm_doc_topic_hist(mvtm_handle *h, int32_t m, int32_t *hist_out, int32_t *max_len_out);
+
+/* modelLogLikelihood M:3322-3452 with MALLET's logGammaStirling; ll_out has M entries.  quirk_len2 != 0
+ * reproduces Q18 (phantom topic-0 tokens of documents shorter than two tokens). */
+int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2);
+
+/* Parity probe: the conditional distribution of token (m, doc, pos) on the current (frozen) counts, computed
+ * by the same device code the sweep uses.  p_row = row m of the view-coupling matrix p (W:327-337), M entries
+ * (NULL = identity).  probs_out[0..K) normalised, probs_out[K] = share of the new-topic bucket (W:515). */
+int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, double *probs_out);
+
+/* n_wk == histogram of (word, z), n_k == histogram of z, no negative cell.
+ * *violations_out = number of offending cells (0 = consistent). */
+int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out);
+
+int mvtm_stats(mvtm_handle *h, mvtm_sweep_stats *out);
+
+/* Multi-GPU plumbing (one handle per rank, documents sharded, n_wk / n_k replicated -- SURVEY 8e).
+ * mvtm_delta_begin snapshots the replicas; after local sweeps mvtm_delta_export turns view m's replica into
+ * its local delta IN PLACE and returns the device pointers (n_wk: V_m x row_stride int32, n_k: row_stride int32)
+ * for the caller's all-reduce (NCCL through torch.distributed); mvtm_delta_import adds the reduced delta back
+ * onto the snapshot, giving every rank the same bit-exact global counts. */
+int mvtm_delta_begin(mvtm_handle *h);
+int mvtm_delta_reset(mvtm_handle *h);      /* snapshot := 0 (the replicas hold purely local counts, e.g. right after a rebuild) */
+int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems);
+int mvtm_delta_import(mvtm_handle *h, int32_t m);
+int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out);
+
+/* Build information: "sm_100a", kernel variants compiled in. */
+const char *mvtm_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVTM_H */

@@ -1,0 +1,783 @@
+// mvtm.cu -- host side of the C ABI declared in include/mvtm.h (libmvtm.so).
+// Plain pointers and sizes only; no torch types.  There is no CPU fallback: every compute entry point
+// needs a CUDA device and reports MVTM_ERR_CUDA otherwise.
+#include "mvtm.h"
+#include "mvtm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ViewDev {
+    bool added = false;
+    int V = 0;
+    long long n_tok = 0;
+    int max_len = 0;
+    long long docs_present = 0;
+    int n_items = 0;
+    long long *doc_off = nullptr;
+    int *word = nullptr, *z = nullptr;
+    unsigned char *present = nullptr;
+    int *nwk = nullptr, *nk = nullptr, *nk_snap = nullptr;
+    int *order = nullptr;
+    float *ga_tree = nullptr, *ga_full = nullptr;
+    int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
+    std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
+};
+
+}  // namespace
+
+struct mvtm_handle {
+    int K = 0, M = 0, Kp = 0, J = 0;
+    long long D = 0;
+    int device = 0, num_sms = 0;
+    unsigned flags = 0;
+    unsigned long long seed = 0;
+    long long doc_id_base = 0, doc_id_stride = 1;
+    int cfg_warps = 0, cfg_ring = 0, cfg_ctas = 0;
+    ViewDev v[MVTM_MAX_VIEWS];
+    // hyper-parameters (host, fp64 as the reference keeps them)
+    std::vector<double> alpha;                      // M x (K+1)
+    double alphaSum[MVTM_MAX_VIEWS], beta[MVTM_MAX_VIEWS], betaSum[MVTM_MAX_VIEWS], gamma[MVTM_MAX_VIEWS];
+    double p_a[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS], p_b[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS];
+    std::vector<int> inactive;
+    bool hyper_dirty = true;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
+    int *work_counter = nullptr;
+    unsigned long long *d_stats = nullptr;
+    int *d_bad = nullptr;
+    mvtm_sweep_stats stats;
+    std::string err;
+};
+
+static std::string g_create_err;
+
+#define FAIL(h, code, ...)                                              \
+    do {                                                                \
+        char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+        (h)->err = _b; return (code);                                   \
+    } while (0)
+#define CK(h, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess) FAIL(h, MVTM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static int pick_J(int K)
+{
+    static const int opts[] = { 1, 2, 3, 4, 6, 8, 12, 16 };
+    for (int j : opts) if (j * 128 >= K) return j;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *mvtm_build_info(void)
+{
+    return "mvtm-b200 sm_100a; k_sweep_view<J in {1,2,3,4,6,8,12,16}, single|multi view>; TMA 1-D bulk ring; Philox4x32-10";
+}
+
+extern "C" const char *mvtm_last_error(const mvtm_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
+{
+    if (!cfg || !out) { g_create_err = "mvtm_create: NULL argument"; return MVTM_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->num_topics < 1 || cfg->num_views < 1 || cfg->num_views > MVTM_MAX_VIEWS || cfg->num_docs < 0 || !cfg->vocab_sizes) {
+        g_create_err = "mvtm_create: bad K / M / D / vocab_sizes"; return MVTM_ERR_ARG;
+    }
+    if (pick_J(cfg->num_topics) == 0) { g_create_err = "mvtm_create: K > 2048 is not supported by this build"; return MVTM_ERR_LIMIT; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("mvtm_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback";
+        return MVTM_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "mvtm_create: bad device ordinal"; return MVTM_ERR_ARG; }
+    mvtm_handle *h = new mvtm_handle();
+    h->K = cfg->num_topics; h->M = cfg->num_views; h->D = cfg->num_docs; h->device = cfg->device;
+    h->flags = cfg->flags; h->seed = cfg->seed;
+    h->doc_id_base = cfg->doc_id_base; h->doc_id_stride = cfg->doc_id_stride ? cfg->doc_id_stride : 1;
+    h->cfg_warps = cfg->warps_per_cta; h->cfg_ring = cfg->ring_depth; h->cfg_ctas = cfg->max_ctas;
+    h->Kp = (h->K + 31) / 32 * 32;
+    h->J = pick_J(h->K);
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->alpha.assign((size_t)h->M * (h->K + 1), 0.1);                    // S:149-159, M:195-239
+    for (int m = 0; m < h->M; m++) {
+        if (cfg->vocab_sizes[m] < 1) { g_create_err = "mvtm_create: vocab size < 1"; delete h; return MVTM_ERR_ARG; }
+        h->v[m].V = cfg->vocab_sizes[m];
+        h->alphaSum[m] = 0.1 * h->K; h->beta[m] = 0.01; h->betaSum[m] = 0.01 * h->v[m].V; h->gamma[m] = 1.0;
+        for (int j = 0; j < h->M; j++) { h->p_a[m][j] = 0.2; h->p_b[m][j] = 1.0; }   // M:1055-1058
+    }
+#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(_e); delete h; return MVTM_ERR_CUDA; } } while (0)
+    CKC(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &ev : h->ev) CKC(cudaEventCreate(&ev));
+    CKC(cudaMalloc(&h->work_counter, sizeof(int)));
+    CKC(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&h->d_bad, sizeof(int)));
+#undef CKC
+    *out = h;
+    return MVTM_OK;
+}
+
+static void free_view(ViewDev &v)
+{
+    cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk); cudaFree(v.nk);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.snap_nwk); cudaFree(v.snap_nk);
+    v = ViewDev();
+}
+
+extern "C" int mvtm_destroy(mvtm_handle *h)
+{
+    if (!h) return MVTM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int m = 0; m < h->M; m++) free_view(h->v[m]);
+    for (auto &ev : h->ev) cudaEventDestroy(ev);
+    cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out)
+{
+    if (!h || !stride_out) return MVTM_ERR_ARG;
+    *stride_out = h->Kp;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, const int32_t *word_id, const uint8_t *present)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !doc_off) FAIL(h, MVTM_ERR_ARG, "mvtm_add_view: bad view index or NULL doc_off");
+    CK(h, cudaSetDevice(h->device));
+    ViewDev &v = h->v[m];
+    const long long D = h->D;
+    if (doc_off[0] != 0) FAIL(h, MVTM_ERR_ARG, "mvtm_add_view: doc_off[0] must be 0");
+    int max_len = 0;
+    for (long long d = 0; d < D; d++) {
+        long long len = doc_off[d + 1] - doc_off[d];
+        if (len < 0) FAIL(h, MVTM_ERR_ARG, "mvtm_add_view: doc_off not monotone at doc %lld", d);
+        if (len > 65535) FAIL(h, MVTM_ERR_LIMIT, "mvtm_add_view: doc %lld holds %lld tokens in view %d (limit 65535)", d, len, m);
+        max_len = std::max<int>(max_len, (int)len);
+    }
+    const long long N = doc_off[D];
+    if (N > 0 && !word_id) FAIL(h, MVTM_ERR_ARG, "mvtm_add_view: NULL word_id");
+    { int V = v.V; free_view(v); v.V = V; }
+    v.n_tok = N; v.max_len = max_len;
+    v.h_doc_off.assign(doc_off, doc_off + D + 1);
+    // work list: documents that hold tokens, longest first (north_star a: bucketed by length and view)
+    std::vector<int> order;
+    order.reserve((size_t)D);
+    std::vector<unsigned char> pres((size_t)std::max<long long>(D, 1));
+    v.docs_present = 0;
+    for (long long d = 0; d < D; d++) {
+        long long len = doc_off[d + 1] - doc_off[d];
+        if (len > 0) order.push_back((int)d);
+        pres[(size_t)d] = present ? present[d] : (len > 0);
+        v.docs_present += pres[(size_t)d];
+    }
+    if (!(h->flags & MVTM_FLAG_DOC_ORDER))
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return doc_off[a + 1] - doc_off[a] > doc_off[b + 1] - doc_off[b]; });
+    v.n_items = (int)order.size();
+    const size_t Kp = (size_t)h->Kp;
+    CK(h, cudaMalloc(&v.doc_off, (size_t)(D + 1) * 8));
+    CK(h, cudaMalloc(&v.word, (size_t)std::max<long long>(N, 1) * 4));
+    CK(h, cudaMalloc(&v.z, (size_t)std::max<long long>(N, 1) * 4));
+    CK(h, cudaMalloc(&v.present, pres.size()));
+    CK(h, cudaMalloc(&v.order, (size_t)std::max<int>(v.n_items, 1) * 4));
+    CK(h, cudaMalloc(&v.nwk, (size_t)v.V * Kp * 4));
+    CK(h, cudaMalloc(&v.nk, Kp * 4));
+    CK(h, cudaMalloc(&v.nk_snap, Kp * 4));
+    CK(h, cudaMalloc(&v.ga_tree, Kp * 4));
+    CK(h, cudaMalloc(&v.ga_full, Kp * 4));
+    CK(h, cudaMemcpy(v.doc_off, doc_off, (size_t)(D + 1) * 8, cudaMemcpyHostToDevice));
+    if (N > 0) CK(h, cudaMemcpy(v.word, word_id, (size_t)N * 4, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(v.present, pres.data(), pres.size(), cudaMemcpyHostToDevice));
+    if (v.n_items) CK(h, cudaMemcpy(v.order, order.data(), (size_t)v.n_items * 4, cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(v.z, 0xff, (size_t)std::max<long long>(N, 1) * 4));       // UNASSIGNED_TOPIC
+    CK(h, cudaMemset(v.nwk, 0, (size_t)v.V * Kp * 4));
+    CK(h, cudaMemset(v.nk, 0, Kp * 4));
+    v.added = true;
+    h->hyper_dirty = true;
+    return MVTM_OK;
+}
+
+static int require_views(mvtm_handle *h, const char *who)
+{
+    for (int m = 0; m < h->M; m++) if (!h->v[m].added) FAIL(h, MVTM_ERR_STATE, "%s: view %d has not been added", who, m);
+    return MVTM_OK;
+}
+
+static int rebuild_counts_view(mvtm_handle *h, int m)
+{
+    ViewDev &v = h->v[m];
+    const size_t Kp = (size_t)h->Kp;
+    CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * Kp * 4, h->stream));
+    CK(h, cudaMemsetAsync(v.nk, 0, Kp * 4, h->stream));
+    CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+    if (v.n_tok > 0) {
+        int blocks = (int)std::min<long long>((v.n_tok + 255) / 256, (long long)h->num_sms * 8);
+        k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad);
+        CK(h, cudaGetLastError());
+    }
+    int bad = 0;
+    CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (bad) FAIL(h, MVTM_ERR_ARG, "assignments of view %d hold %d topic ids >= K", m, bad);
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_init_assignments(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_views(h, "mvtm_init_assignments")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        if (v.n_tok > 0) {
+            int blocks = (int)std::min<long long>((h->D * 32 + 255) / 256, (long long)h->num_sms * 16);
+            k_init_assign<<<std::max(blocks, 1), 256, 0, h->stream>>>(m, h->K, h->D, v.doc_off, h->v[0].doc_off, h->v[0].z, v.z,
+                                                                     (unsigned)h->seed, (unsigned)(h->seed >> 32), h->doc_id_base, h->doc_id_stride);
+            CK(h, cudaGetLastError());
+        }
+        if (int rc = rebuild_counts_view(h, m)) return rc;
+    }
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_set_assignments(mvtm_handle *h, int32_t m, const int32_t *z)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_set_assignments: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    ViewDev &v = h->v[m];
+    if (v.n_tok > 0) {
+        if (!z) FAIL(h, MVTM_ERR_ARG, "mvtm_set_assignments: NULL z");
+        CK(h, cudaMemcpyAsync(v.z, z, (size_t)v.n_tok * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    return rebuild_counts_view(h, m);
+}
+
+extern "C" int mvtm_get_assignments(mvtm_handle *h, int32_t m, int32_t *z_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_get_assignments: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    if (h->v[m].n_tok > 0) {
+        if (!z_out) FAIL(h, MVTM_ERR_ARG, "mvtm_get_assignments: NULL buffer");
+        CK(h, cudaMemcpyAsync(z_out, h->v[m].z, (size_t)h->v[m].n_tok * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_get_counts(mvtm_handle *h, int32_t m, int32_t *n_wk_out, int32_t *n_k_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_get_counts: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    ViewDev &v = h->v[m];
+    if (n_wk_out)
+        CK(h, cudaMemcpy2DAsync(n_wk_out, (size_t)h->K * 4, v.nwk, (size_t)h->Kp * 4, (size_t)h->K * 4, (size_t)v.V, cudaMemcpyDeviceToHost, h->stream));
+    if (n_k_out) CK(h, cudaMemcpyAsync(n_k_out, v.nk, (size_t)h->K * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_set_hyper(mvtm_handle *h, const double *alpha, const double *alpha_sum, const double *beta, const double *beta_sum,
+                              const double *gamma, const double *p_a, const double *p_b, const int32_t *inactive, int32_t n_inactive)
+{
+    if (!h) return MVTM_ERR_ARG;
+    const int M = h->M, K = h->K;
+    if (n_inactive > K || (n_inactive > 0 && !inactive)) FAIL(h, MVTM_ERR_ARG, "mvtm_set_hyper: bad inactive list");
+    if (alpha) {
+        for (size_t i = 0; i < (size_t)M * (K + 1); i++) if (!(alpha[i] >= 0.0) || !std::isfinite(alpha[i])) FAIL(h, MVTM_ERR_ARG, "mvtm_set_hyper: alpha[%zu] not finite/non-negative", i);
+        h->alpha.assign(alpha, alpha + (size_t)M * (K + 1));
+    }
+    for (int m = 0; m < M; m++) {
+        if (alpha_sum) h->alphaSum[m] = alpha_sum[m];
+        if (beta) { if (!(beta[m] > 0.0)) FAIL(h, MVTM_ERR_ARG, "mvtm_set_hyper: beta[%d] must be > 0", m); h->beta[m] = beta[m]; }
+        if (beta_sum) h->betaSum[m] = beta_sum[m];
+        if (gamma) h->gamma[m] = gamma[m];
+        for (int j = 0; j < M; j++) {
+            if (p_a) h->p_a[m][j] = p_a[m * M + j];
+            if (p_b) h->p_b[m][j] = p_b[m * M + j];
+        }
+    }
+    if (n_inactive >= 0) {
+        for (int i = 0; i < n_inactive; i++) if (inactive[i] < 0 || inactive[i] >= K) FAIL(h, MVTM_ERR_ARG, "mvtm_set_hyper: inactive topic %d out of range", inactive[i]);
+        h->inactive.assign(inactive, inactive + n_inactive);
+        std::sort(h->inactive.begin(), h->inactive.end());
+        h->inactive.erase(std::unique(h->inactive.begin(), h->inactive.end()), h->inactive.end());
+    }
+    h->hyper_dirty = true;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_get_hyper(mvtm_handle *h, double *alpha, double *alpha_sum, int32_t *inactive, int32_t *n_inactive)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (alpha) memcpy(alpha, h->alpha.data(), h->alpha.size() * 8);
+    if (alpha_sum) for (int m = 0; m < h->M; m++) alpha_sum[m] = h->alphaSum[m];
+    if (inactive) for (size_t i = 0; i < h->inactive.size(); i++) inactive[i] = h->inactive[i];
+    if (n_inactive) *n_inactive = (int)h->inactive.size();
+    return MVTM_OK;
+}
+
+static int upload_hyper(mvtm_handle *h)
+{
+    if (!h->hyper_dirty) return MVTM_OK;
+    const int K = h->K, Kp = h->Kp;
+    std::vector<float> tree((size_t)Kp), full((size_t)Kp);
+    for (int m = 0; m < h->M; m++) {
+        if (!h->v[m].added) continue;
+        std::fill(tree.begin(), tree.end(), 0.f); std::fill(full.begin(), full.end(), 0.f);
+        for (int t = 0; t < K; t++) {
+            double ga = h->gamma[m] * h->alpha[(size_t)m * (K + 1) + t];
+            full[t] = (float)ga;                                         // W:404
+            tree[t] = (float)ga;                                         // M:2678
+        }
+        for (int t : h->inactive) tree[t] = 0.f;                         // M:2670-2671
+        CK(h, cudaMemcpyAsync(h->v[m].ga_tree, tree.data(), (size_t)Kp * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->v[m].ga_full, full.data(), (size_t)Kp * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    h->hyper_dirty = false;
+    return MVTM_OK;
+}
+
+static void fill_params(mvtm_handle *h, int m, int iteration, int update_global, SweepParams &P)
+{
+    memset(&P, 0, sizeof(P));
+    ViewDev &v = h->v[m];
+    P.M = h->M; P.K = h->K; P.Kp = h->Kp; P.m = m; P.V = v.V;
+    P.n_items = v.n_items; P.order = v.order; P.work_counter = h->work_counter;
+    for (int i = 0; i < h->M; i++) {
+        P.doc_off[i] = h->v[i].doc_off; P.zv[i] = h->v[i].z; P.ga_full[i] = h->v[i].ga_full;
+        P.gas[i] = (float)(h->gamma[i] * h->alphaSum[i]);
+        P.ga_new[i] = (float)(h->gamma[i] * h->alpha[(size_t)i * (h->K + 1) + h->K]);
+        P.pa[i] = h->p_a[m][i]; P.pb[i] = h->p_b[m][i];
+        P.sparse[i] = (h->beta[i] == 0.0001);                            // W:335-336
+    }
+    P.word = v.word; P.nwk = v.nwk; P.nk_frozen = v.nk_snap; P.nk_live = v.nk; P.ga_tree = v.ga_tree;
+    P.beta = (float)h->beta[m]; P.betaSum = (float)h->betaSum[m];
+    P.n_inactive = (int)h->inactive.size(); P.first_inactive = h->inactive.empty() ? 0 : h->inactive[0];
+    P.seed_lo = (unsigned)h->seed; P.seed_hi = (unsigned)(h->seed >> 32); P.iteration = (unsigned)iteration;
+    P.doc_id_base = h->doc_id_base; P.doc_id_stride = h->doc_id_stride;
+    P.update_global = update_global;
+    P.stats = h->d_stats;
+}
+
+struct LaunchCfg { int R, W, grid; size_t smem; };
+
+static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
+{
+    const int KS = h->J * 128;
+    const bool multi = h->M > 1;
+    int R = h->cfg_ring > 0 ? h->cfg_ring : (KS >= 1024 ? 3 : 4);
+    if (const char *e = getenv("MVTM_RING")) R = atoi(e);
+    R = std::max(1, std::min(R, 16));
+    const size_t budget = 227 * 1024 - 1024;
+    int W;
+    for (;;) {
+        size_t per = smem_warp_bytes(KS, R, multi);
+        W = (int)((budget - smem_cta_bytes(KS)) / per);
+        if (W >= 1 || R == 1) break;
+        R--;
+    }
+    if (W < 1) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
+    W = std::min(W, 16);
+    if (h->cfg_warps > 0) W = std::min(W, h->cfg_warps);
+    if (const char *e = getenv("MVTM_WARPS")) W = std::max(1, std::min(W, atoi(e)));
+    int grid = h->num_sms;
+    if (h->cfg_ctas > 0) grid = std::min(grid, h->cfg_ctas);
+    if (const char *e = getenv("MVTM_CTAS")) grid = std::max(1, std::min(grid, atoi(e)));
+    if (h->flags & MVTM_FLAG_SINGLE_WARP) { W = 1; grid = 1; }
+    lc.R = R; lc.W = W; lc.grid = grid;
+    lc.smem = smem_cta_bytes(KS) + (size_t)W * smem_warp_bytes(KS, R, multi);
+    return MVTM_OK;
+}
+
+template <int J, bool MULTI>
+static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_view<J, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+    if (e != cudaSuccess) return e;
+    k_sweep_view<J, MULTI><<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
+    return cudaGetLastError();
+}
+template <int J, bool MULTI>
+static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const double *p_row, double *out, cudaStream_t s)
+{
+    size_t smem = smem_cta_bytes(J * 128) + smem_warp_bytes(J * 128, 1, MULTI);
+    cudaError_t e = cudaFuncSetAttribute(k_cond_probe<J, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_cond_probe<J, MULTI><<<1, 32, smem, s>>>(P, d, pos, p_row, out);
+    return cudaGetLastError();
+}
+
+#define DISPATCH_J(J_, MULTI_, CALL)                                         \
+    switch (J_) {                                                            \
+        case 1: CALL(1, MULTI_); break;   case 2: CALL(2, MULTI_); break;    \
+        case 3: CALL(3, MULTI_); break;   case 4: CALL(4, MULTI_); break;    \
+        case 6: CALL(6, MULTI_); break;   case 8: CALL(8, MULTI_); break;    \
+        case 12: CALL(12, MULTI_); break; case 16: CALL(16, MULTI_); break;  \
+        default: break;                                                      \
+    }
+
+static cudaError_t launch_sweep(mvtm_handle *h, const SweepParams &P, const LaunchCfg &lc)
+{
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL_SWEEP(J_, MU_) e = launch_sweep_t<J_, MU_>(P, lc, h->stream)
+    if (h->M > 1) { DISPATCH_J(h->J, true, CALL_SWEEP) } else { DISPATCH_J(h->J, false, CALL_SWEEP) }
+#undef CALL_SWEEP
+    return e;
+}
+
+// activation of inactive topics that received tokens during the sweep (U:263-270 at sweep granularity)
+static int activate_sampled_topics(mvtm_handle *h)
+{
+    if (h->inactive.empty()) return MVTM_OK;
+    const int K = h->K;
+    std::vector<std::vector<int>> nk((size_t)h->M, std::vector<int>((size_t)K));
+    for (int m = 0; m < h->M; m++) CK(h, cudaMemcpy(nk[m].data(), h->v[m].nk, (size_t)K * 4, cudaMemcpyDeviceToHost));
+    std::vector<int> keep;
+    for (int t : h->inactive) {
+        bool hit = false;
+        for (int m = 0; m < h->M; m++)
+            if (nk[m][t] > 0) { h->alpha[(size_t)m * (K + 1) + t] = h->alpha[(size_t)m * (K + 1) + K]; hit = true; }   // Q16
+        if (!hit) keep.push_back(t);
+    }
+    if (keep.size() != h->inactive.size()) { h->inactive.swap(keep); h->hyper_dirty = true; }
+    return MVTM_OK;
+}
+
+static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool sync_stats)
+{
+    if (int rc = require_views(h, "mvtm_sweep")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    if (int rc = upload_hyper(h)) return rc;
+    LaunchCfg lc;
+    if (int rc = choose_launch(h, lc)) return rc;
+    CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
+    CK(h, cudaEventRecord(h->ev[0], h->stream));
+    int launches = 0;
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
+        if (v.n_items > 0) {
+            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+            SweepParams P;
+            fill_params(h, m, iteration, update_global, P);
+            P.R = lc.R;
+            CK(h, launch_sweep(h, P, lc));
+            launches++;
+        }
+        CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
+    }
+    CK(h, cudaEventRecord(h->ev[1], h->stream));
+    if (sync_stats) {
+        unsigned long long st[4];
+        CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->stats.ms_total = ms;
+        for (int m = 0; m < h->M; m++) { CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m])); h->stats.ms_view[m] = ms; }
+        h->stats.kernel_launches = launches;
+        if (update_global) if (int rc = activate_sampled_topics(h)) return rc;
+    }
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_sweep(mvtm_handle *h, int32_t iteration, int32_t update_global)
+{
+    if (!h) return MVTM_ERR_ARG;
+    return sweep_impl(h, iteration, update_global, true);
+}
+
+extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (!z_inout) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: NULL z_inout");
+    if (int rc = require_views(h, "mvtm_sweep_host")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        if (v.n_tok > 0 && !z_inout[m]) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: NULL z for view %d", m);
+        if (v.n_tok > 0) CK(h, cudaMemcpyAsync(v.z, z_inout[m], (size_t)v.n_tok * 4, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = rebuild_counts_view(h, m)) return rc;
+    }
+    if (int rc = sweep_impl(h, iteration, 1, false)) return rc;
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        if (v.n_tok > 0) CK(h, cudaMemcpyAsync(z_inout[m], v.z, (size_t)v.n_tok * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    unsigned long long st[4];
+    CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->stats.ms_total = ms;
+    return activate_sampled_topics(h);
+}
+
+extern "C" int mvtm_stats(mvtm_handle *h, mvtm_sweep_stats *out)
+{
+    if (!h || !out) return MVTM_ERR_ARG;
+    *out = h->stats;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, double *probs_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_views(h, "mvtm_cond_probs")) return rc;
+    if (m < 0 || m >= h->M || doc < 0 || doc >= h->D || !probs_out) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: bad argument");
+    ViewDev &v = h->v[m];
+    long long len = v.h_doc_off[(size_t)doc + 1] - v.h_doc_off[(size_t)doc];
+    if (pos < 0 || pos >= len) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: position %d outside document of %lld tokens", pos, len);
+    CK(h, cudaSetDevice(h->device));
+    if (int rc = upload_hyper(h)) return rc;
+    int w = 0;
+    CK(h, cudaMemcpy(&w, v.word + v.h_doc_off[(size_t)doc] + pos, 4, cudaMemcpyDeviceToHost));
+    if (w < 0 || w >= v.V) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: token has out-of-vocabulary word id %d (W:427-428 skips it)", w);
+    double *d_out = nullptr, *d_p = nullptr;
+    CK(h, cudaMalloc(&d_out, (size_t)(h->K + 1) * 8));
+    std::vector<double> prow((size_t)h->M, 0.0);
+    if (p_row) prow.assign(p_row, p_row + h->M); else prow[(size_t)m] = 1.0;
+    CK(h, cudaMalloc(&d_p, (size_t)h->M * 8));
+    CK(h, cudaMemcpy(d_p, prow.data(), (size_t)h->M * 8, cudaMemcpyHostToDevice));
+    SweepParams P;
+    fill_params(h, m, 0, 0, P);
+    P.nk_frozen = v.nk;                                                  // frozen counts = the current ones
+    P.R = 1;
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL_PROBE(J_, MU_) e = launch_probe_t<J_, MU_>(P, (int)doc, pos, d_p, d_out, h->stream)
+    if (h->M > 1) { DISPATCH_J(h->J, true, CALL_PROBE) } else { DISPATCH_J(h->J, false, CALL_PROBE) }
+#undef CALL_PROBE
+    if (e == cudaSuccess) e = cudaMemcpyAsync(probs_out, d_out, (size_t)(h->K + 1) * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out); cudaFree(d_p);
+    CK(h, e);
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_doc_topic_hist(mvtm_handle *h, int32_t m, int32_t *hist_out, int32_t *max_len_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_doc_topic_hist: bad view %d", m);
+    ViewDev &v = h->v[m];
+    if (max_len_out) *max_len_out = v.max_len;
+    if (!hist_out) return MVTM_OK;
+    CK(h, cudaSetDevice(h->device));
+    const int stride = v.max_len + 1;
+    const size_t n = (size_t)h->K * stride;
+    int *d_hist = nullptr;
+    CK(h, cudaMalloc(&d_hist, n * 4));
+    cudaError_t e = cudaMemsetAsync(d_hist, 0, n * 4, h->stream);
+    if (e == cudaSuccess && v.n_tok > 0) {
+        const int warps = 4;
+        k_doc_topic_hist<<<h->num_sms * 4, warps * 32, (size_t)warps * h->K * 4, h->stream>>>(h->D, v.doc_off, v.z, h->K, stride, d_hist);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hist_out, d_hist, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_hist);
+    CK(h, e);
+    // bin 0 (M:647-649): documents of the view in which the topic is absent
+    for (int t = 0; t < h->K; t++) {
+        long long s = 0;
+        for (int cidx = 1; cidx < stride; cidx++) s += hist_out[(size_t)t * stride + cidx];
+        hist_out[(size_t)t * stride] = (int)(v.docs_present - s);
+    }
+    return MVTM_OK;
+}
+
+static double host_log_gamma_stirling(double z)
+{
+    int shift = 0;
+    while (z < 2.0) { z += 1.0; shift++; }
+    double r = 0.91893853320467274178 + (z - 0.5) * std::log(z) - z + 1.0 / (12.0 * z) - 1.0 / (360.0 * z * z * z) + 1.0 / (1260.0 * z * z * z * z * z);
+    while (shift-- > 0) { z -= 1.0; r -= std::log(z); }
+    return r;
+}
+
+extern "C" int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (!ll_out) FAIL(h, MVTM_ERR_ARG, "mvtm_loglik: NULL output");
+    if (int rc = require_views(h, "mvtm_loglik")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int K = h->K;
+    const long long D = h->D;
+    double *d_ga = nullptr, *d_tlg = nullptr, *d_doc = nullptr, *d_part = nullptr;
+    long long *d_nnz = nullptr; unsigned char *d_cnt = nullptr;
+    const int cell_blocks = h->num_sms * 8;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaMalloc(&d_ga, (size_t)K * 8)); step(cudaMalloc(&d_tlg, (size_t)K * 8));
+    step(cudaMalloc(&d_doc, (size_t)std::max<long long>(D, 1) * 8)); step(cudaMalloc(&d_cnt, (size_t)std::max<long long>(D, 1)));
+    step(cudaMalloc(&d_part, (size_t)cell_blocks * 8)); step(cudaMalloc(&d_nnz, (size_t)cell_blocks * 8));
+    std::vector<double> ga((size_t)K), tlg((size_t)K), doc_ll((size_t)D), part((size_t)cell_blocks);
+    std::vector<long long> nnzp((size_t)cell_blocks);
+    std::vector<unsigned char> counted((size_t)D);
+    std::vector<int> nk((size_t)K);
+    for (int m = 0; m < h->M && e == cudaSuccess; m++) {
+        ViewDev &v = h->v[m];
+        for (int t = 0; t < K; t++) { ga[t] = h->gamma[m] * h->alpha[(size_t)m * (K + 1) + t]; tlg[t] = host_log_gamma_stirling(ga[t]); }   // M:3343
+        const double gas = h->gamma[m] * h->alphaSum[m];
+        step(cudaMemcpyAsync(d_ga, ga.data(), (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+        step(cudaMemcpyAsync(d_tlg, tlg.data(), (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+        if (e == cudaSuccess && D > 0) {
+            const int warps = 4;
+            k_loglik_docs<<<h->num_sms * 4, warps * 32, (size_t)warps * K * 4, h->stream>>>(D, v.doc_off, v.z, v.present, K, d_ga, d_tlg, gas, quirk_len2, d_doc, d_cnt);
+            step(cudaGetLastError());
+        }
+        if (e == cudaSuccess) { k_loglik_cells<<<cell_blocks, 256, 0, h->stream>>>(v.V, K, h->Kp, v.nwk, h->beta[m], d_part, d_nnz); step(cudaGetLastError()); }
+        if (D > 0) { step(cudaMemcpyAsync(doc_ll.data(), d_doc, (size_t)D * 8, cudaMemcpyDeviceToHost, h->stream));
+                     step(cudaMemcpyAsync(counted.data(), d_cnt, (size_t)D, cudaMemcpyDeviceToHost, h->stream)); }
+        step(cudaMemcpyAsync(part.data(), d_part, (size_t)cell_blocks * 8, cudaMemcpyDeviceToHost, h->stream));
+        step(cudaMemcpyAsync(nnzp.data(), d_nnz, (size_t)cell_blocks * 8, cudaMemcpyDeviceToHost, h->stream));
+        step(cudaMemcpyAsync(nk.data(), v.nk, (size_t)K * 4, cudaMemcpyDeviceToHost, h->stream));
+        step(cudaStreamSynchronize(h->stream));
+        if (e != cudaSuccess) break;
+        double ll = 0.0; long long modalityCnt = 0;
+        for (long long d = 0; d < D; d++) { ll += doc_ll[(size_t)d]; modalityCnt += counted[(size_t)d]; }
+        ll += (double)modalityCnt * host_log_gamma_stirling(gas);                                 // M:3373
+        long long nnz = 0;
+        for (int bidx = 0; bidx < cell_blocks; bidx++) { ll += part[(size_t)bidx]; nnz += nnzp[(size_t)bidx]; }
+        const double bV = h->beta[m] * v.V;
+        for (int t = 0; t < K; t++) ll -= host_log_gamma_stirling(bV + nk[(size_t)t]);           // M:3417-3419
+        ll += host_log_gamma_stirling(bV) * K;                                                    // M:3438
+        ll -= host_log_gamma_stirling(h->beta[m]) * (double)nnz;                                  // M:3441
+        ll_out[m] = ll;
+    }
+    cudaFree(d_ga); cudaFree(d_tlg); cudaFree(d_doc); cudaFree(d_cnt); cudaFree(d_part); cudaFree(d_nnz);
+    CK(h, e);
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (!violations_out) FAIL(h, MVTM_ERR_ARG, "mvtm_check_invariants: NULL output");
+    if (int rc = require_views(h, "mvtm_check_invariants")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    unsigned long long *d_bad = nullptr;
+    CK(h, cudaMalloc(&d_bad, 8));
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, 8, h->stream);
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    for (int m = 0; m < h->M && e == cudaSuccess; m++) {
+        ViewDev &v = h->v[m];
+        const size_t n = (size_t)v.V * h->Kp;
+        int *s_nwk = nullptr, *s_nk = nullptr;
+        step(cudaMalloc(&s_nwk, n * 4)); step(cudaMalloc(&s_nk, (size_t)h->Kp * 4));
+        step(cudaMemsetAsync(s_nwk, 0, n * 4, h->stream)); step(cudaMemsetAsync(s_nk, 0, (size_t)h->Kp * 4, h->stream));
+        step(cudaMemsetAsync(h->d_bad, 0, 4, h->stream));
+        if (e == cudaSuccess && v.n_tok > 0) {
+            int blocks = (int)std::min<long long>((v.n_tok + 255) / 256, (long long)h->num_sms * 8);
+            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, s_nwk, s_nk, h->d_bad);
+            step(cudaGetLastError());
+        }
+        if (e == cudaSuccess) {
+            k_compare_counts<<<h->num_sms * 8, 256, 0, h->stream>>>((long long)n, v.nwk, s_nwk, d_bad);
+            k_compare_counts<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, s_nk, d_bad);
+            step(cudaGetLastError());
+        }
+        step(cudaStreamSynchronize(h->stream));
+        cudaFree(s_nwk); cudaFree(s_nk);
+    }
+    unsigned long long bad = 0; int badz = 0;
+    step(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
+    step(cudaMemcpy(&badz, h->d_bad, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    CK(h, e);
+    *violations_out = (int64_t)bad + badz;
+    return MVTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU delta plumbing: snapshot, export local delta in place, import reduced delta
+// ------------------------------------------------------------------------------------------------
+extern "C" int mvtm_delta_begin(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_views(h, "mvtm_delta_begin")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        const size_t n = (size_t)v.V * h->Kp;
+        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, n * 4)); CK(h, cudaMalloc(&v.snap_nk, (size_t)h->Kp * 4)); }
+        CK(h, cudaMemcpyAsync(v.snap_nwk, v.nwk, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(v.snap_nk, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_delta_reset(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_views(h, "mvtm_delta_reset")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        const size_t n = (size_t)v.V * h->Kp;
+        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, n * 4)); CK(h, cudaMalloc(&v.snap_nk, (size_t)h->Kp * 4)); }
+        CK(h, cudaMemsetAsync(v.snap_nwk, 0, n * 4, h->stream));
+        CK(h, cudaMemsetAsync(v.snap_nk, 0, (size_t)h->Kp * 4, h->stream));
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_delta_export: bad view %d", m);
+    ViewDev &v = h->v[m];
+    if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_export: call mvtm_delta_begin first");
+    CK(h, cudaSetDevice(h->device));
+    const long long n = (long long)v.V * h->Kp;
+    k_sub_inplace<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk);
+    k_sub_inplace<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (n_wk_dev) *n_wk_dev = v.nwk;
+    if (n_wk_elems) *n_wk_elems = n;
+    if (n_k_dev) *n_k_dev = v.nk;
+    if (n_k_elems) *n_k_elems = h->Kp;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_delta_import: bad view %d", m);
+    ViewDev &v = h->v[m];
+    if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_import: call mvtm_delta_begin first");
+    CK(h, cudaSetDevice(h->device));
+    const long long n = (long long)v.V * h->Kp;
+    k_add_snapshot<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk);
+    k_add_snapshot<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}

@@ -1,0 +1,621 @@
+// mvtm_kernels.cuh -- sm_100a kernels of the collapsed-Gibbs engine (no host code here).
+//
+// Reference tags as in include/mvtm.h (W = FastQMVWVWorkerRunnable, U = FastQMVWVUpdaterRunnable,
+// M = FastQMVWVParallelTopicModel, FT = FTree).
+//
+// Design (DESIGN.md has the long form):
+//  * one warp per document-view (north_star a); persistent CTAs, one per SM, pull work items from a
+//    longest-first list with an atomic counter;
+//  * the document's topic counts n_d (u16) and its per-topic factor q[t] live in shared memory (b);
+//    q[t] = (p_mm*n_d[t] + [t in S]*O_m[t] + gamma*alpha[t]) / (n_k[t] + betaSum), so that the weight of
+//    topic t for a token of word w is simply (n_wk[w][t] + beta) * q[t]  -- the net distribution of
+//    W:495-538 (doc bucket + tree bucket) evaluated densely;
+//  * n_wk rows are staged global -> shared by the TMA engine (cp.async.bulk 1-D, mbarrier complete_tx)
+//    through a per-warp ring that keeps `R` rows in flight, and consumed as 128-bit LDS (b);
+//  * the conditional is sampled by a warp-cooperative scan: per-lane partial sums, __shfl_up inclusive
+//    scan over lanes, __ballot to find the lane, register-resident chunk sums to find the element (c);
+//  * RNG is Philox4x32-10 keyed on (seed; token position, global doc id, iteration, view|purpose) (d);
+//  * count deltas: n_wk by global RED atomics issued by two lanes, n_k through a per-CTA shared-memory
+//    delta vector flushed once per kernel (e).  No tensor cores: nothing here is a contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MVTM_MAXM 8
+
+struct SweepParams {
+    int M, K, Kp, m, V;
+    int n_items;
+    const int *order;                 // work list: local doc ids, longest first
+    int *work_counter;
+    const long long *doc_off[MVTM_MAXM];
+    const int *word;                  // view m
+    int *zv[MVTM_MAXM];               // assignments of every view (view m is written)
+    int *nwk;                         // V x Kp
+    const int *nk_frozen;             // Kp, snapshot taken before the launch
+    int *nk_live;                     // Kp, receives the flushed deltas
+    const float *ga_tree;             // gamma_m*alpha_m[t], 0 for inactive topics (M:2670-2678)
+    const float *ga_full[MVTM_MAXM];  // gamma_i*alpha_i[t] unmasked (W:404)
+    float beta, betaSum;
+    float gas[MVTM_MAXM];             // gamma_i*alphaSum_i
+    float ga_new[MVTM_MAXM];          // gamma_i*alpha_i[K]
+    double pa[MVTM_MAXM], pb[MVTM_MAXM];   // p_a[m][i], p_b[m][i]
+    unsigned char sparse[MVTM_MAXM];  // beta[i] == 0.0001 (W:335-336)
+    int n_inactive, first_inactive;
+    unsigned seed_lo, seed_hi, iteration;
+    long long doc_id_base, doc_id_stride;
+    int update_global;
+    int R;                            // ring depth
+    unsigned long long *stats;        // [0] tokens, [1] changed, [2] new-topic draws
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+enum { PURPOSE_SAMPLE = 0, PURPOSE_INIT = 1, PURPOSE_PDRAW = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy + mbarrier helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init()
+{ asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async()
+{ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_row_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp context (pointers into shared memory + per-document scalars)
+// ------------------------------------------------------------------------------------------------
+struct WarpCtx {
+    float *q;              // KS
+    unsigned short *nd;    // KS
+    float *oc;             // KS   (MULTI) sum_i c_i * n_d[i][t]
+    unsigned *om;          // KS/32 (MULTI) bit t: some other view holds topic t
+    float *cpar;           // 8    (MULTI) c_i = p[m][i] / (len_i + gas_i), 0 if len_i == 0 or i == m
+    const float2 *ginv;    // KS   CTA-shared {ga_tree, 1/(n_k + betaSum)}
+    float pmm, coefm, C;   // p[m][m]; len_m + gas_m; new-topic mass per token (W:515)
+};
+
+template <bool MULTI>
+__device__ __forceinline__ float q_value(float ndv, bool inS, float ocv, float pri, float coefm, float pmm, float2 gi)
+{
+    float v = ndv * pmm;
+    if (MULTI) { if (inS) v += coefm * (ocv + pri); }
+    return (v + gi.x) * gi.y;
+}
+
+template <bool MULTI>
+__device__ __forceinline__ float prior_other(const SweepParams &P, const WarpCtx &c, int t)
+{
+    float pri = 0.f;
+    if (MULTI) {
+        for (int i = 0; i < P.M; i++) { float ci = c.cpar[i]; if (ci != 0.f) pri += ci * __ldg(P.ga_full[i] + t); }
+    }
+    return pri;
+}
+
+// recompute q[t] after n_d[t] changed (one lane)
+template <bool MULTI>
+__device__ __forceinline__ void update_q_entry(const SweepParams &P, WarpCtx &c, int t)
+{
+    float ndv = (float)c.nd[t];
+    bool inS = false; float ocv = 0.f, pri = 0.f;
+    if (MULTI) {
+        inS = (ndv > 0.f) || ((c.om[t >> 5] >> (t & 31)) & 1u);
+        if (inS) { ocv = c.oc[t]; pri = prior_other<MULTI>(P, c, t); }
+    }
+    c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, c.ginv[t]);
+}
+
+// the view-coupling draw p[m][i] of W:327-337 for document gdoc (all lanes compute the same value)
+__device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
+{
+    int m = P.m;
+    double r;
+    if (p_override) r = p_override[i];
+    else if (i == m) r = 1.0;
+    else if (P.pa[i] == 0.0) r = 0.0;
+    else {
+        int lo = m < i ? m : i, hi = m < i ? i : m;
+        uint4 x = philox4x32_10(0u, gdoc, P.iteration, ((uint32_t)(lo * P.M + hi) << 8) | PURPOSE_PDRAW, P.seed_lo, P.seed_hi);
+        double u = (double)(x.x >> 8) * (1.0 / 16777216.0);
+        double b = pow(u, 1.0 / P.pa[i]);                       // Beta(a,1) by inversion (Q5: true law)
+        r = floor(1000.0 * b + 0.5) / 1000.0;                   // W:333 Math.round(1000*x)/1000
+    }
+    if (!p_override && i != 0 && P.sparse[i]) r = 0.0;          // W:335-336 (column i zeroed, incl. the diagonal)
+    return (float)r;
+}
+
+// Build n_d, (MULTI: oc/om/cpar), q for document d of view P.m.  KS = J*128 slot elements.
+template <int J, bool MULTI>
+__device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int d, int lane, const double *p_override)
+{
+    constexpr int KS = J * 128;
+    const int m = P.m;
+    const long long b = P.doc_off[m][d];
+    const int len = (int)(P.doc_off[m][d + 1] - b);
+    uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
+
+    unsigned *nd32 = reinterpret_cast<unsigned *>(c.nd);
+#pragma unroll
+    for (int k = lane; k < KS / 2; k += 32) nd32[k] = 0u;
+    c.pmm = 1.f; c.coefm = (float)len + P.gas[m]; c.C = 0.f;
+    if (MULTI) {
+        c.pmm = draw_p(P, m, gdoc, p_override);
+#pragma unroll
+        for (int k = lane; k < KS; k += 32) c.oc[k] = 0.f;
+        if (lane < KS / 32) c.om[lane] = 0u;                     // KS/32 <= 64: two passes
+        if (lane + 32 < KS / 32) c.om[lane + 32] = 0u;
+        float cdoc = 0.f;
+        unsigned *tmp32 = reinterpret_cast<unsigned *>(c.q);      // q is built last: reuse it as u16 scratch
+        for (int i = 0; i < P.M; i++) {
+            const long long bi = P.doc_off[i][d];
+            const int leni = (int)(P.doc_off[i][d + 1] - bi);
+            float pmi = (i == m) ? c.pmm : draw_p(P, i, gdoc, p_override);
+            float denom = (float)leni + P.gas[i];
+            cdoc += pmi * P.ga_new[i] / denom;                    // W:414-416 (every view, no length test)
+            float ci = (i != m && leni != 0) ? pmi / denom : 0.f; // W:403-404
+            __syncwarp();
+            if (lane == 0) c.cpar[i] = ci;
+            if (i == m || leni == 0) continue;
+#pragma unroll
+            for (int k = lane; k < KS / 2; k += 32) tmp32[k] = 0u;
+            __syncwarp();
+            const int *zi = P.zv[i] + bi;
+            for (int k = lane; k < leni; k += 32) { int t = zi[k]; if (t >= 0) atomicAdd(&tmp32[t >> 1], 1u << ((t & 1) * 16)); }
+            __syncwarp();
+            const unsigned short *tmp16 = reinterpret_cast<const unsigned short *>(tmp32);
+#pragma unroll
+            for (int k = lane; k < KS; k += 32) {
+                unsigned cnt = tmp16[k];
+                if (cnt) { c.oc[k] += ci * (float)cnt; atomicOr(&c.om[k >> 5], 1u << (k & 31)); }
+            }
+            __syncwarp();
+        }
+        c.C = (P.n_inactive > 0) ? (cdoc * c.coefm) / (float)P.K : 0.f;   // W:418, W:515
+        __syncwarp();
+    } else {
+        // single view: p[0][0] = 1; C_doc = coefm * gamma*alpha[K] / (len + gas)  (W:413-418 with M = 1)
+        c.C = (P.n_inactive > 0) ? (P.ga_new[m] / ((float)len + P.gas[m]) * c.coefm) / (float)P.K : 0.f;
+        __syncwarp();
+    }
+    // own-view histogram (W:352-359)
+    {
+        const int *zm = P.zv[m] + b;
+        for (int k = lane; k < len; k += 32) { int t = zm[k]; if (t >= 0) atomicAdd(&nd32[t >> 1], 1u << ((t & 1) * 16)); }
+    }
+    __syncwarp();
+    // q for every topic, four per lane per step
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        const int cidx = lane + 32 * j, t0 = cidx * 4;
+        const uint2 n2 = reinterpret_cast<const uint2 *>(c.nd)[cidx];
+        const float4 g01 = reinterpret_cast<const float4 *>(c.ginv)[2 * cidx];
+        const float4 g23 = reinterpret_cast<const float4 *>(c.ginv)[2 * cidx + 1];
+        float ndv[4] = { (float)(n2.x & 0xffffu), (float)(n2.x >> 16), (float)(n2.y & 0xffffu), (float)(n2.y >> 16) };
+        float2 gi[4] = { make_float2(g01.x, g01.y), make_float2(g01.z, g01.w), make_float2(g23.x, g23.y), make_float2(g23.z, g23.w) };
+        float out[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            bool inS = false; float ocv = 0.f, pri = 0.f;
+            if (MULTI) {
+                int t = t0 + e;
+                inS = (ndv[e] > 0.f) || ((c.om[t >> 5] >> (t & 31)) & 1u);
+                if (inS && t < P.K) { ocv = c.oc[t]; pri = prior_other<MULTI>(P, c, t); }
+            }
+            out[e] = q_value<MULTI>(ndv[e], inS, ocv, pri, c.coefm, c.pmm, gi[e]);
+        }
+        reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(out[0], out[1], out[2], out[3]);
+    }
+    __syncwarp();
+}
+
+// per-lane weights of one row: s[j] = sum of the lane's 4 topics in chunk j, returns the lane total
+template <int J>
+__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, float beta, float (&s)[J])
+{
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        const int4 r = row4[lane + 32 * j];
+        const float4 qq = q4[lane + 32 * j];
+        float w0 = (__int2float_rn(r.x) + beta) * qq.x, w1 = (__int2float_rn(r.y) + beta) * qq.y;
+        float w2 = (__int2float_rn(r.z) + beta) * qq.z, w3 = (__int2float_rn(r.w) + beta) * qq.w;
+        s[j] = (w0 + w1) + (w2 + w3);
+        tot += s[j];
+    }
+    return tot;
+}
+
+// warp-cooperative selection: returns the topic whose cumulative weight (lane-major scan order) first exceeds
+// target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket.  total_out = sum of weights.
+template <int J>
+__device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, int lane, float beta, float u, float C,
+                                           float &total_out)
+{
+    float s[J];
+    const float lane_total = lane_weights<J>(row4, q4, lane, beta, s);
+    float incl = lane_total;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { float v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    total_out = total;
+    float target = u * (total + C);
+    if (C > 0.f) { if (target < C) return -1; target -= C; }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > target);
+    const unsigned pos = __ballot_sync(0xffffffffu, lane_total > 0.f);
+    const int L = hit ? (__ffs(hit) - 1) : (pos ? 31 - __clz(pos) : 0);
+    const float r = target - (incl - lane_total);
+    // chunk: first j whose running sum exceeds r, else the last positive chunk
+    int jsel = -1, jlast = 0; float base = 0.f, blast = 0.f, cum = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        float c2 = cum + s[j];
+        if (jsel < 0 && c2 > r) { jsel = j; base = cum; }
+        if (s[j] > 0.f) { jlast = j; blast = cum; }
+        cum = c2;
+    }
+    if (jsel < 0) { jsel = jlast; base = blast; }
+    const float r2 = r - base;
+    const int cidx = lane + 32 * jsel;
+    const int4 rr = row4[cidx];
+    const float4 qq = q4[cidx];
+    float w0 = (__int2float_rn(rr.x) + beta) * qq.x, w1 = (__int2float_rn(rr.y) + beta) * qq.y;
+    float w2 = (__int2float_rn(rr.z) + beta) * qq.z, w3 = (__int2float_rn(rr.w) + beta) * qq.w;
+    int e;
+    float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
+    if (w0 > r2) e = 0; else if (c1 > r2) e = 1; else if (c2 > r2) e = 2; else if (c3 > r2) e = 3;
+    else e = (w3 > 0.f) ? 3 : (w2 > 0.f) ? 2 : (w1 > 0.f) ? 1 : 0;
+    const int mine = 4 * cidx + e;
+    return __shfl_sync(0xffffffffu, mine, L);
+}
+
+// shared-memory carve-up -------------------------------------------------------------------------
+__host__ __device__ inline size_t smem_cta_bytes(int KS) { return (size_t)KS * 8 + (size_t)KS * 4; }
+__host__ __device__ inline size_t smem_warp_bytes(int KS, int R, bool multi)
+{
+    size_t b = (size_t)KS * 4 + (size_t)KS * 2;                   // q, nd
+    if (multi) b += (size_t)KS * 4 + 256 + 64;                    // oc, om (<= 64 words), cpar
+    b += (size_t)R * KS * 4 + 128;                                // ring + mbarriers
+    return (b + 127) & ~(size_t)127;
+}
+
+__device__ __forceinline__ void carve_warp(unsigned char *base, int KS, int R, bool multi, WarpCtx &c, int *&ring, unsigned long long *&mbar)
+{
+    unsigned char *p = base;
+    ring = reinterpret_cast<int *>(p); p += (size_t)R * KS * 4;
+    c.q = reinterpret_cast<float *>(p); p += (size_t)KS * 4;
+    if (multi) { c.oc = reinterpret_cast<float *>(p); p += (size_t)KS * 4; } else c.oc = nullptr;
+    c.nd = reinterpret_cast<unsigned short *>(p); p += (size_t)KS * 2;
+    if (multi) { c.om = reinterpret_cast<unsigned *>(p); p += 256; c.cpar = reinterpret_cast<float *>(p); p += 64; }
+    else { c.om = nullptr; c.cpar = nullptr; }
+    mbar = reinterpret_cast<unsigned long long *>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE sweep kernel: one launch = one view pass over all documents of the shard  (W:186-233, W:301-597, U:197-218)
+// ------------------------------------------------------------------------------------------------
+template <int J, bool MULTI>
+__global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
+{
+    constexpr int KS = J * 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int R = P.R;
+
+    float2 *ginv = reinterpret_cast<float2 *>(smem);
+    int *dnk = reinterpret_cast<int *>(smem + (size_t)KS * 8);
+    for (int t = threadIdx.x; t < KS; t += blockDim.x) {
+        float2 g = make_float2(0.f, 0.f);
+        if (t < P.K) { g.x = __ldg(P.ga_tree + t); g.y = 1.0f / ((float)__ldg(P.nk_frozen + t) + P.betaSum); }
+        ginv[t] = g;                                              // topics >= K get weight 0
+        dnk[t] = 0;
+    }
+    WarpCtx c; int *ring; unsigned long long *mbar;
+    carve_warp(smem + smem_cta_bytes(KS) + (size_t)warp * smem_warp_bytes(KS, R, MULTI), KS, R, MULTI, c, ring, mbar);
+    c.ginv = ginv;
+    if (lane == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
+    for (int k = lane; k < R * KS; k += 32) ring[k] = 0;
+    fence_proxy_async();
+    __syncthreads();
+
+    const uint32_t row_bytes = (uint32_t)P.Kp * 4u;
+    const uint32_t ring_u32 = smem_u32(ring), mbar_u32 = smem_u32(mbar);
+    unsigned phasebits = 0u;
+    unsigned long long n_tok = 0, n_changed = 0, n_new = 0;
+    const int m = P.m;
+    int *zmv = P.zv[m];
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(P.work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= P.n_items) break;
+        const int d = __ldg(P.order + item);
+        const long long b = P.doc_off[m][d];
+        const int len = (int)(P.doc_off[m][d + 1] - b);
+        const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
+
+        // first block of tokens; rows of the first R tokens go in flight before the per-document setup
+        int wcur = (lane < len) ? __ldg(P.word + b + lane) : 0;
+        int zcur = (lane < len) ? zmv[b + lane] : -1;
+        int wnext = (32 + lane < len) ? __ldg(P.word + b + 32 + lane) : 0;
+        {
+            const int npre = len < R ? len : R;
+            for (int i = 0; i < npre; i++) {
+                int w = __shfl_sync(0xffffffffu, wcur, i);
+                if ((unsigned)w >= (unsigned)P.V) w = 0;
+                if (lane == 0) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
+            }
+        }
+        warp_setup<J, MULTI>(P, c, d, lane, nullptr);
+
+        int slot = 0;
+        for (int base = 0; base < len; base += 32) {
+            const int nblk = (len - base) < 32 ? (len - base) : 32;
+            // one Philox call per lane covers the 32 tokens of the block
+            const uint4 rnd = philox4x32_10((uint32_t)(base + lane), gdoc, P.iteration, ((uint32_t)m << 8) | PURPOSE_SAMPLE, P.seed_lo, P.seed_hi);
+            const float umine = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+            int znew = zcur;
+            for (int i = 0; i < nblk; i++) {
+                const int w = __shfl_sync(0xffffffffu, wcur, i);
+                const int ot = __shfl_sync(0xffffffffu, zcur, i);
+                const float u = __shfl_sync(0xffffffffu, umine, i);
+                const bool valid = (unsigned)w < (unsigned)P.V;              // W:427-428
+                // word of the token R positions ahead (for the ring refill)
+                const int ia = i + R;
+                const int wa_c = __shfl_sync(0xffffffffu, wcur, ia & 31), wa_n = __shfl_sync(0xffffffffu, wnext, ia & 31);
+                int wa = ia < 32 ? wa_c : wa_n;
+                if (valid && ot >= 0 && lane == 0) { c.nd[ot] -= 1; update_q_entry<MULTI>(P, c, ot); }   // W:434-471
+                mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
+                phasebits ^= 1u << slot;
+                __syncwarp();
+                int nt = ot;
+                if (valid) {
+                    float total;
+                    nt = warp_select<J>(reinterpret_cast<const int4 *>(ring + (size_t)slot * KS), reinterpret_cast<const float4 *>(c.q),
+                                        lane, P.beta, u, c.C, total);
+                    if (nt < 0) { nt = P.first_inactive; n_new++; }          // W:522-526
+                }
+                __syncwarp();
+                // slot consumed: refill it with the row of token base+i+R
+                if (base + ia < len && lane == 0) {
+                    if ((unsigned)wa >= (unsigned)P.V) wa = 0;
+                    tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
+                }
+                if (valid) {
+                    if (lane == 0) { c.nd[nt] += 1; update_q_entry<MULTI>(P, c, nt); }   // W:557-560
+                    if (nt != ot && P.update_global) {                                    // U:197-218
+                        if (lane == 1) atomicAdd(P.nwk + (size_t)w * P.Kp + nt, 1);
+                        if (lane == 2 && ot >= 0) atomicAdd(P.nwk + (size_t)w * P.Kp + ot, -1);
+                        if (lane == 3) atomicAdd(dnk + nt, 1);
+                        if (lane == 4 && ot >= 0) atomicAdd(dnk + ot, -1);
+                    }
+                    n_changed += (nt != ot);
+                    n_tok++;
+                    if (lane == i) znew = nt;
+                }
+                __syncwarp();
+                slot = (slot + 1 == R) ? 0 : slot + 1;
+            }
+            if (lane < nblk) zmv[b + base + lane] = znew;
+            wcur = wnext;
+            zcur = (base + 32 + lane < len) ? zmv[b + base + 32 + lane] : -1;
+            wnext = (base + 64 + lane < len) ? __ldg(P.word + b + base + 64 + lane) : 0;
+        }
+    }
+    if (lane == 0) {
+        if (n_tok) atomicAdd(P.stats + 0, n_tok);
+        if (n_changed) atomicAdd(P.stats + 1, n_changed);
+        if (n_new) atomicAdd(P.stats + 2, n_new);
+    }
+    __syncthreads();
+    if (P.update_global)
+        for (int t = threadIdx.x; t < P.K; t += blockDim.x) { int v = dnk[t]; if (v) atomicAdd(P.nk_live + t, v); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// parity probe: conditional of one token on frozen counts, same device functions as the sweep
+// ------------------------------------------------------------------------------------------------
+template <int J, bool MULTI>
+__global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d, int pos, const double *p_row, double *out)
+{
+    constexpr int KS = J * 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    float2 *ginv = reinterpret_cast<float2 *>(smem);
+    for (int t = lane; t < KS; t += 32) {
+        float2 g = make_float2(0.f, 0.f);
+        if (t < P.K) { g.x = P.ga_tree[t]; g.y = 1.0f / ((float)P.nk_frozen[t] + P.betaSum); }
+        ginv[t] = g;
+    }
+    WarpCtx c; int *ring; unsigned long long *mbar;
+    carve_warp(smem + smem_cta_bytes(KS), KS, 1, MULTI, c, ring, mbar);
+    c.ginv = ginv;
+    __syncwarp();
+    warp_setup<J, MULTI>(P, c, d, lane, p_row);
+    const long long b = P.doc_off[P.m][d];
+    const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
+    if (ot >= 0 && lane == 0) { c.nd[ot] -= 1; update_q_entry<MULTI>(P, c, ot); }
+    for (int t = lane; t < KS; t += 32) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
+    __syncwarp();
+    float s[J];
+    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, P.beta, s);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lt += __shfl_xor_sync(0xffffffffu, lt, off);
+    const float total = lt + c.C;
+    for (int t = lane; t < P.K; t += 32) {
+        float wgt = ((float)ring[t] + P.beta) * c.q[t];
+        if (c.C > 0.f && t == P.first_inactive) wgt += c.C;
+        out[t] = (double)(wgt / total);
+    }
+    if (lane == 0) out[P.K] = (double)(c.C / total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialisation, counts, histogram, log-likelihood, invariants
+// ------------------------------------------------------------------------------------------------
+// random initialisation M:465-515 (previousModel == null): view 0 uniform over K, view m>0 uniform over the
+// document's view-0 draws (uniform over K when the document has no view-0 tokens).  One thread per token;
+// view 0 must be initialised first.
+__global__ void k_init_assign(int m, int K, long long n_docs, const long long *off_m, const long long *off_0, const int *z0, int *z,
+                              unsigned seed_lo, unsigned seed_hi, long long doc_id_base, long long doc_id_stride)
+{
+    // one warp per document keeps the doc id lookup trivial
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long d = wid; d < n_docs; d += nw) {
+        const long long b = off_m[d]; const int len = (int)(off_m[d + 1] - b);
+        const long long b0 = off_0[d]; const int len0 = (int)(off_0[d + 1] - b0);
+        const uint32_t gdoc = (uint32_t)(doc_id_base + d * doc_id_stride);
+        for (int i = lane; i < len; i += 32) {
+            uint4 x = philox4x32_10((uint32_t)i, gdoc, 0u, ((uint32_t)m << 8) | PURPOSE_INIT, seed_lo, seed_hi);
+            int t;
+            if (m == 0 || len0 == 0) t = (int)__umulhi(x.x, (uint32_t)K);
+            else t = z0[b0 + (long long)__umulhi(x.x, (uint32_t)len0)];
+            z[b + i] = t;
+        }
+    }
+}
+
+// buildInitialTypeTopicCounts M:600-652: n_wk / n_k from (word, z); n_k through a shared-memory histogram
+__global__ void k_build_counts(long long n_tok, const int *word, const int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad)
+{
+    extern __shared__ int hk[];
+    for (int t = threadIdx.x; t < K; t += blockDim.x) hk[t] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += (long long)gridDim.x * blockDim.x) {
+        int t = z[i], w = word[i];
+        if (t < 0) continue;                                      // UNASSIGNED_TOPIC, M:634
+        if (t >= K) { atomicAdd(bad, 1); continue; }
+        atomicAdd(hk + t, 1);
+        if ((unsigned)w < (unsigned)V) atomicAdd(nwk + (size_t)w * Kp + t, 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < K; t += blockDim.x) { int v = hk[t]; if (v) atomicAdd(nk + t, v); }
+}
+
+// topicDocCounts (U:220-232 / M:647-649) recomputed: one warp per document, bins c >= 1
+__global__ void k_doc_topic_hist(long long n_docs, const long long *off, const int *z, int K, int stride, int *hist)
+{
+    extern __shared__ int sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int *cnt = sm + (size_t)warp * K;
+    for (int t = lane; t < K; t += 32) cnt[t] = 0;
+    __syncwarp();
+    for (long long d = (long long)blockIdx.x * nwarp + warp; d < n_docs; d += (long long)gridDim.x * nwarp) {
+        const long long b = off[d]; const int len = (int)(off[d + 1] - b);
+        if (len == 0) continue;
+        for (int i = lane; i < len; i += 32) { int t = z[b + i]; if (t >= 0) atomicAdd(cnt + t, 1); }
+        __syncwarp();
+        for (int t = lane; t < K; t += 32) { int cv = cnt[t]; if (cv) { atomicAdd(hist + (size_t)t * stride + cv, 1); cnt[t] = 0; } }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ double log_gamma_stirling(double z)
+{   // cc.mallet.types.Dirichlet.logGammaStirling
+    int shift = 0;
+    while (z < 2.0) { z += 1.0; shift++; }
+    double r = 0.91893853320467274178 + (z - 0.5) * log(z) - z + 1.0 / (12.0 * z) - 1.0 / (360.0 * z * z * z) + 1.0 / (1260.0 * z * z * z * z * z);
+    while (shift-- > 0) { z -= 1.0; r -= log(z); }
+    return r;
+}
+
+// document part of modelLogLikelihood M:3341-3370: per-document term written to doc_ll[d] (0 for skipped docs),
+// counted[d] = 1 when the document contributed (modalityCnt, M:3366)
+__global__ void k_loglik_docs(long long n_docs, const long long *off, const int *z, const unsigned char *present, int K,
+                              const double *ga, const double *tlg, double gas, int quirk_len2, double *doc_ll, unsigned char *counted)
+{
+    extern __shared__ int sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int *cnt = sm + (size_t)warp * K;
+    for (int t = lane; t < K; t += 32) cnt[t] = 0;
+    __syncwarp();
+    for (long long d = (long long)blockIdx.x * nwarp + warp; d < n_docs; d += (long long)gridDim.x * nwarp) {
+        const long long b = off[d]; const int len = (int)(off[d + 1] - b);
+        const int arrlen = quirk_len2 ? (len < 2 ? 2 : len) : len;        // Q18
+        if (!present[d] || arrlen == 0) { if (lane == 0) { doc_ll[d] = 0.0; counted[d] = 0; } continue; }
+        for (int i = lane; i < len; i += 32) atomicAdd(cnt + z[b + i], 1);
+        if (lane == 0 && arrlen > len) atomicAdd(cnt + 0, arrlen - len);
+        __syncwarp();
+        double acc = 0.0;
+        for (int t = lane; t < K; t += 32) {
+            int cv = cnt[t];
+            if (cv > 0) { acc += log_gamma_stirling(ga[t] + (double)cv) - tlg[t]; cnt[t] = 0; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { doc_ll[d] = acc - log_gamma_stirling(gas + (double)arrlen); counted[d] = 1; }
+        __syncwarp();
+    }
+}
+
+// topic-word part M:3389-3415: per-block partial sums of lgamma(beta + n) over cells with n > 0 and their count
+__global__ void k_loglik_cells(int V, int K, int Kp, const int *nwk, double beta, double *part_sum, long long *part_nnz)
+{
+    __shared__ double ssum[32]; __shared__ long long snnz[32];
+    double acc = 0.0; long long nnz = 0;
+    const long long n = (long long)V * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)(i % Kp);
+        int cv = nwk[i];
+        if (t < K && cv > 0) { nnz++; acc += log_gamma_stirling(beta + (double)cv); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); nnz += __shfl_xor_sync(0xffffffffu, nnz, o); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ssum[warp] = acc; snnz[warp] = nnz; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0; long long c = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { a += ssum[k]; c += snnz[k]; }
+        part_sum[blockIdx.x] = a; part_nnz[blockIdx.x] = c;
+    }
+}
+
+// invariants: scratch holds a recount of n_wk; compare cell by cell, flag negatives
+__global__ void k_compare_counts(long long n, const int *a, const int *b, unsigned long long *bad)
+{
+    unsigned long long local = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        local += (a[i] != b[i]) || (a[i] < 0);
+    if (local) atomicAdd(bad, local);
+}
+
+// multi-GPU delta plumbing: elementwise a -= b / a += b, and snapshot advance
+__global__ void k_sub_inplace(long long n, int *a, const int *b)
+{ for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] -= b[i]; }
+__global__ void k_add_snapshot(long long n, int *a, int *snap)
+{   // a holds the reduced delta: a = snap + a, snap = a
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { int v = a[i] + snap[i]; a[i] = v; snap[i] = v; }
+}

@@ -1,0 +1,74 @@
+"""Multi-GPU host logic: documents sharded over ranks, n_wk / n_k replicated, one integer all-reduce of the
+per-sweep count deltas per view.  torch.distributed is plumbing only (NCCL on GPUs,
+gloo in the CPU tests); the delta arithmetic runs in the engine's own kernels (mvtm_delta_*).
+
+Protocol per view, bit-exact in int32:
+    delta_g = replica_g - snapshot          (mvtm_delta_export, in place)
+    delta   = all_reduce_sum(delta_g)       (NCCL over NVLink / NVSwitch)
+    replica = snapshot + delta; snapshot = replica   (mvtm_delta_import)
+so after the exchange every rank holds the same global counts, equal to the histogram of all ranks' assignments.
+"""
+import numpy as np
+
+
+def shard_doc_ids(num_docs, rank, world):
+    """Strided sharding: rank r owns global documents r, r+world, ... (all views of a document stay together).
+    Returns (doc_id_base, doc_id_stride, local_count) -- the engine keys its Philox stream on the global id."""
+    return rank, world, len(range(rank, num_docs, world))
+
+
+class _DevBuf:
+    """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+class EngineAdapter:
+    """delta_begin / delta_reset / delta_export(m) -> (n_wk tensor, n_k tensor) / delta_import(m) on a CUDA Engine."""
+
+    def __init__(self, engine, device):
+        import torch
+        self.e, self.dev, self.torch = engine, device, torch
+        self.M = engine.M
+
+    def delta_begin(self):
+        self.e.delta_begin()
+
+    def delta_reset(self):
+        self.e.delta_reset()
+
+    def delta_export(self, m):
+        (p1, n1), (p2, n2) = self.e.delta_export(m)
+        t = self.torch
+        return (t.as_tensor(_DevBuf(p1, n1), device=f"cuda:{self.dev}"), t.as_tensor(_DevBuf(p2, n2), device=f"cuda:{self.dev}"))
+
+    def delta_import(self, m):
+        self.torch.cuda.synchronize(self.dev)      # the all-reduce ran on torch's stream
+        self.e.delta_import(m)
+
+
+class CountExchange:
+    """Runs the delta protocol over a torch.distributed process group for any adapter with the four methods above."""
+
+    def __init__(self, adapter, group=None):
+        import torch.distributed as dist
+        self.a, self.dist, self.group = adapter, dist, group
+        self.bytes_per_exchange = 0
+
+    def begin(self):
+        self.a.delta_begin()
+
+    def reset(self):
+        self.a.delta_reset()
+
+    def exchange(self, views=None):
+        total = 0
+        for m in (range(self.a.M) if views is None else views):
+            nwk, nk = self.a.delta_export(m)
+            self.dist.all_reduce(nwk, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(nk, op=self.dist.ReduceOp.SUM, group=self.group)
+            total += (nwk.numel() + nk.numel()) * 4
+            self.a.delta_import(m)
+        self.bytes_per_exchange = total
+        return total

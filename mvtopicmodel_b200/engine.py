@@ -1,0 +1,164 @@
+"""Thin numpy-facing wrapper over the C ABI (one Engine = one mvtm_handle = one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MvtmConfig, MvtmSweepStats
+
+
+class MvtmError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"mvtm status {status}: {message}")
+        self.status = status
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, K, V, views, seed=1, device=0, flags=0, doc_id_base=0, doc_id_stride=1, present=None,
+                 warps_per_cta=0, ring_depth=0, max_ctas=0):
+        """views: list of (doc_off int64[D+1], word_id int32[N]) -- a doc-aligned CSR per view (MA:13-19)."""
+        self.L = _lib.lib()
+        self.K, self.M = int(K), len(views)
+        self.V = np.ascontiguousarray(V, dtype=np.int32)
+        assert len(self.V) == self.M
+        self.D = len(views[0][0]) - 1
+        cfg = MvtmConfig(self.K, self.M, self.D, self.V.ctypes.data_as(C.POINTER(C.c_int32)), int(seed), int(device),
+                         int(flags), int(doc_id_base), int(doc_id_stride), int(warps_per_cta), int(ring_depth), int(max_ctas))
+        h = C.c_void_p()
+        rc = self.L.mvtm_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise MvtmError(rc, self.L.mvtm_last_error(None).decode())
+        self.h = h
+        self.ntok = []
+        for m, (off, word) in enumerate(views):
+            off = np.ascontiguousarray(off, dtype=np.int64)
+            word = np.ascontiguousarray(word, dtype=np.int32)
+            if len(off) != self.D + 1:
+                raise ValueError("every view needs num_docs+1 offsets")
+            pr = None if present is None or present[m] is None else np.ascontiguousarray(present[m], dtype=np.uint8)
+            self._ck(self.L.mvtm_add_view(self.h, m, _ptr(off), _ptr(word), _ptr(pr)))
+            self.ntok.append(int(off[-1]))
+
+    def _ck(self, rc):
+        if rc:
+            raise MvtmError(rc, self.L.mvtm_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mvtm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- state ---------------------------------------------------------------------------------
+    def init_assignments(self):
+        self._ck(self.L.mvtm_init_assignments(self.h))
+
+    def set_assignments(self, m, z):
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        if len(z) != self.ntok[m]:
+            raise ValueError("assignment array length != tokens of the view")
+        self._ck(self.L.mvtm_set_assignments(self.h, m, _ptr(z)))
+
+    def get_assignments(self, m):
+        z = np.empty(self.ntok[m], dtype=np.int32)
+        self._ck(self.L.mvtm_get_assignments(self.h, m, _ptr(z)))
+        return z
+
+    def get_counts(self, m, want_nwk=True):
+        nwk = np.empty((int(self.V[m]), self.K), dtype=np.int32) if want_nwk else None
+        nk = np.empty(self.K, dtype=np.int32)
+        self._ck(self.L.mvtm_get_counts(self.h, m, _ptr(nwk), _ptr(nk)))
+        return nwk, nk
+
+    def set_hyper(self, alpha=None, alphaSum=None, beta=None, betaSum=None, gamma=None, p_a=None, p_b=None,
+                  inactive=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        alpha, alphaSum, beta, betaSum, gamma, p_a, p_b = map(f, (alpha, alphaSum, beta, betaSum, gamma, p_a, p_b))
+        if alpha is not None and alpha.size != self.M * (self.K + 1):
+            raise ValueError("alpha must be M x (K+1)")
+        if inactive is None:
+            ina, n = None, -1
+        else:
+            ina = np.ascontiguousarray(sorted(inactive), dtype=np.int32)
+            n = len(ina)
+        self._ck(self.L.mvtm_set_hyper(self.h, _ptr(alpha), _ptr(alphaSum), _ptr(beta), _ptr(betaSum), _ptr(gamma),
+                                       _ptr(p_a), _ptr(p_b), _ptr(ina), n))
+
+    def get_hyper(self):
+        alpha = np.empty((self.M, self.K + 1), dtype=np.float64)
+        asum = np.empty(self.M, dtype=np.float64)
+        ina = np.empty(self.K, dtype=np.int32)
+        n = C.c_int32()
+        self._ck(self.L.mvtm_get_hyper(self.h, _ptr(alpha), _ptr(asum), _ptr(ina), C.byref(n)))
+        return alpha, asum, ina[:n.value].copy()
+
+    # --- the hot path ----------------------------------------------------------------------------
+    def sweep(self, iteration, update_global=True):
+        self._ck(self.L.mvtm_sweep(self.h, int(iteration), int(bool(update_global))))
+
+    def sweep_host(self, iteration, z_arrays):
+        """z_arrays: one int32 numpy array per view, updated in place (host buffers in, host buffers out)."""
+        ptrs = (C.c_void_p * self.M)()
+        for m, z in enumerate(z_arrays):
+            assert z.dtype == np.int32 and z.flags["C_CONTIGUOUS"] and len(z) == self.ntok[m]
+            ptrs[m] = z.ctypes.data
+        self._ck(self.L.mvtm_sweep_host(self.h, int(iteration), ptrs))
+
+    def stats(self):
+        s = MvtmSweepStats()
+        self._ck(self.L.mvtm_stats(self.h, C.byref(s)))
+        return {"tokens": s.tokens, "changed": s.changed, "new_topic": s.new_topic, "ms_total": s.ms_total,
+                "ms_view": [s.ms_view[m] for m in range(self.M)], "kernel_launches": s.kernel_launches}
+
+    # --- readers -----------------------------------------------------------------------------------
+    def cond_probs(self, m, doc, pos, p_row=None):
+        out = np.empty(self.K + 1, dtype=np.float64)
+        pr = None if p_row is None else np.ascontiguousarray(p_row, dtype=np.float64)
+        self._ck(self.L.mvtm_cond_probs(self.h, int(m), int(doc), int(pos), _ptr(pr), _ptr(out)))
+        return out
+
+    def loglik(self, quirk_len2=False):
+        out = np.empty(self.M, dtype=np.float64)
+        self._ck(self.L.mvtm_loglik(self.h, _ptr(out), int(quirk_len2)))
+        return out
+
+    def doc_topic_hist(self, m):
+        ml = C.c_int32()
+        self._ck(self.L.mvtm_doc_topic_hist(self.h, m, None, C.byref(ml)))
+        hist = np.empty((self.K, ml.value + 1), dtype=np.int32)
+        self._ck(self.L.mvtm_doc_topic_hist(self.h, m, _ptr(hist), C.byref(ml)))
+        return hist
+
+    def check_invariants(self):
+        v = C.c_int64()
+        self._ck(self.L.mvtm_check_invariants(self.h, C.byref(v)))
+        return v.value
+
+    # --- multi-GPU plumbing ------------------------------------------------------------------------
+    def row_stride(self):
+        s = C.c_int32()
+        self._ck(self.L.mvtm_row_stride(self.h, C.byref(s)))
+        return s.value
+
+    def delta_begin(self):
+        self._ck(self.L.mvtm_delta_begin(self.h))
+
+    def delta_reset(self):
+        self._ck(self.L.mvtm_delta_reset(self.h))
+
+    def delta_export(self, m):
+        p1, n1, p2, n2 = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        self._ck(self.L.mvtm_delta_export(self.h, m, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
+        return (p1.value, n1.value), (p2.value, n2.value)
+
+    def delta_import(self, m):
+        self._ck(self.L.mvtm_delta_import(self.h, m))

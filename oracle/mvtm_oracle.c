@@ -38,6 +38,7 @@
 #define ORC_F_BETA_MALLET   8u   /* Q5: MALLET Randoms.nextBeta law instead of true Beta(a,1)=u^(1/a)    */
 #define ORC_F_ENGINE_MIRROR 16u  /* view-major order, dense single-scan sampler in the engine's order     */
 #define ORC_F_DOC_ORDER     32u  /* (engine mirror) plain document order, no length sort                 */
+#define ORC_F_FROZEN        64u  /* (engine mirror) global counts frozen: the inferencer's nut = 0 mode, I:211-256 */
 
 typedef struct {
     int M, K;
@@ -626,7 +627,7 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
         int new_t = orc_engine_select(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1);
         o->z[m][b + pos] = new_t;
         s->nd[m * K + new_t]++;
-        if (new_t != old_t) {   /* n_wk live, n_k deferred to the end of the view pass (engine semantics) */
+        if (new_t != old_t && !(flags & ORC_F_FROZEN)) {   /* n_wk live, n_k deferred to the end of the view pass (engine semantics) */
             int32_t *row = o->n_wk[m] + (size_t)w * K;
             if (old_t != ORC_UNASSIGNED) row[old_t]--;
             row[new_t]++;
@@ -681,10 +682,10 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
             for (int64_t d = 0; d < o->D; d++) order[d] = d;
             if (!(flags & ORC_F_DOC_ORDER)) qsort_r(order, (size_t)o->D, 8, cmp_len_desc, o->doc_off[m]);
             for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, flags, s, nk_frozen, cnt);
-            recount_nk_hist(o, m);
+            if (!(flags & ORC_F_FROZEN)) recount_nk_hist(o, m);
         }
         free(nk_frozen); free(order);
-        activate_sampled_topics(o);
+        if (!(flags & ORC_F_FROZEN)) activate_sampled_topics(o);
     } else {
         if ((flags & ORC_F_STALE_TREES) && !o->tree[0]) orc_rebuild_trees(o);
         emit_ctx ctx = { o, s, flags };

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmvtm_oracle.so")
 
-F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER = 1, 2, 4, 8, 16, 32
+F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER, F_FROZEN = 1, 2, 4, 8, 16, 32, 64
 
 
 def build(force=False):
