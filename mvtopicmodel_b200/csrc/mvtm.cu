@@ -387,7 +387,7 @@ static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
 {
     const int KS = h->J * 128;
     const bool multi = h->M > 1;
-    int R = h->cfg_ring > 0 ? h->cfg_ring : (KS >= 1024 ? 3 : 4);
+    int R = h->cfg_ring > 0 ? h->cfg_ring : 2;
     if (const char *e = getenv("MVTM_RING")) R = atoi(e);
     R = std::max(1, std::min(R, 16));
     const size_t budget = 227 * 1024 - 1024;
@@ -399,7 +399,7 @@ static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
         R--;
     }
     if (W < 1) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
-    W = std::min(W, 16);
+    W = std::min(W, (h->J <= 4 ? 768 : (h->J <= 8 ? 512 : 384)) / 32);
     if (h->cfg_warps > 0) W = std::min(W, h->cfg_warps);
     if (const char *e = getenv("MVTM_WARPS")) W = std::max(1, std::min(W, atoi(e)));
     int grid = h->num_sms;

@@ -91,6 +91,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
     } while (!ok);
 }
 
+// explicit .shared accesses through a 32-bit address held in a register (keeps ptxas from rematerialising the
+// dynamic-smem base with S2UR SR_CgaCtaId on every access of the CTA-level vectors)
+__device__ __forceinline__ float2 lds_f2(uint32_t a)
+{ float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void reds_add(uint32_t a, int v)
+{ asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // per-warp context (pointers into shared memory + per-document scalars)
 // ------------------------------------------------------------------------------------------------
@@ -101,6 +108,7 @@ struct WarpCtx {
     unsigned *om;          // KS/32 (MULTI) bit t: some other view holds topic t
     float *cpar;           // 8    (MULTI) c_i = p[m][i] / (len_i + gas_i), 0 if len_i == 0 or i == m
     const float2 *ginv;    // KS   CTA-shared {ga_tree, 1/(n_k + betaSum)}
+    uint32_t ginv_sa;      // the same vector as a .shared address
     float pmm, coefm, C;   // p[m][m]; len_m + gas_m; new-topic mass per token (W:515)
 };
 
@@ -122,17 +130,38 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const WarpCtx
     return pri;
 }
 
-// recompute q[t] after n_d[t] changed (one lane)
-template <bool MULTI>
-__device__ __forceinline__ void update_q_entry(const SweepParams &P, WarpCtx &c, int t)
+// n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over its 4-topic chunk).  Executed by the
+// lane that owns topic t in the scan layout (lane == (t >> 2) & 31), W:434-471 / W:557-584.
+template <int J, bool MULTI>
+__device__ __forceinline__ void apply_count_delta(const SweepParams &P, WarpCtx &c, int t, int dl, int lane, float (&bsq)[J])
 {
-    float ndv = (float)c.nd[t];
+    const unsigned ndv_i = (unsigned)((int)c.nd[t] + dl);
+    c.nd[t] = (unsigned short)ndv_i;
+    const float ndv = (float)ndv_i;
     bool inS = false; float ocv = 0.f, pri = 0.f;
     if (MULTI) {
-        inS = (ndv > 0.f) || ((c.om[t >> 5] >> (t & 31)) & 1u);
+        inS = (ndv_i > 0u) || ((c.om[t >> 5] >> (t & 31)) & 1u);
         if (inS) { ocv = c.oc[t]; pri = prior_other<MULTI>(P, c, t); }
     }
-    c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, c.ginv[t]);
+    c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
+    const int j = t >> 7;
+    const float4 qq = reinterpret_cast<const float4 *>(c.q)[lane + 32 * j];   // own store is visible in program order
+    const float v = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
+#pragma unroll
+    for (int jj = 0; jj < J; jj++) if (jj == j) bsq[jj] = v;
+}
+
+// one warp step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the
+// owners differ
+template <int J, bool MULTI>
+__device__ __forceinline__ void apply_pair(const SweepParams &P, WarpCtx &c, int tinc, int tdec, int lane, float (&bsq)[J])
+{
+    if (tinc == tdec) return;                                   // same topic: the two changes cancel
+    const int own_i = tinc >= 0 ? ((tinc >> 2) & 31) : -1, own_d = tdec >= 0 ? ((tdec >> 2) & 31) : -2;
+    int t = -1, dl = 0;
+    if (lane == own_i) { t = tinc; dl = 1; } else if (lane == own_d) { t = tdec; dl = -1; }
+    if (t >= 0) apply_count_delta<J, MULTI>(P, c, t, dl, lane, bsq);
+    if (own_i == own_d) { if (lane == own_d) apply_count_delta<J, MULTI>(P, c, tdec, -1, lane, bsq); }   // warp-uniform test
 }
 
 // the view-coupling draw p[m][i] of W:327-337 for document gdoc (all lanes compute the same value)
@@ -156,7 +185,7 @@ __device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gd
 
 // Build n_d, (MULTI: oc/om/cpar), q for document d of view P.m.  KS = J*128 slot elements.
 template <int J, bool MULTI>
-__device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int d, int lane, const double *p_override)
+__device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int d, int lane, const double *p_override, float (&bsq)[J])
 {
     constexpr int KS = J * 128;
     const int m = P.m;
@@ -234,40 +263,45 @@ __device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int
             out[e] = q_value<MULTI>(ndv[e], inS, ocv, pri, c.coefm, c.pmm, gi[e]);
         }
         reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(out[0], out[1], out[2], out[3]);
+        bsq[j] = P.beta * ((out[0] + out[1]) + (out[2] + out[3]));
     }
     __syncwarp();
 }
 
-// per-lane weights of one row: s[j] = sum of the lane's 4 topics in chunk j, returns the lane total
+// weight of one topic: (n + beta) * q evaluated as n*q + beta*q
+__device__ __forceinline__ float topic_weight(int n, float q, float beta) { return fmaf(__int2float_rn(n), q, beta * q); }
+
+// per-lane weights of one row: s[j] = sum over the lane's 4 topics of chunk j of (n + beta) * q, evaluated as
+// beta*sum(q) (kept in registers, bsq) + sum n*q; returns the lane total
 template <int J>
-__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, float beta, float (&s)[J])
+__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, const float (&bsq)[J], float (&s)[J])
 {
     float tot = 0.f;
 #pragma unroll
     for (int j = 0; j < J; j++) {
         const int4 r = row4[lane + 32 * j];
         const float4 qq = q4[lane + 32 * j];
-        float w0 = (__int2float_rn(r.x) + beta) * qq.x, w1 = (__int2float_rn(r.y) + beta) * qq.y;
-        float w2 = (__int2float_rn(r.z) + beta) * qq.z, w3 = (__int2float_rn(r.w) + beta) * qq.w;
-        s[j] = (w0 + w1) + (w2 + w3);
-        tot += s[j];
+        float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
+        a = fmaf(__int2float_rn(r.y), qq.y, a);
+        a = fmaf(__int2float_rn(r.z), qq.z, a);
+        a = fmaf(__int2float_rn(r.w), qq.w, a);
+        s[j] = a;
+        tot += a;
     }
     return tot;
 }
 
 // warp-cooperative selection: returns the topic whose cumulative weight (lane-major scan order) first exceeds
-// target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket.  total_out = sum of weights.
+// target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket.
 template <int J>
-__device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, int lane, float beta, float u, float C,
-                                           float &total_out)
+__device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, int lane, float beta, const float (&bsq)[J], float u, float C)
 {
     float s[J];
-    const float lane_total = lane_weights<J>(row4, q4, lane, beta, s);
+    const float lane_total = lane_weights<J>(row4, q4, lane, bsq, s);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { float v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
     const float total = __shfl_sync(0xffffffffu, incl, 31);
-    total_out = total;
     float target = u * (total + C);
     if (C > 0.f) { if (target < C) return -1; target -= C; }
     const unsigned hit = __ballot_sync(0xffffffffu, incl > target);
@@ -288,10 +322,10 @@ __device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, i
     const int cidx = lane + 32 * jsel;
     const int4 rr = row4[cidx];
     const float4 qq = q4[cidx];
-    float w0 = (__int2float_rn(rr.x) + beta) * qq.x, w1 = (__int2float_rn(rr.y) + beta) * qq.y;
-    float w2 = (__int2float_rn(rr.z) + beta) * qq.z, w3 = (__int2float_rn(rr.w) + beta) * qq.w;
+    const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
+    const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
     int e;
-    float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
+    const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
     if (w0 > r2) e = 0; else if (c1 > r2) e = 1; else if (c2 > r2) e = 2; else if (c3 > r2) e = 3;
     else e = (w3 > 0.f) ? 3 : (w2 > 0.f) ? 2 : (w1 > 0.f) ? 1 : 0;
     const int mine = 4 * cidx + e;
@@ -323,12 +357,14 @@ __device__ __forceinline__ void carve_warp(unsigned char *base, int KS, int R, b
 // ------------------------------------------------------------------------------------------------
 // THE sweep kernel: one launch = one view pass over all documents of the shard  (W:186-233, W:301-597, U:197-218)
 // ------------------------------------------------------------------------------------------------
+constexpr int sweep_max_threads(int J) { return J <= 4 ? 768 : (J <= 8 ? 512 : 384); }
+
 template <int J, bool MULTI>
-__global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
+__global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const SweepParams P)
 {
     constexpr int KS = J * 128;
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int R = P.R;
 
     float2 *ginv = reinterpret_cast<float2 *>(smem);
@@ -342,6 +378,10 @@ __global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
     WarpCtx c; int *ring; unsigned long long *mbar;
     carve_warp(smem + smem_cta_bytes(KS) + (size_t)warp * smem_warp_bytes(KS, R, MULTI), KS, R, MULTI, c, ring, mbar);
     c.ginv = ginv;
+    uint32_t cta_sa = smem_u32(smem);
+    asm volatile("" : "+r"(cta_sa));                              // opaque: hold the base in a register
+    c.ginv_sa = cta_sa;
+    const uint32_t dnk_sa = cta_sa + (uint32_t)KS * 8u;
     if (lane == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
     for (int k = lane; k < R * KS; k += 32) ring[k] = 0;
     fence_proxy_async();
@@ -353,6 +393,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
     unsigned long long n_tok = 0, n_changed = 0, n_new = 0;
     const int m = P.m;
     int *zmv = P.zv[m];
+    float bsq[J];
 
     for (;;) {
         int item = 0;
@@ -376,7 +417,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
                 if (lane == 0) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
             }
         }
-        warp_setup<J, MULTI>(P, c, d, lane, nullptr);
+        warp_setup<J, MULTI>(P, c, d, lane, nullptr, bsq);
 
         int slot = 0;
         for (int base = 0; base < len; base += 32) {
@@ -384,25 +425,32 @@ __global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
             // one Philox call per lane covers the 32 tokens of the block
             const uint4 rnd = philox4x32_10((uint32_t)(base + lane), gdoc, P.iteration, ((uint32_t)m << 8) | PURPOSE_SAMPLE, P.seed_lo, P.seed_hi);
             const float umine = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+            // zeff: topic (>= 0), -1 = UNASSIGNED_TOPIC, -2 = out-of-vocabulary word: the token is skipped and neither
+            // leaves nor joins n_d (W:427-428)
+            const int zeff = ((unsigned)wcur < (unsigned)P.V) ? zcur : -2;
             int znew = zcur;
+            {   // the first token of the block leaves its topic (W:434-471); later tokens do so paired with the
+                // previous token's increment
+                const int ot0 = __shfl_sync(0xffffffffu, zeff, 0);
+                apply_pair<J, MULTI>(P, c, -1, ot0 >= 0 ? ot0 : -1, lane, bsq);
+                __syncwarp();
+            }
             for (int i = 0; i < nblk; i++) {
                 const int w = __shfl_sync(0xffffffffu, wcur, i);
-                const int ot = __shfl_sync(0xffffffffu, zcur, i);
+                const int ot = __shfl_sync(0xffffffffu, zeff, i);
                 const float u = __shfl_sync(0xffffffffu, umine, i);
-                const bool valid = (unsigned)w < (unsigned)P.V;              // W:427-428
+                const int otn = __shfl_sync(0xffffffffu, zeff, (i + 1) & 31);
+                const bool valid = (ot != -2);
                 // word of the token R positions ahead (for the ring refill)
                 const int ia = i + R;
                 const int wa_c = __shfl_sync(0xffffffffu, wcur, ia & 31), wa_n = __shfl_sync(0xffffffffu, wnext, ia & 31);
                 int wa = ia < 32 ? wa_c : wa_n;
-                if (valid && ot >= 0 && lane == 0) { c.nd[ot] -= 1; update_q_entry<MULTI>(P, c, ot); }   // W:434-471
                 mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
                 phasebits ^= 1u << slot;
-                __syncwarp();
                 int nt = ot;
                 if (valid) {
-                    float total;
                     nt = warp_select<J>(reinterpret_cast<const int4 *>(ring + (size_t)slot * KS), reinterpret_cast<const float4 *>(c.q),
-                                        lane, P.beta, u, c.C, total);
+                                        lane, P.beta, bsq, u, c.C);
                     if (nt < 0) { nt = P.first_inactive; n_new++; }          // W:522-526
                 }
                 __syncwarp();
@@ -411,13 +459,15 @@ __global__ void __launch_bounds__(512, 1) k_sweep_view(const SweepParams P)
                     if ((unsigned)wa >= (unsigned)P.V) wa = 0;
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
+                // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
+                apply_pair<J, MULTI>(P, c, valid ? nt : -1, (i + 1 < nblk && otn >= 0) ? otn : -1, lane, bsq);
                 if (valid) {
-                    if (lane == 0) { c.nd[nt] += 1; update_q_entry<MULTI>(P, c, nt); }   // W:557-560
-                    if (nt != ot && P.update_global) {                                    // U:197-218
-                        if (lane == 1) atomicAdd(P.nwk + (size_t)w * P.Kp + nt, 1);
-                        if (lane == 2 && ot >= 0) atomicAdd(P.nwk + (size_t)w * P.Kp + ot, -1);
-                        if (lane == 3) atomicAdd(dnk + nt, 1);
-                        if (lane == 4 && ot >= 0) atomicAdd(dnk + ot, -1);
+                    if (nt != ot && P.update_global) {                       // U:197-218
+                        const int tsel = (lane & 1) ? ot : nt, v = (lane & 1) ? -1 : 1;
+                        if (tsel >= 0) {
+                            if (lane < 2) atomicAdd(P.nwk + (size_t)w * P.Kp + tsel, v);
+                            else if (lane < 4) reds_add(dnk_sa + 4u * (uint32_t)tsel, v);
+                        }
                     }
                     n_changed += (nt != ot);
                     n_tok++;
@@ -460,20 +510,22 @@ __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d
     WarpCtx c; int *ring; unsigned long long *mbar;
     carve_warp(smem + smem_cta_bytes(KS), KS, 1, MULTI, c, ring, mbar);
     c.ginv = ginv;
+    c.ginv_sa = smem_u32(smem);
     __syncwarp();
-    warp_setup<J, MULTI>(P, c, d, lane, p_row);
+    float bsq[J];
+    warp_setup<J, MULTI>(P, c, d, lane, p_row, bsq);
     const long long b = P.doc_off[P.m][d];
     const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
-    if (ot >= 0 && lane == 0) { c.nd[ot] -= 1; update_q_entry<MULTI>(P, c, ot); }
+    apply_pair<J, MULTI>(P, c, -1, ot, lane, bsq);
     for (int t = lane; t < KS; t += 32) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
     __syncwarp();
     float s[J];
-    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, P.beta, s);
+    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, bsq, s);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) lt += __shfl_xor_sync(0xffffffffu, lt, off);
     const float total = lt + c.C;
     for (int t = lane; t < P.K; t += 32) {
-        float wgt = ((float)ring[t] + P.beta) * c.q[t];
+        float wgt = topic_weight(ring[t], c.q[t], P.beta);
         if (c.C > 0.f && t == P.first_inactive) wgt += c.C;
         out[t] = (double)(wgt / total);
     }
