@@ -271,10 +271,11 @@ __device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int
 // weight of one topic: (n + beta) * q evaluated as n*q + beta*q
 __device__ __forceinline__ float topic_weight(int n, float q, float beta) { return fmaf(__int2float_rn(n), q, beta * q); }
 
-// per-lane weights of one row: s[j] = sum over the lane's 4 topics of chunk j of (n + beta) * q, evaluated as
-// beta*sum(q) (kept in registers, bsq) + sum n*q; returns the lane total
+// per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, chunk j holding the lane's 4 topics
+// 4*(lane+32j)..+3, each weighted (n + beta) * q and evaluated as beta*sum(q) (registers, bsq) + sum n*q.
+// Returns the lane total (= cum[J-1]).
 template <int J>
-__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, const float (&bsq)[J], float (&s)[J])
+__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, const float (&bsq)[J], float (&cum)[J])
 {
     float tot = 0.f;
 #pragma unroll
@@ -285,19 +286,22 @@ __device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4
         a = fmaf(__int2float_rn(r.y), qq.y, a);
         a = fmaf(__int2float_rn(r.z), qq.z, a);
         a = fmaf(__int2float_rn(r.w), qq.w, a);
-        s[j] = a;
         tot += a;
+        cum[j] = tot;
     }
     return tot;
 }
+
+// largest float below a positive x (x > 0)
+__device__ __forceinline__ float next_below(float x) { return __int_as_float(__float_as_int(x) - 1); }
 
 // warp-cooperative selection: returns the topic whose cumulative weight (lane-major scan order) first exceeds
 // target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket.
 template <int J>
 __device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, int lane, float beta, const float (&bsq)[J], float u, float C)
 {
-    float s[J];
-    const float lane_total = lane_weights<J>(row4, q4, lane, bsq, s);
+    float cum[J];
+    const float lane_total = lane_weights<J>(row4, q4, lane, bsq, cum);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) { float v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
@@ -306,28 +310,21 @@ __device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, i
     if (C > 0.f) { if (target < C) return -1; target -= C; }
     const unsigned hit = __ballot_sync(0xffffffffu, incl > target);
     const unsigned pos = __ballot_sync(0xffffffffu, lane_total > 0.f);
-    const int L = hit ? (__ffs(hit) - 1) : (pos ? 31 - __clz(pos) : 0);
-    const float r = target - (incl - lane_total);
-    // chunk: first j whose running sum exceeds r, else the last positive chunk
-    int jsel = -1, jlast = 0; float base = 0.f, blast = 0.f, cum = 0.f;
+    const int L = hit ? (__ffs(hit) - 1) : (31 - __clz(pos));           // some lane is positive: every topic < K is
+    // residual inside the lane, clamped strictly below the lane total so that the chunk found has positive weight
+    float r = fminf(target - (incl - lane_total), next_below(lane_total));
+    // chunk: number of running sums <= r (the last one cannot be, by the clamp)
+    int jsel = 0; float base = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; j++) {
-        float c2 = cum + s[j];
-        if (jsel < 0 && c2 > r) { jsel = j; base = cum; }
-        if (s[j] > 0.f) { jlast = j; blast = cum; }
-        cum = c2;
-    }
-    if (jsel < 0) { jsel = jlast; base = blast; }
-    const float r2 = r - base;
+    for (int j = 0; j < J - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
     const int cidx = lane + 32 * jsel;
     const int4 rr = row4[cidx];
     const float4 qq = q4[cidx];
     const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
     const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
-    int e;
     const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
-    if (w0 > r2) e = 0; else if (c1 > r2) e = 1; else if (c2 > r2) e = 2; else if (c3 > r2) e = 3;
-    else e = (w3 > 0.f) ? 3 : (w2 > 0.f) ? 2 : (w1 > 0.f) ? 1 : 0;
+    const float r2 = fminf(r - base, next_below(c3));                 // same clamp one level down
+    const int e = (r2 >= w0 ? 1 : 0) + (r2 >= c1 ? 1 : 0) + (r2 >= c2 ? 1 : 0);
     const int mine = 4 * cidx + e;
     return __shfl_sync(0xffffffffu, mine, L);
 }
@@ -409,6 +406,7 @@ __global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const Sw
         int wcur = (lane < len) ? __ldg(P.word + b + lane) : 0;
         int zcur = (lane < len) ? zmv[b + lane] : -1;
         int wnext = (32 + lane < len) ? __ldg(P.word + b + 32 + lane) : 0;
+        int wahead = (R + lane < len) ? __ldg(P.word + b + R + lane) : 0;        // word of the token R positions ahead
         {
             const int npre = len < R ? len : R;
             for (int i = 0; i < npre; i++) {
@@ -441,10 +439,8 @@ __global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const Sw
                 const float u = __shfl_sync(0xffffffffu, umine, i);
                 const int otn = __shfl_sync(0xffffffffu, zeff, (i + 1) & 31);
                 const bool valid = (ot != -2);
-                // word of the token R positions ahead (for the ring refill)
                 const int ia = i + R;
-                const int wa_c = __shfl_sync(0xffffffffu, wcur, ia & 31), wa_n = __shfl_sync(0xffffffffu, wnext, ia & 31);
-                int wa = ia < 32 ? wa_c : wa_n;
+                int wa = __shfl_sync(0xffffffffu, wahead, i);             // word of token base+i+R (ring refill)
                 mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
                 phasebits ^= 1u << slot;
                 int nt = ot;
@@ -478,6 +474,7 @@ __global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const Sw
             }
             if (lane < nblk) zmv[b + base + lane] = znew;
             wcur = wnext;
+            wahead = (base + 32 + R + lane < len) ? __ldg(P.word + b + base + 32 + R + lane) : 0;
             zcur = (base + 32 + lane < len) ? zmv[b + base + 32 + lane] : -1;
             wnext = (base + 64 + lane < len) ? __ldg(P.word + b + base + 64 + lane) : 0;
         }
@@ -519,8 +516,8 @@ __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d
     apply_pair<J, MULTI>(P, c, -1, ot, lane, bsq);
     for (int t = lane; t < KS; t += 32) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
     __syncwarp();
-    float s[J];
-    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, bsq, s);
+    float cum[J];
+    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, bsq, cum);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) lt += __shfl_xor_sync(0xffffffffu, lt, off);
     const float total = lt + c.C;
