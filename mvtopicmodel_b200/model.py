@@ -1,0 +1,166 @@
+"""Host-side mirror of the reference's trainer class for the sampling path.
+
+`FastQMVWVParallelTopicModel` keeps the method names, argument meaning and the iteration schedule of
+org.madgik.MVTopicModel.FastQMVWVParallelTopicModel (M) for the calls on the hot path -- constructor M:183-247,
+setters M:273-335, addInstances M:396-533, estimate M:1033-1356, modelLogLikelihood M:3322-3452 -- and routes
+them to the C ABI (include/mvtm.h).  Everything outside the path (hyper-parameter optimisers, DB output,
+diagnostics, embeddings) is out of scope and raises NotImplementedError instead of
+silently doing something else.
+"""
+import numpy as np
+
+from .engine import Engine
+
+
+class Instance:
+    """Stand-in for a MALLET Instance whose data is a FeatureSequence: a name (entity id) + word ids."""
+    __slots__ = ("name", "features")
+
+    def __init__(self, name, features):
+        self.name = str(name)
+        self.features = np.asarray(features, dtype=np.int32)
+
+
+class InstanceList(list):
+    """Stand-in for a MALLET InstanceList of one view: a list of Instance + the size of its data alphabet."""
+
+    def __init__(self, instances=(), alphabet_size=None):
+        super().__init__(instances)
+        self._alphabet_size = alphabet_size
+
+    def alphabet_size(self):
+        if self._alphabet_size is not None:
+            return int(self._alphabet_size)
+        return int(max((int(i.features.max()) for i in self if len(i.features)), default=-1) + 1)
+
+
+class FastQMVWVParallelTopicModel:
+    UNASSIGNED_TOPIC = -1
+
+    def __init__(self, numTopics, numModalities, alpha=0.1, beta=0.01, useCycleProposals=False, SQLConnectionString="",
+                 useTypeVectors=False, vectorsLambda=0.0, trainTypeVectors=False):
+        if useTypeVectors or trainTypeVectors or vectorsLambda:
+            raise NotImplementedError("word-embedding mixing (W:504-507) is outside the accelerated path; keep vectorsLambda = 0")
+        if useCycleProposals:
+            raise NotImplementedError("cycle proposals are commented out in the reference (W:614-858)")
+        self.numTopics, self.numModalities = int(numTopics), int(numModalities)
+        K, M = self.numTopics, self.numModalities
+        # M:195-239
+        self.alpha = np.full((M, K + 1), float(alpha))
+        self.alphaSum = np.full(M, float(alpha) * K)
+        self.beta = np.full(M, float(beta))
+        self.betaSum = np.zeros(M)
+        self.gamma = np.ones(M)
+        self.p_a = np.full((M, M), 0.2)
+        self.p_b = np.ones((M, M))
+        self.numIterations, self.burninPeriod, self.optimizeInterval = 1000, 200, 50      # M:111-126
+        self.showTopicsInterval, self.wordsPerTopic = 50, 7
+        self.randomSeed, self.numThreads = -1, 1
+        self.perplexities = np.zeros((M, 200))                                                  # M:234 (Q10)
+        self.data = []            # entity ids in document order (M:67)
+        self.numTypes = [0] * M
+        self.totalTokens = [0] * M
+        self.engine = None
+        self.device = 0
+        self.iterationsSoFar = 0
+        self.sweep_ms = []
+
+    # ---- setters, M:273-335 ------------------------------------------------------------------------
+    def setNumIterations(self, n): self.numIterations = int(n)
+    def setBurninPeriod(self, n): self.burninPeriod = int(n)
+    def setTopicDisplay(self, interval, n): self.showTopicsInterval, self.wordsPerTopic = int(interval), int(n)
+    def setRandomSeed(self, seed): self.randomSeed = int(seed)
+    def setOptimizeInterval(self, interval): self.optimizeInterval = int(interval)
+    def setNumThreads(self, threads): self.numThreads = int(threads)   # kept for API parity; the GPU bounds asynchrony itself
+    def setSymmetricAlpha(self, b): pass
+    def setSaveState(self, interval, filename): raise NotImplementedError("state files are out of scope (SURVEY 8f rank 3)")
+    def setSaveSerializedModel(self, interval, filename): raise NotImplementedError("Java serialisation is out of scope")
+
+    # ---- addInstances, M:396-533 ---------------------------------------------------------------------
+    def addInstances(self, training, batchId="", vectorSize=0, previousModel=None):
+        if previousModel is not None:
+            raise NotImplementedError("warm start from a previous model's trees (M:488-496) is not on the accelerated path")
+        M, K = self.numModalities, self.numTopics
+        if len(training) != M:
+            raise ValueError("one InstanceList per modality is required")
+        entityPosition, docs = {}, []           # M:398, M:437-455: view 0 always appends, views m > 0 join by name
+        for m in range(M):
+            self.numTypes[m] = training[m].alphabet_size()
+            self.betaSum[m] = self.beta[m] * self.numTypes[m]                                   # M:420
+            for inst in training[m]:
+                if m != 0 and inst.name in entityPosition:
+                    docs[entityPosition[inst.name]][m] = inst.features
+                else:
+                    row = [None] * M
+                    row[m] = inst.features
+                    docs.append(row)
+                    entityPosition[inst.name] = len(docs) - 1
+                    self.data.append(inst.name)
+        D = len(docs)
+        views, present = [], []
+        for m in range(M):
+            lens = np.array([0 if r[m] is None else len(r[m]) for r in docs], dtype=np.int64)
+            off = np.zeros(D + 1, dtype=np.int64)
+            np.cumsum(lens, out=off[1:])
+            words = np.concatenate([r[m] for r in docs if r[m] is not None and len(r[m])]) if off[-1] else np.zeros(0, np.int32)
+            views.append((off, words.astype(np.int32)))
+            present.append(np.array([r[m] is not None for r in docs], dtype=np.uint8))
+            self.totalTokens[m] = int(off[-1])
+        seed = self.randomSeed if self.randomSeed != -1 else int(np.random.SeedSequence().entropy % (1 << 63))
+        self.engine = Engine(K, [max(1, v) for v in self.numTypes], views, seed=seed, device=self.device, present=present)
+        self._push_hyper()
+        self.engine.init_assignments()          # M:465-515 + buildInitialTypeTopicCounts M:600-652
+
+    def _push_hyper(self):
+        self.engine.set_hyper(alpha=self.alpha, alphaSum=self.alphaSum, beta=self.beta, betaSum=self.betaSum, gamma=self.gamma,
+                              p_a=self.p_a, p_b=self.p_b)
+
+    # ---- estimate, M:1033-1356 -------------------------------------------------------------------------
+    def estimate(self):
+        if self.engine is None:
+            raise RuntimeError("addInstances must be called before estimate")
+        self.p_a[:] = 0.2; self.p_b[:] = 1.0                                                        # M:1055-1058
+        for iteration in range(1, self.numIterations + 1):                                          # M:1146
+            if iteration < self.burninPeriod and self.numModalities > 1:
+                self.p_a[:] = min(iteration / 100.0 + 0.3, 1.1)                                     # M:1166-1169
+            elif iteration > self.burninPeriod and self.optimizeInterval != 0 and iteration % self.optimizeInterval == 0:
+                self.optimizeHyperParameters(iteration)                                            # M:1173-1210
+            self._push_hyper()
+            self.engine.sweep(iteration)                                                           # M:1213-1239
+            self.sweep_ms.append(self.engine.stats()["ms_total"])
+            if iteration % 10 == 0:                                                                # M:1296-1304
+                ll = self.modelLogLikelihood()
+                if iteration // 10 < self.perplexities.shape[1]:
+                    for m in range(self.numModalities):
+                        self.perplexities[m, iteration // 10] = ll[m] / max(1, self.totalTokens[m])
+            self.iterationsSoFar = iteration
+            alpha, alphaSum, _ = self.engine.get_hyper()      # topics activated by the sweep (U:263-270)
+            self.alpha, self.alphaSum = alpha, alphaSum
+
+    def optimizeHyperParameters(self, iteration):
+        """optimizeP / optimizeDP / optimizeGamma / optimizeBeta (M:2288-2632, 2698-2819) run on the host from the
+        engine's exported statistics; they are SURVEY 8(f) rank-1 "next" work and not part of this path yet."""
+        return None
+
+    # ---- readers ---------------------------------------------------------------------------------------
+    def modelLogLikelihood(self, quirk_len2=False):
+        return self.engine.loglik(quirk_len2)
+
+    @property
+    def typeTopicCounts(self):
+        return [self.engine.get_counts(m)[0] for m in range(self.numModalities)]
+
+    @property
+    def tokensPerTopic(self):
+        return [self.engine.get_counts(m, want_nwk=False)[1] for m in range(self.numModalities)]
+
+    def topicDocCounts(self, m):
+        return self.engine.doc_topic_hist(m)
+
+    def getTopicAssignments(self, m):
+        return self.engine.get_assignments(m)
+
+    def getTopWords(self, m, numWords):
+        """Indices of the top words per topic by count (the ranking of M:1792-1890 without the alphabet lookup)."""
+        nwk = self.engine.get_counts(m)[0]
+        return np.argsort(-nwk, axis=0, kind="stable")[:numWords].T

@@ -63,6 +63,7 @@ typedef struct {
     int n_inactive;
     int32_t *inactive;               /* ascending topic ids */
     uint64_t seed;
+    int64_t doc_base, doc_stride;    /* global id of local document d = doc_base + d*doc_stride (keys the RNG) */
     int64_t cnt_new, cnt_doc, cnt_tree, cnt_changed;   /* W:33-35 bucket counters */
     char err[256];
 } orc_t;
@@ -181,7 +182,7 @@ orc_t *orc_create(int M, int K, int64_t D, const int32_t *V, uint64_t seed)
 {
     if (M < 1 || M > ORC_MAXM || K < 1 || D < 0) return NULL;
     orc_t *o = (orc_t *)calloc(1, sizeof(orc_t));
-    o->M = M; o->K = K; o->D = D; o->seed = seed;
+    o->M = M; o->K = K; o->D = D; o->seed = seed; o->doc_base = 0; o->doc_stride = 1;
     o->inactive = (int32_t *)calloc((size_t)K, sizeof(int32_t));
     for (int m = 0; m < M; m++) {
         o->V[m] = V[m];
@@ -323,7 +324,7 @@ int orc_init_assignments(orc_t *o)
             int64_t b = o->doc_off[m][d], e = o->doc_off[m][d + 1];
             for (int64_t i = b; i < e; i++) {
                 uint32_t x[4];
-                orc_draw(o, (uint32_t)(i - b), (uint32_t)d, 0, (uint32_t)m, ORC_PURPOSE_INIT, x);
+                orc_draw(o, (uint32_t)(i - b), (uint32_t)(o->doc_base + d * o->doc_stride), 0, (uint32_t)m, ORC_PURPOSE_INIT, x);
                 int t;
                 if (m == 0 || len0 == 0) t = (int)(((uint64_t)x[0] * (uint64_t)K) >> 32);          /* M:500,506 */
                 else t = o->z[0][b0 + (int64_t)(((uint64_t)x[0] * (uint64_t)len0) >> 32)];       /* M:503-504 */
@@ -344,6 +345,13 @@ int orc_get_counts(const orc_t *o, int m, int32_t *n_wk, int32_t *n_k)
 {
     if (n_wk) memcpy(n_wk, o->n_wk[m], (size_t)o->V[m] * o->K * 4);
     if (n_k) memcpy(n_k, o->n_k[m], (size_t)o->K * 4);
+    return 0;
+}
+void orc_set_doc_ids(orc_t *o, int64_t base, int64_t stride) { o->doc_base = base; o->doc_stride = stride ? stride : 1; }
+int orc_set_counts(orc_t *o, int m, const int32_t *n_wk, const int32_t *n_k)
+{   /* multi-rank tests: install globally reduced counts */
+    if (n_wk) memcpy(o->n_wk[m], n_wk, (size_t)o->V[m] * o->K * 4);
+    if (n_k) memcpy(o->n_k[m], n_k, (size_t)o->K * 4);
     return 0;
 }
 int orc_maxlen(const orc_t *o, int m) { return o->maxlen[m]; }
@@ -398,7 +406,7 @@ static void draw_p(const orc_t *o, int64_t d, int iteration, unsigned flags, dou
             else if (o->p_a[m][j] == 0) r = 0.0;
             else {
                 uint32_t x[4];
-                orc_draw(o, 0, (uint32_t)d, (uint32_t)iteration, (uint32_t)(m * M + j), ORC_PURPOSE_PDRAW, x);
+                orc_draw(o, 0, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)(m * M + j), ORC_PURPOSE_PDRAW, x);
                 double b;
                 if (flags & ORC_F_BETA_MALLET) b = orc_next_beta_mallet(((uint64_t)x[1] << 32) | x[2], o->p_a[m][j], o->p_b[m][j]);
                 else b = pow(u24(x[0]), 1.0 / o->p_a[m][j]);          /* true Beta(a,1), engine default (Q5) */
@@ -499,7 +507,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
             else { build_tree_for_word(o, m, w, s->ttree, s->tmp); tree = s->ttree; }
             double B = tree[1];
             uint32_t x[4];
-            orc_draw(o, (uint32_t)pos, (uint32_t)d, (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
+            orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
             double sample = u24(x[0]) * (C + acc + B);                   /* W:517-519 */
             int new_t;
             if (sample < C) { new_t = o->inactive[0]; cnt[0]++; }        /* W:522-526 */
@@ -598,7 +606,7 @@ int orc_engine_select(const double *wgt, int K, double u, double C, int first_in
 }
 
 static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, unsigned flags, orc_scratch *s,
-                                  const int32_t *nk_frozen, int64_t cnt[4])
+                                  const int32_t *nk_frozen, int32_t *dnk, int64_t cnt[4])
 {
     int M = o->M, K = o->K;
     double p[ORC_MAXM][ORC_MAXM];
@@ -623,14 +631,14 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
         if (old_t != ORC_UNASSIGNED) s->nd[m * K + old_t]--;
         engine_weights(o, m, w, s->nd, len, p, nk_frozen, s->cum);
         uint32_t x[4];
-        orc_draw(o, (uint32_t)pos, (uint32_t)d, (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
+        orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
         int new_t = orc_engine_select(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1);
         o->z[m][b + pos] = new_t;
         s->nd[m * K + new_t]++;
         if (new_t != old_t && !(flags & ORC_F_FROZEN)) {   /* n_wk live, n_k deferred to the end of the view pass (engine semantics) */
             int32_t *row = o->n_wk[m] + (size_t)w * K;
-            if (old_t != ORC_UNASSIGNED) row[old_t]--;
-            row[new_t]++;
+            if (old_t != ORC_UNASSIGNED) { row[old_t]--; dnk[old_t]--; }
+            row[new_t]++; dnk[new_t]++;
             cnt[3]++;
         }
     }
@@ -676,15 +684,21 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
     if (flags & ORC_F_ENGINE_MIRROR) {
         int K = o->K;
         int32_t *nk_frozen = (int32_t *)malloc((size_t)K * 4);
+        int32_t *dnk = (int32_t *)malloc((size_t)K * 4);
         int64_t *order = (int64_t *)malloc((size_t)(o->D > 0 ? o->D : 1) * 8);
         for (int m = 0; m < o->M; m++) {
             memcpy(nk_frozen, o->n_k[m], (size_t)K * 4);
             for (int64_t d = 0; d < o->D; d++) order[d] = d;
             if (!(flags & ORC_F_DOC_ORDER)) qsort_r(order, (size_t)o->D, 8, cmp_len_desc, o->doc_off[m]);
-            for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, flags, s, nk_frozen, cnt);
-            if (!(flags & ORC_F_FROZEN)) recount_nk_hist(o, m);
+            memset(dnk, 0, (size_t)K * 4);
+            for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, flags, s, nk_frozen, dnk, cnt);
+            if (!(flags & ORC_F_FROZEN)) {       /* the engine flushes its n_k deltas at the end of the view pass */
+                memcpy(nk_frozen, o->n_k[m], (size_t)K * 4);
+                recount_nk_hist(o, m);           /* local doc-topic histogram (and a local n_k, replaced below)  */
+                for (int t = 0; t < K; t++) o->n_k[m][t] = nk_frozen[t] + dnk[t];
+            }
         }
-        free(nk_frozen); free(order);
+        free(nk_frozen); free(dnk); free(order);
         if (!(flags & ORC_F_FROZEN)) activate_sampled_topics(o);
     } else {
         if ((flags & ORC_F_STALE_TREES) && !o->tree[0]) orc_rebuild_trees(o);

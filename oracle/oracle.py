@@ -51,6 +51,8 @@ def lib():
             "orc_get_assignments": (i32, [p, i32, p]),
             "orc_get_counts": (i32, [p, i32, p, p]),
             "orc_maxlen": (i32, [p, i32]),
+            "orc_set_doc_ids": (None, [p, i64, i64]),
+            "orc_set_counts": (i32, [p, i32, p, p]),
             "orc_get_hist": (i32, [p, i32, p]),
             "orc_get_alpha": (i32, [p, i32, p]),
             "orc_get_inactive": (i32, [p, p]),
@@ -179,6 +181,14 @@ class Oracle:
         nk = np.zeros(self.K, dtype=np.int32)
         lib().orc_get_counts(self.h, m, _ptr(nwk), _ptr(nk))
         return nwk, nk
+
+    def set_doc_ids(self, base, stride):
+        lib().orc_set_doc_ids(self.h, int(base), int(stride))
+
+    def set_counts(self, m, nwk=None, nk=None):
+        nwk = None if nwk is None else np.ascontiguousarray(nwk, dtype=np.int32)
+        nk = None if nk is None else np.ascontiguousarray(nk, dtype=np.int32)
+        lib().orc_set_counts(self.h, m, _ptr(nwk), _ptr(nk))
 
     def get_hist(self, m):
         ml = lib().orc_maxlen(self.h, m)

@@ -1,0 +1,85 @@
+"""CPU tests of the drop-in boundary: libmvtm.so loads, exports every symbol include/mvtm.h declares, and fails
+loudly (no fallback) when there is no CUDA device.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "mvtm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvtm_[a-z_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(engine_lib):
+    from mvtopicmodel_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(engine_lib, n), f"{n} declared in mvtm.h but not exported by libmvtm.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_library_is_sm100a_native(engine_lib):
+    from mvtopicmodel_b200 import _lib
+    assert b"sm_100a" in engine_lib.mvtm_build_info()
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass                 # TMA 1-D bulk copies of the n_wk rows
+    assert "SYNCS.ARRIVE.TRANS64" in sass   # mbarrier expect_tx
+    assert "REDG" in sass or "RED." in sass # count deltas as reductions
+
+
+def test_no_cpu_fallback_without_device(engine_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from mvtopicmodel_b200 import Engine, MvtmError
+    import numpy as np
+    with pytest.raises(MvtmError) as ei:
+        Engine(10, [5], [(np.array([0, 2], dtype=np.int64), np.array([1, 2], dtype=np.int32))])
+    assert ei.value.status == 3 and "no CPU fallback" in str(ei.value)
+
+
+def test_argument_validation_before_any_device_work(engine_lib):
+    from mvtopicmodel_b200 import _lib
+    h = C.c_void_p()
+    V = (C.c_int32 * 1)(5)
+    cfg = _lib.MvtmConfig(0, 1, 1, V, 1, 0, 0, 0, 1, 0, 0, 0)          # K = 0
+    assert engine_lib.mvtm_create(C.byref(cfg), C.byref(h)) == 1
+    cfg = _lib.MvtmConfig(5000, 1, 1, V, 1, 0, 0, 0, 1, 0, 0, 0)       # K beyond this build
+    assert engine_lib.mvtm_create(C.byref(cfg), C.byref(h)) == 5
+    assert b"2048" in engine_lib.mvtm_last_error(None)
+    assert engine_lib.mvtm_create(None, C.byref(h)) == 1
+    assert engine_lib.mvtm_destroy(None) == 0
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under mvtopicmodel_b200/ or include/ may import, include or link it."""
+    bad = re.compile(r"(^\s*(from|import)\s+oracle\b)|(#include\s*[\"<][^\">]*oracle)|(libmvtm_oracle)|(orc_[a-z_]+\s*\()", re.M)
+    for top in ("mvtopicmodel_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not bad.search(txt), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_cpp_host_mirror_compiles(engine_lib, tmp_path):
+    exe = tmp_path / "host_driver"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_driver.cpp"),
+                           "-o", str(exe), "-L" + os.path.join(ROOT, "mvtopicmodel_b200"), "-lmvtm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "mvtopicmodel_b200")])
+    import torch
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout
+    else:
+        assert r.returncode == 2 and "no CUDA device" in r.stdout     # loud failure, not a fallback

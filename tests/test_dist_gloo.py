@@ -1,0 +1,126 @@
+"""CPU tests of the multi-rank host logic (world_size 2, gloo): document sharding with global ids, and the integer
+delta all-reduce protocol of mvtopicmodel_b200/dist.py.  The per-rank sampler here is the CPU oracle (a test
+stand-in for the CUDA engine, which needs a GPU); the protocol code under test is the product's CountExchange."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class OracleAdapter:
+    """delta_begin / delta_reset / delta_export / delta_import over an Oracle, mirroring EngineAdapter on CPU tensors."""
+
+    def __init__(self, o):
+        self.o, self.M = o, o.M
+        self.snap = [None] * o.M
+        self.buf = [None] * o.M
+
+    def _cur(self, m):
+        nwk, nk = self.o.get_counts(m)
+        return torch.from_numpy(nwk.reshape(-1).copy()), torch.from_numpy(nk.copy())
+
+    def delta_begin(self):
+        self.snap = [self._cur(m) for m in range(self.M)]
+
+    def delta_reset(self):
+        self.snap = [tuple(torch.zeros_like(t) for t in self._cur(m)) for m in range(self.M)]
+
+    def delta_export(self, m):
+        a, b = self._cur(m)
+        self.buf[m] = (a - self.snap[m][0], b - self.snap[m][1])
+        return self.buf[m]
+
+    def delta_import(self, m):
+        a = self.snap[m][0] + self.buf[m][0]
+        b = self.snap[m][1] + self.buf[m][1]
+        self.snap[m] = (a, b)
+        self.o.set_counts(m, a.numpy().reshape(int(self.o.V[m]), self.o.K), b.numpy())
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import random_corpus, recount
+        from mvtopicmodel_b200 import corpus
+        from mvtopicmodel_b200.dist import CountExchange, shard_doc_ids
+        from oracle import oracle as O
+        K, Vs = 24, [80, 30]
+        full = random_corpus(17, 301, K, Vs, [9, 3])
+        D = len(full[0][0]) - 1
+        base, stride, n_local = shard_doc_ids(D, rank, world)
+        views = corpus.shard_views(full, rank, world)
+        assert len(views[0][0]) - 1 == n_local
+        o = O.Oracle(K, Vs, views, seed=5)
+        o.set_doc_ids(base, stride)
+        x = CountExchange(OracleAdapter(o))
+        x.reset()
+        o.init_assignments()
+        # (1) a sharded run draws what the unsharded one does: compare with the unsharded oracle's init
+        ref = O.Oracle(K, Vs, full, seed=5)
+        ref.init_assignments()
+        for m in range(2):
+            zr, zl = ref.get_assignments(m), o.get_assignments(m)
+            off = full[m][0]
+            mine = np.concatenate([zr[off[d]:off[d + 1]] for d in range(rank, D, world)]) if len(zl) else zl
+            assert np.array_equal(mine, zl)
+        x.exchange()
+        for m in range(2):      # (2) after the exchange every rank holds the global counts of the unsharded init
+            a, b = o.get_counts(m); ra, rb = ref.get_counts(m)
+            assert np.array_equal(a, ra) and np.array_equal(b, rb)
+        # (3) sweeps with the exchange keep the global invariants bit-exact
+        for it in range(1, 5):
+            o.sweep(it, O.F_ENGINE_MIRROR)
+            nbytes = x.exchange()
+            assert nbytes == sum((Vs[m] * K + K) * 4 for m in range(2))
+            zs_all = [None] * world
+            dist.all_gather_object(zs_all, [o.get_assignments(m) for m in range(2)])
+            for m in range(2):
+                nwk = np.zeros((Vs[m], K), dtype=np.int64); nk = np.zeros(K, dtype=np.int64)
+                for r in range(world):
+                    vr = corpus.shard_views(full, r, world)
+                    (a, b), = recount([vr[m]], [zs_all[r][m]], K, [Vs[m]])
+                    nwk += a; nk += b
+                a, b = o.get_counts(m)
+                assert np.array_equal(a, nwk) and np.array_equal(b, nk)
+        q.put((rank, "ok"))
+    except Exception as e:   # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_delta_exchange_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_views_partition():
+    from helpers import random_corpus
+    from mvtopicmodel_b200 import corpus
+    full = random_corpus(3, 50, 8, [20, 10], [5, 2])
+    for world in (1, 2, 4, 8):
+        tot = [0, 0]
+        for r in range(world):
+            sv = corpus.shard_views(full, r, world)
+            for m in range(2):
+                tot[m] += len(sv[m][1])
+                assert sv[m][0][-1] == len(sv[m][1])
+        assert tot == [len(full[0][1]), len(full[1][1])]

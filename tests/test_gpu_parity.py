@@ -350,3 +350,71 @@ def test_full_size_properties_lda_100k(engine_lib):
     assert int(nk.sum()) == ntok
     ll1 = e.loglik()[0] / ntok
     assert ll1 > ll0 + 0.1, (ll0, ll1)
+
+
+def test_golden_init_vector(engine_lib):
+    """Bit-exact against the committed golden vector (tests/golden/oracle_tiny.json, made by make_golden.py)."""
+    import json, os
+    from mvtopicmodel_b200 import Engine
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_tiny.json")))
+    views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in g["views"]]
+    e = Engine(g["K"], g["V"], views, seed=g["seed"])
+    e.init_assignments()
+    for m in range(len(views)):
+        assert e.get_assignments(m).tolist() == g["z_init"][m]
+    # and the golden final state of the oracle is a valid state for the engine: same LL, consistent counts
+    for m in range(len(views)):
+        e.set_assignments(m, np.array(g["z_final"][m], dtype=np.int32))
+    assert np.allclose(e.loglik(), g["loglik"], rtol=1e-10)
+    assert e.check_invariants() == 0
+
+
+def test_sms_config_200_iterations(engine_lib, oracle_mod):
+    """BASELINE configs[0]: the SMS collection, single view, K = 50, 200 iterations, through the
+    FastQMVWVParallelTopicModel mirror (addInstances / estimate); LL/token within 1 % of the sequential oracle and not
+    behind the reference's threaded scheme.  5.5 K documents: asynchrony bounded as in the reference (6 samplers)."""
+    import os
+    from mvtopicmodel_b200.model import FastQMVWVParallelTopicModel, Instance, InstanceList
+    O = oracle_mod
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "sms_corpus.npz"))
+    off, words, V = f["doc_off"], f["word_id"], int(f["V"])
+    D = len(off) - 1
+    il = InstanceList([Instance(f"sms{d}", words[off[d]:off[d + 1]]) for d in range(D)], alphabet_size=V)
+    os.environ["MVTM_CTAS"], os.environ["MVTM_WARPS"] = "6", "4"
+    try:
+        model = FastQMVWVParallelTopicModel(50, 1, 0.1, 0.01)
+        model.setRandomSeed(20261018)
+        model.setNumIterations(200)
+        model.setBurninPeriod(250)          # no optimiser step inside these 200 sweeps (fixed hyper-parameters)
+        model.addInstances([il], "sms", 0, None)
+        model.estimate()
+    finally:
+        del os.environ["MVTM_CTAS"], os.environ["MVTM_WARPS"]
+    assert model.engine.check_invariants() == 0
+    ntok = len(words)
+    le = model.modelLogLikelihood()[0] / ntok
+    assert model.perplexities[0, 20] == pytest.approx(le, rel=1e-12)        # LL series M:1296-1304
+    o = O.Oracle(50, [V], [(off, words)], seed=20261018, present=[np.ones(D, dtype=np.uint8)])
+    o2 = O.Oracle(50, [V], [(off, words)], seed=20261018, present=[np.ones(D, dtype=np.uint8)])
+    o.init_assignments(); o2.init_assignments()
+    for it in range(1, 201):
+        o.sweep(it, O.F_STALE_TREES); o2.sweep_mt(it, 8)
+    lo, lo2 = o.loglik()[0] / ntok, o2.loglik()[0] / ntok
+    print("SMS LL/token engine", le, "oracle sequential", lo, "oracle 8 threads", lo2,
+          "quirk Q18 engine", model.modelLogLikelihood(True)[0] / ntok, "oracle", o.loglik(True)[0] / ntok)
+    assert abs(le - lo) / abs(lo) < REL_TOL_LL, (le, lo)
+    assert le > lo2 - REL_TOL_LL * abs(lo2)
+    # Q18 (phantom topic-0 tokens of 0/1-token documents) shifts LL/token by a few per cent on this corpus
+    assert abs(model.modelLogLikelihood(True)[0] - o.loglik(True)[0]) / abs(o.loglik(True)[0]) < REL_TOL_LL
+
+
+def test_cpp_host_driver_runs(engine_lib, tmp_path):
+    """The C++ FastQMVWVParallelTopicModel mirror (include/mvtm_model.hpp) drives the C ABI end to end."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_driver"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_driver.cpp"),
+                           "-o", str(exe), "-L" + os.path.join(root, "mvtopicmodel_b200"), "-lmvtm", "-Wl,-rpath," + os.path.join(root, "mvtopicmodel_b200")])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and "OK" in r.stdout
