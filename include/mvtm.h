@@ -139,6 +139,11 @@ int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_
 int mvtm_delta_import(mvtm_handle *h, int32_t m);
 int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out);
 
+/* Scan layout of the sampler (for order-exact checkers): a document-view is sampled by `lanes_per_doc` lanes (8, 16 or
+ * 32); topic t sits in 4-topic chunk c = t/4 owned by lane c % lanes_per_doc as its (c / lanes_per_doc)-th chunk, and the
+ * cumulative scan runs lane-major (all chunks of lane 0, then lane 1, ...). */
+int mvtm_scan_layout(mvtm_handle *h, int32_t *lanes_per_doc, int32_t *chunks_per_lane);
+
 /* Build information: "sm_100a", kernel variants compiled in. */
 const char *mvtm_build_info(void);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mvtm_delta_export": (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
     "mvtm_delta_import": (_i32, [_vp, _i32]),
     "mvtm_row_stride": (_i32, [_vp, C.POINTER(_i32)]),
+    "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_build_info": (C.c_char_p, []),
 }
 

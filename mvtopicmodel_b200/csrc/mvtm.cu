@@ -35,7 +35,7 @@ struct ViewDev {
 }  // namespace
 
 struct mvtm_handle {
-    int K = 0, M = 0, Kp = 0, J = 0;
+    int K = 0, M = 0, Kp = 0, J = 0, KS = 0, G = 32;
     long long D = 0;
     int device = 0, num_sms = 0;
     unsigned flags = 0;
@@ -52,6 +52,8 @@ struct mvtm_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
     int *work_counter = nullptr;
+    float *oc_scratch = nullptr;                    // multi-view: Kp floats per resident document slot
+    size_t oc_scratch_floats = 0;
     unsigned long long *d_stats = nullptr;
     int *d_bad = nullptr;
     mvtm_sweep_stats stats;
@@ -77,11 +79,25 @@ static int pick_J(int K)
     for (int j : opts) if (j * 128 >= K) return j;
     return 0;
 }
+// lanes per document-view (the lane group G of mvtm_kernels.cuh) for a slot size KS = 128 * J.
+// Compiled combinations: (128,8) (256,8) (384,16) (512,8) (512,16) (512,32) (768,16) (1024,16) (1024,32) (1536,32) (2048,32).
+static int pick_G(int KS, bool multi)
+{
+    int g = KS <= 256 ? 8 : (KS <= 1024 ? 16 : 32);       // measured on B200: lda_100k 3.4 (G=16) vs 2.6 G tok/s (G=32)
+    if (multi && KS >= 1024) g = 32;                      // measured: acm_2v 1.43 (G=32) vs 1.30 G tok/s (G=16)
+    if (const char *e = getenv("MVTM_GROUP")) {
+        int want = atoi(e);
+        if (want == 32 && (KS == 512 || KS == 1024)) g = 32;
+        if (want == 16 && (KS == 512 || KS == 1024)) g = 16;
+        if (want == 8 && KS == 512) g = 8;
+    }
+    return g;
+}
 
 // ------------------------------------------------------------------------------------------------
 extern "C" const char *mvtm_build_info(void)
 {
-    return "mvtm-b200 sm_100a; k_sweep_view<J in {1,2,3,4,6,8,12,16}, single|multi view>; TMA 1-D bulk ring; Philox4x32-10";
+    return "mvtm-b200 sm_100a; k_sweep_view<KS in {128..2048}, lanes per document G in {8,16,32}, single|multi view>; TMA 1-D bulk ring; Philox4x32-10";
 }
 
 extern "C" const char *mvtm_last_error(const mvtm_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -108,6 +124,8 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
     h->cfg_warps = cfg->warps_per_cta; h->cfg_ring = cfg->ring_depth; h->cfg_ctas = cfg->max_ctas;
     h->Kp = (h->K + 31) / 32 * 32;
     h->J = pick_J(h->K);
+    h->KS = h->J * 128;
+    h->G = pick_G(h->KS, h->M > 1);
     memset(&h->stats, 0, sizeof(h->stats));
     h->alpha.assign((size_t)h->M * (h->K + 1), 0.1);                    // S:149-159, M:195-239
     for (int m = 0; m < h->M; m++) {
@@ -145,7 +163,7 @@ extern "C" int mvtm_destroy(mvtm_handle *h)
     cudaStreamSynchronize(h->stream);
     for (int m = 0; m < h->M; m++) free_view(h->v[m]);
     for (auto &ev : h->ev) cudaEventDestroy(ev);
-    cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad);
+    cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad); cudaFree(h->oc_scratch);
     cudaStreamDestroy(h->stream);
     delete h;
     return MVTM_OK;
@@ -155,6 +173,14 @@ extern "C" int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out)
 {
     if (!h || !stride_out) return MVTM_ERR_ARG;
     *stride_out = h->Kp;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_scan_layout(mvtm_handle *h, int32_t *lanes_per_doc, int32_t *chunks_per_lane)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (lanes_per_doc) *lanes_per_doc = h->G;
+    if (chunks_per_lane) *chunks_per_lane = h->KS / (4 * h->G);
     return MVTM_OK;
 }
 
@@ -379,27 +405,40 @@ static void fill_params(mvtm_handle *h, int m, int iteration, int update_global,
     P.doc_id_base = h->doc_id_base; P.doc_id_stride = h->doc_id_stride;
     P.update_global = update_global;
     P.stats = h->d_stats;
+    P.oc_scratch = h->oc_scratch;
+}
+
+static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
+{
+    if (h->M < 2) return MVTM_OK;
+    const size_t need = doc_slots * (size_t)h->Kp;
+    if (need <= h->oc_scratch_floats) return MVTM_OK;
+    CK(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->oc_scratch); h->oc_scratch = nullptr; h->oc_scratch_floats = 0;
+    CK(h, cudaMalloc(&h->oc_scratch, need * sizeof(float)));
+    h->oc_scratch_floats = need;
+    return MVTM_OK;
 }
 
 struct LaunchCfg { int R, W, grid; size_t smem; };
 
 static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
 {
-    const int KS = h->J * 128;
+    const int KS = h->KS, G = h->G, NSUB = 32 / G, JG = KS / (4 * G);
     const bool multi = h->M > 1;
-    int R = h->cfg_ring > 0 ? h->cfg_ring : 2;
+    int R = h->cfg_ring > 0 ? h->cfg_ring : 1;        // measured: more resident documents beat a deeper ring
     if (const char *e = getenv("MVTM_RING")) R = atoi(e);
-    R = std::max(1, std::min(R, 16));
+    R = std::max(1, std::min(R, 8));
     const size_t budget = 227 * 1024 - 1024;
-    int W;
+    int docs;
     for (;;) {
-        size_t per = smem_warp_bytes(KS, R, multi);
-        W = (int)((budget - smem_cta_bytes(KS)) / per);
-        if (W >= 1 || R == 1) break;
+        docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0)) / smem_doc_bytes(KS, R, multi));
+        if (docs >= NSUB || R == 1) break;
         R--;
     }
-    if (W < 1) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
-    W = std::min(W, (h->J <= 4 ? 768 : (h->J <= 8 ? 512 : 384)) / 32);
+    if (docs < NSUB) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
+    int W = docs / NSUB;
+    W = std::min(W, sweep_max_threads(JG) / 32);
     if (h->cfg_warps > 0) W = std::min(W, h->cfg_warps);
     if (const char *e = getenv("MVTM_WARPS")) W = std::max(1, std::min(W, atoi(e)));
     int grid = h->num_sms;
@@ -407,42 +446,44 @@ static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
     if (const char *e = getenv("MVTM_CTAS")) grid = std::max(1, std::min(grid, atoi(e)));
     if (h->flags & MVTM_FLAG_SINGLE_WARP) { W = 1; grid = 1; }
     lc.R = R; lc.W = W; lc.grid = grid;
-    lc.smem = smem_cta_bytes(KS) + (size_t)W * smem_warp_bytes(KS, R, multi);
+    lc.smem = smem_cta_bytes(KS, multi ? h->M : 0) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi);
     return MVTM_OK;
 }
 
-template <int J, bool MULTI>
+template <int KS, int G, bool MULTI>
 static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_view<J, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_view<KS, G, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
     if (e != cudaSuccess) return e;
-    k_sweep_view<J, MULTI><<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
+    k_sweep_view<KS, G, MULTI><<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
     return cudaGetLastError();
 }
-template <int J, bool MULTI>
+template <int KS, int G, bool MULTI>
 static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const double *p_row, double *out, cudaStream_t s)
 {
-    size_t smem = smem_cta_bytes(J * 128) + smem_warp_bytes(J * 128, 1, MULTI);
-    cudaError_t e = cudaFuncSetAttribute(k_cond_probe<J, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(32 / G) * smem_doc_bytes(KS, 1, MULTI);
+    cudaError_t e = cudaFuncSetAttribute(k_cond_probe<KS, G, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_cond_probe<J, MULTI><<<1, 32, smem, s>>>(P, d, pos, p_row, out);
+    k_cond_probe<KS, G, MULTI><<<1, 32, smem, s>>>(P, d, pos, p_row, out);
     return cudaGetLastError();
 }
 
-#define DISPATCH_J(J_, MULTI_, CALL)                                         \
-    switch (J_) {                                                            \
-        case 1: CALL(1, MULTI_); break;   case 2: CALL(2, MULTI_); break;    \
-        case 3: CALL(3, MULTI_); break;   case 4: CALL(4, MULTI_); break;    \
-        case 6: CALL(6, MULTI_); break;   case 8: CALL(8, MULTI_); break;    \
-        case 12: CALL(12, MULTI_); break; case 16: CALL(16, MULTI_); break;  \
-        default: break;                                                      \
+#define DISPATCH_KG(KS_, G_, MULTI_, CALL)                                                        \
+    switch ((KS_) * 64 + (G_)) {                                                                  \
+        case 128 * 64 + 8: CALL(128, 8, MULTI_); break;    case 256 * 64 + 8: CALL(256, 8, MULTI_); break;      \
+        case 384 * 64 + 16: CALL(384, 16, MULTI_); break;  case 512 * 64 + 16: CALL(512, 16, MULTI_); break;    \
+        case 512 * 64 + 32: CALL(512, 32, MULTI_); break;  case 768 * 64 + 16: CALL(768, 16, MULTI_); break;    \
+        case 512 * 64 + 8: CALL(512, 8, MULTI_); break;                                                         \
+        case 1024 * 64 + 16: CALL(1024, 16, MULTI_); break; case 1024 * 64 + 32: CALL(1024, 32, MULTI_); break; \
+        case 1536 * 64 + 32: CALL(1536, 32, MULTI_); break; case 2048 * 64 + 32: CALL(2048, 32, MULTI_); break; \
+        default: break;                                                                           \
     }
 
 static cudaError_t launch_sweep(mvtm_handle *h, const SweepParams &P, const LaunchCfg &lc)
 {
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL_SWEEP(J_, MU_) e = launch_sweep_t<J_, MU_>(P, lc, h->stream)
-    if (h->M > 1) { DISPATCH_J(h->J, true, CALL_SWEEP) } else { DISPATCH_J(h->J, false, CALL_SWEEP) }
+#define CALL_SWEEP(KS_, G_, MU_) e = launch_sweep_t<KS_, G_, MU_>(P, lc, h->stream)
+    if (h->M > 1) { DISPATCH_KG(h->KS, h->G, true, CALL_SWEEP) } else { DISPATCH_KG(h->KS, h->G, false, CALL_SWEEP) }
 #undef CALL_SWEEP
     return e;
 }
@@ -472,6 +513,7 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
     if (int rc = upload_hyper(h)) return rc;
     LaunchCfg lc;
     if (int rc = choose_launch(h, lc)) return rc;
+    if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(h, cudaEventRecord(h->ev[0], h->stream));
     int launches = 0;
@@ -555,6 +597,7 @@ extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t p
     if (pos < 0 || pos >= len) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: position %d outside document of %lld tokens", pos, len);
     CK(h, cudaSetDevice(h->device));
     if (int rc = upload_hyper(h)) return rc;
+    if (int rc = ensure_oc_scratch(h, (size_t)(32 / h->G))) return rc;
     int w = 0;
     CK(h, cudaMemcpy(&w, v.word + v.h_doc_off[(size_t)doc] + pos, 4, cudaMemcpyDeviceToHost));
     if (w < 0 || w >= v.V) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: token has out-of-vocabulary word id %d (W:427-428 skips it)", w);
@@ -569,8 +612,8 @@ extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t p
     P.nk_frozen = v.nk;                                                  // frozen counts = the current ones
     P.R = 1;
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL_PROBE(J_, MU_) e = launch_probe_t<J_, MU_>(P, (int)doc, pos, d_p, d_out, h->stream)
-    if (h->M > 1) { DISPATCH_J(h->J, true, CALL_PROBE) } else { DISPATCH_J(h->J, false, CALL_PROBE) }
+#define CALL_PROBE(KS_, G_, MU_) e = launch_probe_t<KS_, G_, MU_>(P, (int)doc, pos, d_p, d_out, h->stream)
+    if (h->M > 1) { DISPATCH_KG(h->KS, h->G, true, CALL_PROBE) } else { DISPATCH_KG(h->KS, h->G, false, CALL_PROBE) }
 #undef CALL_PROBE
     if (e == cudaSuccess) e = cudaMemcpyAsync(probs_out, d_out, (size_t)(h->K + 1) * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

@@ -4,16 +4,19 @@
 // M = FastQMVWVParallelTopicModel, FT = FTree).
 //
 // Design (DESIGN.md has the long form):
-//  * one warp per document-view (north_star a); persistent CTAs, one per SM, pull work items from a
-//    longest-first list with an atomic counter;
+//  * one lane group per document-view (north_star a): G = 32 lanes (a whole warp) for large K, G = 16 or 8 lanes
+//    for small K so that a warp hosts 2 or 4 document-views of near-equal length and the per-token control
+//    instructions (shuffles, searches, TMA issue, bookkeeping) are shared between them; persistent CTAs, one per
+//    SM, pull groups of work items from a longest-first list with an atomic counter;
 //  * the document's topic counts n_d (u16) and its per-topic factor q[t] live in shared memory (b);
 //    q[t] = (p_mm*n_d[t] + [t in S]*O_m[t] + gamma*alpha[t]) / (n_k[t] + betaSum), so that the weight of
 //    topic t for a token of word w is simply (n_wk[w][t] + beta) * q[t]  -- the net distribution of
 //    W:495-538 (doc bucket + tree bucket) evaluated densely;
 //  * n_wk rows are staged global -> shared by the TMA engine (cp.async.bulk 1-D, mbarrier complete_tx)
 //    through a per-warp ring that keeps `R` rows in flight, and consumed as 128-bit LDS (b);
-//  * the conditional is sampled by a warp-cooperative scan: per-lane partial sums, __shfl_up inclusive
-//    scan over lanes, __ballot to find the lane, register-resident chunk sums to find the element (c);
+//  * the conditional is sampled by a group-cooperative scan: per-lane partial sums, segmented __shfl_up
+//    inclusive scan over the group's lanes, __ballot to find the lane, register-resident chunk sums to find the
+//    chunk, a 4-element search to find the topic (c);
 //  * RNG is Philox4x32-10 keyed on (seed; token position, global doc id, iteration, view|purpose) (d);
 //  * count deltas: n_wk by global RED atomics issued by two lanes, n_k through a per-CTA shared-memory
 //    delta vector flushed once per kernel (e).  No tensor cores: nothing here is a contraction.
@@ -47,6 +50,7 @@ struct SweepParams {
     int update_global;
     int R;                            // ring depth
     unsigned long long *stats;        // [0] tokens, [1] changed, [2] new-topic draws
+    float *oc_scratch;                // (multi-view) per resident document slot: Kp floats, see DocCtx::oc
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -98,17 +102,24 @@ __device__ __forceinline__ float2 lds_f2(uint32_t a)
 __device__ __forceinline__ void reds_add(uint32_t a, int v)
 { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+#define FULL 0xffffffffu
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
 // ------------------------------------------------------------------------------------------------
-// per-warp context (pointers into shared memory + per-document scalars)
+// per-document context: pointers into the lane group's shared-memory area + per-document scalars.
+// Layout of the scan: topic t lives in chunk c = t >> 2 (4 topics, one 128-bit word); chunk c is owned by group
+// lane gl = c % G and is that lane's j = c / G -th chunk (JG = KS / (4 G) chunks per lane).
 // ------------------------------------------------------------------------------------------------
-struct WarpCtx {
+struct DocCtx {
     float *q;              // KS
     unsigned short *nd;    // KS
-    float *oc;             // KS   (MULTI) sum_i c_i * n_d[i][t]
+    float *oc;             // Kp, GLOBAL scratch (MULTI) sum_i c_i * n_d[i][t]; only entries whose `om` bit is set are
+                           //     ever written or read, so it is neither zeroed nor resident in shared memory
     unsigned *om;          // KS/32 (MULTI) bit t: some other view holds topic t
     float *cpar;           // 8    (MULTI) c_i = p[m][i] / (len_i + gas_i), 0 if len_i == 0 or i == m
-    const float2 *ginv;    // KS   CTA-shared {ga_tree, 1/(n_k + betaSum)}
-    uint32_t ginv_sa;      // the same vector as a .shared address
+    uint32_t ginv_sa;      // CTA-shared {ga_tree, 1/(n_k + betaSum)} float2[KS] as a .shared address
+    const float *gaf;      // (MULTI) CTA-shared gamma_i*alpha_i[t] of every view, [M][KS] (W:404)
+    int gaf_stride;        // = KS
     float pmm, coefm, C;   // p[m][m]; len_m + gas_m; new-topic mass per token (W:515)
 };
 
@@ -121,51 +132,58 @@ __device__ __forceinline__ float q_value(float ndv, bool inS, float ocv, float p
 }
 
 template <bool MULTI>
-__device__ __forceinline__ float prior_other(const SweepParams &P, const WarpCtx &c, int t)
+__device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx &c, int t)
 {
     float pri = 0.f;
     if (MULTI) {
-        for (int i = 0; i < P.M; i++) { float ci = c.cpar[i]; if (ci != 0.f) pri += ci * __ldg(P.ga_full[i] + t); }
+        for (int i = 0; i < P.M; i++) { float ci = c.cpar[i]; if (ci != 0.f) pri += ci * c.gaf[(size_t)i * c.gaf_stride + t]; }
     }
     return pri;
 }
 
-// n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over its 4-topic chunk).  Executed by the
-// lane that owns topic t in the scan layout (lane == (t >> 2) & 31), W:434-471 / W:557-584.
-template <int J, bool MULTI>
-__device__ __forceinline__ void apply_count_delta(const SweepParams &P, WarpCtx &c, int t, int dl, int lane, float (&bsq)[J])
+// n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over the chunk).  Executed by the lane that
+// owns topic t (gl == (t >> 2) % G), W:434-471 / W:557-584.
+template <int KS, int G, bool MULTI>
+__device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl, int gl, float (&bsq)[KS / (4 * G)])
 {
+    constexpr int JG = KS / (4 * G);
     const unsigned ndv_i = (unsigned)((int)c.nd[t] + dl);
     c.nd[t] = (unsigned short)ndv_i;
     const float ndv = (float)ndv_i;
     bool inS = false; float ocv = 0.f, pri = 0.f;
     if (MULTI) {
-        inS = (ndv_i > 0u) || ((c.om[t >> 5] >> (t & 31)) & 1u);
-        if (inS) { ocv = c.oc[t]; pri = prior_other<MULTI>(P, c, t); }
+        const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
+        inS = (ndv_i > 0u) || oth;
+        if (inS) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
     }
     c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
-    const int j = t >> 7;
-    const float4 qq = reinterpret_cast<const float4 *>(c.q)[lane + 32 * j];   // own store is visible in program order
+    constexpr int LG = ilog2(G);
+    const int j = t >> (2 + LG);
+    const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];   // own store is visible in program order
     const float v = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
 #pragma unroll
-    for (int jj = 0; jj < J; jj++) if (jj == j) bsq[jj] = v;
+    for (int jj = 0; jj < JG; jj++) if (jj == j) bsq[jj] = v;
 }
 
-// one warp step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the
-// owners differ
-template <int J, bool MULTI>
-__device__ __forceinline__ void apply_pair(const SweepParams &P, WarpCtx &c, int tinc, int tdec, int lane, float (&bsq)[J])
+// one step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the owners
+// differ (a second pass runs only when one lane owns both).  No warp-level synchronisation inside: the lane groups of a
+// warp may diverge here.
+template <int KS, int G, bool MULTI>
+__device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int tinc, int tdec, int gl, float (&bsq)[KS / (4 * G)])
 {
     if (tinc == tdec) return;                                   // same topic: the two changes cancel
-    const int own_i = tinc >= 0 ? ((tinc >> 2) & 31) : -1, own_d = tdec >= 0 ? ((tdec >> 2) & 31) : -2;
-    int t = -1, dl = 0;
-    if (lane == own_i) { t = tinc; dl = 1; } else if (lane == own_d) { t = tdec; dl = -1; }
-    if (t >= 0) apply_count_delta<J, MULTI>(P, c, t, dl, lane, bsq);
-    if (own_i == own_d) { if (lane == own_d) apply_count_delta<J, MULTI>(P, c, tdec, -1, lane, bsq); }   // warp-uniform test
+    const int own_i = tinc >= 0 ? ((tinc >> 2) & (G - 1)) : -1, own_d = tdec >= 0 ? ((tdec >> 2) & (G - 1)) : -2;
+    int t = -1, dl = 0, t2 = -1;
+    if (gl == own_i) { t = tinc; dl = 1; if (own_i == own_d) t2 = tdec; } else if (gl == own_d) { t = tdec; dl = -1; }
+#pragma unroll 1
+    while (t >= 0) {
+        apply_count_delta<KS, G, MULTI>(P, c, t, dl, gl, bsq);
+        t = t2; t2 = -1; dl = -1;
+    }
 }
 
-// the view-coupling draw p[m][i] of W:327-337 for document gdoc (all lanes compute the same value)
-__device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
+// the view-coupling draw p[m][i] of W:327-337 for document gdoc (every lane of the group computes the same value)
+__device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
 {
     int m = P.m;
     double r;
@@ -183,87 +201,101 @@ __device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gd
     return (float)r;
 }
 
-// Build n_d, (MULTI: oc/om/cpar), q for document d of view P.m.  KS = J*128 slot elements.
-template <int J, bool MULTI>
-__device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int d, int lane, const double *p_override, float (&bsq)[J])
+// Build n_d, (MULTI: oc/om/cpar), q and beta*sum(q) for document d of view P.m (len == 0: nothing to do, but every
+// lane still walks the same __syncwarp sequence -- the groups of a warp hold different documents).
+template <int KS, int G, bool MULTI>
+__device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d, int len, int gl, const double *p_override,
+                                          bool skip_first, float (&bsq)[KS / (4 * G)])
 {
-    constexpr int KS = J * 128;
+    constexpr int JG = KS / (4 * G);
     const int m = P.m;
     const long long b = P.doc_off[m][d];
-    const int len = (int)(P.doc_off[m][d + 1] - b);
-    uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
-
+    const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
     unsigned *nd32 = reinterpret_cast<unsigned *>(c.nd);
-#pragma unroll
-    for (int k = lane; k < KS / 2; k += 32) nd32[k] = 0u;
+#pragma unroll 4
+    for (int k = gl; k < KS / 2; k += G) nd32[k] = 0u;
     c.pmm = 1.f; c.coefm = (float)len + P.gas[m]; c.C = 0.f;
     if (MULTI) {
         c.pmm = draw_p(P, m, gdoc, p_override);
-#pragma unroll
-        for (int k = lane; k < KS; k += 32) c.oc[k] = 0.f;
-        if (lane < KS / 32) c.om[lane] = 0u;                     // KS/32 <= 64: two passes
-        if (lane + 32 < KS / 32) c.om[lane + 32] = 0u;
+        for (int k = gl; k < KS / 32; k += G) c.om[k] = 0u;
         float cdoc = 0.f;
         unsigned *tmp32 = reinterpret_cast<unsigned *>(c.q);      // q is built last: reuse it as u16 scratch
-        for (int i = 0; i < P.M; i++) {
+        for (int i = 0; i < P.M; i++) {                           // uniform trip count; per-group work is predicated
             const long long bi = P.doc_off[i][d];
             const int leni = (int)(P.doc_off[i][d + 1] - bi);
-            float pmi = (i == m) ? c.pmm : draw_p(P, i, gdoc, p_override);
-            float denom = (float)leni + P.gas[i];
+            const float pmi = (i == m) ? c.pmm : draw_p(P, i, gdoc, p_override);
+            const float denom = (float)leni + P.gas[i];
             cdoc += pmi * P.ga_new[i] / denom;                    // W:414-416 (every view, no length test)
-            float ci = (i != m && leni != 0) ? pmi / denom : 0.f; // W:403-404
+            const bool other = (i != m && leni != 0 && len != 0);
+            const float ci = other ? pmi / denom : 0.f;           // W:403-404
             __syncwarp();
-            if (lane == 0) c.cpar[i] = ci;
-            if (i == m || leni == 0) continue;
-#pragma unroll
-            for (int k = lane; k < KS / 2; k += 32) tmp32[k] = 0u;
-            __syncwarp();
-            const int *zi = P.zv[i] + bi;
-            for (int k = lane; k < leni; k += 32) { int t = zi[k]; if (t >= 0) atomicAdd(&tmp32[t >> 1], 1u << ((t & 1) * 16)); }
-            __syncwarp();
-            const unsigned short *tmp16 = reinterpret_cast<const unsigned short *>(tmp32);
-#pragma unroll
-            for (int k = lane; k < KS; k += 32) {
-                unsigned cnt = tmp16[k];
-                if (cnt) { c.oc[k] += ci * (float)cnt; atomicOr(&c.om[k >> 5], 1u << (k & 31)); }
+            if (gl == 0) c.cpar[i] = ci;
+            if (other) {
+#pragma unroll 4
+                for (int k = gl; k < KS / 2; k += G) tmp32[k] = 0u;
             }
             __syncwarp();
+            if (other) {
+                const int *zi = P.zv[i] + bi;
+                for (int k = gl; k < leni; k += G) { int t = zi[k]; if (t >= 0) atomicAdd(&tmp32[t >> 1], 1u << ((t & 1) * 16)); }
+            }
+            __syncwarp();
+            if (other) {
+                const unsigned short *tmp16 = reinterpret_cast<const unsigned short *>(tmp32);
+#pragma unroll 2
+                for (int k = gl; k < KS; k += G) {
+                    unsigned cnt = tmp16[k];
+                    if (cnt) {        // first writer of a topic stores, later views accumulate (each k has one owner lane)
+                        const bool seen = (c.om[k >> 5] >> (k & 31)) & 1u;
+                        c.oc[k] = (seen ? c.oc[k] : 0.f) + ci * (float)cnt;
+                        if (!seen) atomicOr(&c.om[k >> 5], 1u << (k & 31));
+                    }
+                }
+            }
         }
         c.C = (P.n_inactive > 0) ? (cdoc * c.coefm) / (float)P.K : 0.f;   // W:418, W:515
-        __syncwarp();
     } else {
         // single view: p[0][0] = 1; C_doc = coefm * gamma*alpha[K] / (len + gas)  (W:413-418 with M = 1)
         c.C = (P.n_inactive > 0) ? (P.ga_new[m] / ((float)len + P.gas[m]) * c.coefm) / (float)P.K : 0.f;
-        __syncwarp();
-    }
-    // own-view histogram (W:352-359)
-    {
-        const int *zm = P.zv[m] + b;
-        for (int k = lane; k < len; k += 32) { int t = zm[k]; if (t >= 0) atomicAdd(&nd32[t >> 1], 1u << ((t & 1) * 16)); }
     }
     __syncwarp();
-    // q for every topic, four per lane per step
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-        const int cidx = lane + 32 * j, t0 = cidx * 4;
+    {   // own-view histogram (W:352-359).  With skip_first the document's first token is left out: it is the first to
+        // be resampled, so its removal (W:434-471) is folded into the setup
+        const int *zm = P.zv[m] + b;
+        for (int k = gl; k < len; k += G) {
+            int t = zm[k];
+            if (k == 0 && skip_first && (unsigned)__ldg(P.word + b) < (unsigned)P.V) t = -1;
+            if (t >= 0) atomicAdd(&nd32[t >> 1], 1u << ((t & 1) * 16));
+        }
+    }
+    __syncwarp();
+    // q for every topic, four per lane per step (kept rolled in the multi-view build: it runs once per document and
+    // the unrolled body would push the hot loop out of the instruction cache)
+#pragma unroll(MULTI ? 1 : JG)
+    for (int j = 0; j < JG; j++) {
+        const int cidx = gl + G * j, t0 = cidx * 4;
         const uint2 n2 = reinterpret_cast<const uint2 *>(c.nd)[cidx];
-        const float4 g01 = reinterpret_cast<const float4 *>(c.ginv)[2 * cidx];
-        const float4 g23 = reinterpret_cast<const float4 *>(c.ginv)[2 * cidx + 1];
-        float ndv[4] = { (float)(n2.x & 0xffffu), (float)(n2.x >> 16), (float)(n2.y & 0xffffu), (float)(n2.y >> 16) };
-        float2 gi[4] = { make_float2(g01.x, g01.y), make_float2(g01.z, g01.w), make_float2(g23.x, g23.y), make_float2(g23.z, g23.w) };
+        const float2 gi[4] = { lds_f2(c.ginv_sa + 8u * (uint32_t)t0), lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 1)),
+                               lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 2)), lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 3)) };
+        const float ndv[4] = { (float)(n2.x & 0xffffu), (float)(n2.x >> 16), (float)(n2.y & 0xffffu), (float)(n2.y >> 16) };
         float out[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             bool inS = false; float ocv = 0.f, pri = 0.f;
             if (MULTI) {
                 int t = t0 + e;
-                inS = (ndv[e] > 0.f) || ((c.om[t >> 5] >> (t & 31)) & 1u);
-                if (inS && t < P.K) { ocv = c.oc[t]; pri = prior_other<MULTI>(P, c, t); }
+                const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
+                inS = (ndv[e] > 0.f) || oth;
+                if (inS && t < P.K) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
             }
             out[e] = q_value<MULTI>(ndv[e], inS, ocv, pri, c.coefm, c.pmm, gi[e]);
         }
         reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(out[0], out[1], out[2], out[3]);
-        bsq[j] = P.beta * ((out[0] + out[1]) + (out[2] + out[3]));
+        const float v = P.beta * ((out[0] + out[1]) + (out[2] + out[3]));
+        if (MULTI) {
+#pragma unroll
+            for (int jj = 0; jj < JG; jj++) if (jj == j) bsq[jj] = v;
+        } else bsq[j] = v;
     }
     __syncwarp();
 }
@@ -271,17 +303,16 @@ __device__ __forceinline__ void warp_setup(const SweepParams &P, WarpCtx &c, int
 // weight of one topic: (n + beta) * q evaluated as n*q + beta*q
 __device__ __forceinline__ float topic_weight(int n, float q, float beta) { return fmaf(__int2float_rn(n), q, beta * q); }
 
-// per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, chunk j holding the lane's 4 topics
-// 4*(lane+32j)..+3, each weighted (n + beta) * q and evaluated as beta*sum(q) (registers, bsq) + sum n*q.
-// Returns the lane total (= cum[J-1]).
-template <int J>
-__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int lane, const float (&bsq)[J], float (&cum)[J])
+// per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, each topic weighted (n + beta) * q,
+// evaluated as beta*sum(q) (registers, bsq) + sum n*q.  Returns the lane total (= cum[JG-1]).
+template <int JG, int G>
+__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int gl, const float (&bsq)[JG], float (&cum)[JG])
 {
     float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < J; j++) {
-        const int4 r = row4[lane + 32 * j];
-        const float4 qq = q4[lane + 32 * j];
+    for (int j = 0; j < JG; j++) {
+        const int4 r = row4[gl + G * j];
+        const float4 qq = q4[gl + G * j];
         float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
         a = fmaf(__int2float_rn(r.y), qq.y, a);
         a = fmaf(__int2float_rn(r.z), qq.z, a);
@@ -292,59 +323,63 @@ __device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4
     return tot;
 }
 
-// largest float below a positive x (x > 0)
+// largest float below a positive x
 __device__ __forceinline__ float next_below(float x) { return __int_as_float(__float_as_int(x) - 1); }
 
-// warp-cooperative selection: returns the topic whose cumulative weight (lane-major scan order) first exceeds
-// target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket.
-template <int J>
-__device__ __forceinline__ int warp_select(const int4 *row4, const float4 *q4, int lane, float beta, const float (&bsq)[J], float u, float C)
+// group-cooperative selection: returns the topic whose cumulative weight (lane-major scan order inside the group) first
+// exceeds target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket (W:522).  Every lane of the warp
+// must call it (full-mask shuffles); groups whose document is exhausted compute on stale data and ignore the result.
+template <int JG, int G>
+__device__ __forceinline__ int group_select(const int4 *row4, const float4 *q4, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
 {
-    float cum[J];
-    const float lane_total = lane_weights<J>(row4, q4, lane, bsq, cum);
+    float cum[JG];
+    const float lane_total = lane_weights<JG, G>(row4, q4, gl, bsq, cum);
     float incl = lane_total;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { float v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
-    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
+    const float total = __shfl_sync(FULL, incl, G - 1, G);
     float target = u * (total + C);
-    if (C > 0.f) { if (target < C) return -1; target -= C; }
-    const unsigned hit = __ballot_sync(0xffffffffu, incl > target);
-    const unsigned pos = __ballot_sync(0xffffffffu, lane_total > 0.f);
-    const int L = hit ? (__ffs(hit) - 1) : (31 - __clz(pos));           // some lane is positive: every topic < K is
+    const bool newbucket = (C > 0.f) && (target < C);
+    target -= C;
+    const unsigned sh = (unsigned)(lane - gl);                                  // first lane of my group
+    const unsigned gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
+    const unsigned hit = (__ballot_sync(FULL, incl > target) >> sh) & gmask;
+    const unsigned pos = (__ballot_sync(FULL, lane_total > 0.f) >> sh) & gmask;
+    const int L = hit ? (__ffs(hit) - 1) : (pos ? 31 - __clz(pos) : 0);
     // residual inside the lane, clamped strictly below the lane total so that the chunk found has positive weight
-    float r = fminf(target - (incl - lane_total), next_below(lane_total));
-    // chunk: number of running sums <= r (the last one cannot be, by the clamp)
-    int jsel = 0; float base = 0.f;
+    const float r = fminf(target - (incl - lane_total), next_below(lane_total));
+    int jsel = 0; float base = 0.f;                                             // chunk: number of running sums <= r
 #pragma unroll
-    for (int j = 0; j < J - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
-    const int cidx = lane + 32 * jsel;
+    for (int j = 0; j < JG - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
+    const int cidx = gl + G * jsel;
     const int4 rr = row4[cidx];
     const float4 qq = q4[cidx];
     const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
     const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
     const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
-    const float r2 = fminf(r - base, next_below(c3));                 // same clamp one level down
+    const float r2 = fminf(r - base, next_below(c3));                           // same clamp one level down
     const int e = (r2 >= w0 ? 1 : 0) + (r2 >= c1 ? 1 : 0) + (r2 >= c2 ? 1 : 0);
     const int mine = 4 * cidx + e;
-    return __shfl_sync(0xffffffffu, mine, L);
+    const int sel = __shfl_sync(FULL, mine, L, G);
+    return newbucket ? -1 : sel;
 }
 
 // shared-memory carve-up -------------------------------------------------------------------------
-__host__ __device__ inline size_t smem_cta_bytes(int KS) { return (size_t)KS * 8 + (size_t)KS * 4; }
-__host__ __device__ inline size_t smem_warp_bytes(int KS, int R, bool multi)
+__host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi) { return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4; }
+__host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi)
 {
     size_t b = (size_t)KS * 4 + (size_t)KS * 2;                   // q, nd
-    if (multi) b += (size_t)KS * 4 + 256 + 64;                    // oc, om (<= 64 words), cpar
+    if (multi) b += 256 + 64;                                     // om (<= 64 words), cpar
     b += (size_t)R * KS * 4 + 128;                                // ring + mbarriers
     return (b + 127) & ~(size_t)127;
 }
 
-__device__ __forceinline__ void carve_warp(unsigned char *base, int KS, int R, bool multi, WarpCtx &c, int *&ring, unsigned long long *&mbar)
+__device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bool multi, DocCtx &c, int *&ring, unsigned long long *&mbar)
 {
     unsigned char *p = base;
     ring = reinterpret_cast<int *>(p); p += (size_t)R * KS * 4;
     c.q = reinterpret_cast<float *>(p); p += (size_t)KS * 4;
-    if (multi) { c.oc = reinterpret_cast<float *>(p); p += (size_t)KS * 4; } else c.oc = nullptr;
+    c.oc = nullptr;
     c.nd = reinterpret_cast<unsigned short *>(p); p += (size_t)KS * 2;
     if (multi) { c.om = reinterpret_cast<unsigned *>(p); p += 256; c.cpar = reinterpret_cast<float *>(p); p += 64; }
     else { c.om = nullptr; c.cpar = nullptr; }
@@ -354,33 +389,42 @@ __device__ __forceinline__ void carve_warp(unsigned char *base, int KS, int R, b
 // ------------------------------------------------------------------------------------------------
 // THE sweep kernel: one launch = one view pass over all documents of the shard  (W:186-233, W:301-597, U:197-218)
 // ------------------------------------------------------------------------------------------------
-constexpr int sweep_max_threads(int J) { return J <= 4 ? 768 : (J <= 8 ? 512 : 384); }
+__host__ __device__ constexpr int sweep_max_threads(int JG) { return JG <= 8 ? 768 : 512; }
 
-template <int J, bool MULTI>
-__global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const SweepParams P)
+template <int KS, int G, bool MULTI>
+__global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_view(const SweepParams P)
 {
-    constexpr int KS = J * 128;
+    constexpr int JG = KS / (4 * G), NSUB = 32 / G;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / G, gl = lane % G;
     const int R = P.R;
 
-    float2 *ginv = reinterpret_cast<float2 *>(smem);
-    int *dnk = reinterpret_cast<int *>(smem + (size_t)KS * 8);
-    for (int t = threadIdx.x; t < KS; t += blockDim.x) {
-        float2 g = make_float2(0.f, 0.f);
-        if (t < P.K) { g.x = __ldg(P.ga_tree + t); g.y = 1.0f / ((float)__ldg(P.nk_frozen + t) + P.betaSum); }
-        ginv[t] = g;                                              // topics >= K get weight 0
-        dnk[t] = 0;
+    {
+        float2 *ginv = reinterpret_cast<float2 *>(smem);
+        int *dnk = reinterpret_cast<int *>(smem + (size_t)KS * 8);
+        for (int t = threadIdx.x; t < KS; t += blockDim.x) {
+            float2 g = make_float2(0.f, 0.f);
+            if (t < P.K) { g.x = __ldg(P.ga_tree + t); g.y = 1.0f / ((float)__ldg(P.nk_frozen + t) + P.betaSum); }
+            ginv[t] = g;                                              // topics >= K get weight 0
+            dnk[t] = 0;
+        }
+        if (MULTI) {
+            float *gaf = reinterpret_cast<float *>(smem + (size_t)KS * 12);
+            for (int i = 0; i < P.M; i++)
+                for (int t = threadIdx.x; t < KS; t += blockDim.x) gaf[(size_t)i * KS + t] = (t < P.K) ? __ldg(P.ga_full[i] + t) : 0.f;
+        }
     }
-    WarpCtx c; int *ring; unsigned long long *mbar;
-    carve_warp(smem + smem_cta_bytes(KS) + (size_t)warp * smem_warp_bytes(KS, R, MULTI), KS, R, MULTI, c, ring, mbar);
-    c.ginv = ginv;
+    DocCtx c; int *ring; unsigned long long *mbar;
+    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(warp * NSUB + sub) * smem_doc_bytes(KS, R, MULTI), KS, R, MULTI, c, ring, mbar);
+    c.gaf = reinterpret_cast<const float *>(smem + (size_t)KS * 12); c.gaf_stride = KS;
+    if (MULTI) c.oc = P.oc_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) * NSUB + (size_t)(warp * NSUB + sub)) * P.Kp;
     uint32_t cta_sa = smem_u32(smem);
     asm volatile("" : "+r"(cta_sa));                              // opaque: hold the base in a register
     c.ginv_sa = cta_sa;
     const uint32_t dnk_sa = cta_sa + (uint32_t)KS * 8u;
-    if (lane == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
-    for (int k = lane; k < R * KS; k += 32) ring[k] = 0;
+    if (gl == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
+    for (int k = gl; k < R * KS; k += G) ring[k] = 0;
     fence_proxy_async();
     __syncthreads();
 
@@ -390,143 +434,156 @@ __global__ void __launch_bounds__(sweep_max_threads(J), 1) k_sweep_view(const Sw
     unsigned long long n_tok = 0, n_changed = 0, n_new = 0;
     const int m = P.m;
     int *zmv = P.zv[m];
-    float bsq[J];
+    float bsq[JG];
 
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(P.work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= P.n_items) break;
-        const int d = __ldg(P.order + item);
+        int item0 = 0;
+        if (lane == 0) item0 = atomicAdd(P.work_counter, NSUB);
+        item0 = __shfl_sync(FULL, item0, 0);
+        if (item0 >= P.n_items) break;
+        const bool have = item0 + sub < P.n_items;                 // the last fetch may leave trailing groups idle
+        const int d = have ? __ldg(P.order + item0 + sub) : 0;
         const long long b = P.doc_off[m][d];
-        const int len = (int)(P.doc_off[m][d + 1] - b);
+        const int len = have ? (int)(P.doc_off[m][d + 1] - b) : 0;
+        const int maxlen = (NSUB == 1) ? len : __reduce_max_sync(FULL, len);
         const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
 
         // first block of tokens; rows of the first R tokens go in flight before the per-document setup
-        int wcur = (lane < len) ? __ldg(P.word + b + lane) : 0;
-        int zcur = (lane < len) ? zmv[b + lane] : -1;
-        int wnext = (32 + lane < len) ? __ldg(P.word + b + 32 + lane) : 0;
-        int wahead = (R + lane < len) ? __ldg(P.word + b + R + lane) : 0;        // word of the token R positions ahead
-        {
-            const int npre = len < R ? len : R;
-            for (int i = 0; i < npre; i++) {
-                int w = __shfl_sync(0xffffffffu, wcur, i);
-                if ((unsigned)w >= (unsigned)P.V) w = 0;
-                if (lane == 0) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
-            }
+        int wcur = (gl < len) ? __ldg(P.word + b + gl) : 0;
+        int zcur = (gl < len) ? zmv[b + gl] : -1;
+        int wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
+        int wahead = (R + gl < len) ? __ldg(P.word + b + R + gl) : 0;        // word of the token R positions ahead
+        for (int i = 0; i < R; i++) {
+            int w = __shfl_sync(FULL, wcur, i, G);
+            if ((unsigned)w >= (unsigned)P.V) w = 0;
+            if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
-        warp_setup<J, MULTI>(P, c, d, lane, nullptr, bsq);
+        doc_setup<KS, G, MULTI>(P, c, d, len, gl, nullptr, true, bsq);
 
         int slot = 0;
-        for (int base = 0; base < len; base += 32) {
-            const int nblk = (len - base) < 32 ? (len - base) : 32;
-            // one Philox call per lane covers the 32 tokens of the block
-            const uint4 rnd = philox4x32_10((uint32_t)(base + lane), gdoc, P.iteration, ((uint32_t)m << 8) | PURPOSE_SAMPLE, P.seed_lo, P.seed_hi);
+        for (int base = 0; base < maxlen; base += G) {
+            const int nblk = min(max(len - base, 0), G);            // tokens of my document in this block
+            const int nblk_max = min(maxlen - base, G);             // uniform trip count of the warp
+            // one Philox call per lane covers the G tokens of the block
+            const uint4 rnd = philox4x32_10((uint32_t)(base + gl), gdoc, P.iteration, ((uint32_t)m << 8) | PURPOSE_SAMPLE, P.seed_lo, P.seed_hi);
             const float umine = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
             // zeff: topic (>= 0), -1 = UNASSIGNED_TOPIC, -2 = out-of-vocabulary word: the token is skipped and neither
             // leaves nor joins n_d (W:427-428)
             const int zeff = ((unsigned)wcur < (unsigned)P.V) ? zcur : -2;
             int znew = zcur;
-            {   // the first token of the block leaves its topic (W:434-471); later tokens do so paired with the
-                // previous token's increment
-                const int ot0 = __shfl_sync(0xffffffffu, zeff, 0);
-                apply_pair<J, MULTI>(P, c, -1, ot0 >= 0 ? ot0 : -1, lane, bsq);
-                __syncwarp();
-            }
-            for (int i = 0; i < nblk; i++) {
-                const int w = __shfl_sync(0xffffffffu, wcur, i);
-                const int ot = __shfl_sync(0xffffffffu, zeff, i);
-                const float u = __shfl_sync(0xffffffffu, umine, i);
-                const int otn = __shfl_sync(0xffffffffu, zeff, (i + 1) & 31);
-                const bool valid = (ot != -2);
-                const int ia = i + R;
-                int wa = __shfl_sync(0xffffffffu, wahead, i);             // word of token base+i+R (ring refill)
-                mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
-                phasebits ^= 1u << slot;
-                int nt = ot;
-                if (valid) {
-                    nt = warp_select<J>(reinterpret_cast<const int4 *>(ring + (size_t)slot * KS), reinterpret_cast<const float4 *>(c.q),
-                                        lane, P.beta, bsq, u, c.C);
-                    if (nt < 0) { nt = P.first_inactive; n_new++; }          // W:522-526
+            // first token of the NEXT block: it leaves its topic (W:434-471) paired with this block's last increment
+            // (the document's very first token was left out of n_d by doc_setup)
+            const int znext = (base + G < len) ? zmv[b + base + G] : -1;
+            const int wnext0 = __shfl_sync(FULL, wnext, 0, G);
+            const int ot_nextblk = ((unsigned)wnext0 < (unsigned)P.V && base + G < len) ? znext : -1;
+            for (int i = 0; i < nblk_max; i++) {
+                const bool act = i < nblk;
+                const int w = __shfl_sync(FULL, wcur, i, G);
+                const int ot = __shfl_sync(FULL, zeff, i, G);
+                const float u = __shfl_sync(FULL, umine, i, G);
+                int otn = __shfl_sync(FULL, zeff, (i + 1) & (G - 1), G);
+                if (i + 1 == G) otn = ot_nextblk;
+                int wa = __shfl_sync(FULL, wahead, i, G);                      // word of token base+i+R (ring refill)
+                const bool valid = act && (ot != -2);
+                if (act) {
+                    mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
+                    phasebits ^= 1u << slot;
                 }
                 __syncwarp();
+                int nt = group_select<JG, G>(reinterpret_cast<const int4 *>(ring + (size_t)slot * KS), reinterpret_cast<const float4 *>(c.q),
+                                             lane, gl, P.beta, bsq, u, c.C);
+                if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
+                else nt = ot;
+                __syncwarp();
                 // slot consumed: refill it with the row of token base+i+R
-                if (base + ia < len && lane == 0) {
+                if (act && gl == 0 && base + i + R < len) {
                     if ((unsigned)wa >= (unsigned)P.V) wa = 0;
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
-                apply_pair<J, MULTI>(P, c, valid ? nt : -1, (i + 1 < nblk && otn >= 0) ? otn : -1, lane, bsq);
+                apply_pair<KS, G, MULTI>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
                 if (valid) {
                     if (nt != ot && P.update_global) {                       // U:197-218
-                        const int tsel = (lane & 1) ? ot : nt, v = (lane & 1) ? -1 : 1;
+                        const int tsel = (gl & 1) ? ot : nt, v = (gl & 1) ? -1 : 1;
                         if (tsel >= 0) {
-                            if (lane < 2) atomicAdd(P.nwk + (size_t)w * P.Kp + tsel, v);
-                            else if (lane < 4) reds_add(dnk_sa + 4u * (uint32_t)tsel, v);
+                            if (gl < 2) atomicAdd(P.nwk + (size_t)w * P.Kp + tsel, v);
+                            else if (gl < 4) reds_add(dnk_sa + 4u * (uint32_t)tsel, v);
                         }
                     }
                     n_changed += (nt != ot);
                     n_tok++;
-                    if (lane == i) znew = nt;
+                    if (gl == i) znew = nt;
                 }
                 __syncwarp();
-                slot = (slot + 1 == R) ? 0 : slot + 1;
+                if (act) slot = (slot + 1 == R) ? 0 : slot + 1;
             }
-            if (lane < nblk) zmv[b + base + lane] = znew;
+            if (gl < nblk) zmv[b + base + gl] = znew;
             wcur = wnext;
-            wahead = (base + 32 + R + lane < len) ? __ldg(P.word + b + base + 32 + R + lane) : 0;
-            zcur = (base + 32 + lane < len) ? zmv[b + base + 32 + lane] : -1;
-            wnext = (base + 64 + lane < len) ? __ldg(P.word + b + base + 64 + lane) : 0;
+            wahead = (base + G + R + gl < len) ? __ldg(P.word + b + base + G + R + gl) : 0;
+            zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;
+            wnext = (base + 2 * G + gl < len) ? __ldg(P.word + b + base + 2 * G + gl) : 0;
         }
     }
-    if (lane == 0) {
+    if (gl == 0) {
         if (n_tok) atomicAdd(P.stats + 0, n_tok);
         if (n_changed) atomicAdd(P.stats + 1, n_changed);
         if (n_new) atomicAdd(P.stats + 2, n_new);
     }
     __syncthreads();
-    if (P.update_global)
+    if (P.update_global) {
+        const int *dnk = reinterpret_cast<const int *>(smem + (size_t)KS * 8);
         for (int t = threadIdx.x; t < P.K; t += blockDim.x) { int v = dnk[t]; if (v) atomicAdd(P.nk_live + t, v); }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// parity probe: conditional of one token on frozen counts, same device functions as the sweep
+// parity probe: conditional of one token on frozen counts, same device functions as the sweep.  One warp; every lane
+// group works on the same document in its own shared-memory area, group 0 writes the result.
 // ------------------------------------------------------------------------------------------------
-template <int J, bool MULTI>
+template <int KS, int G, bool MULTI>
 __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d, int pos, const double *p_row, double *out)
 {
-    constexpr int KS = J * 128;
+    constexpr int JG = KS / (4 * G);
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x, sub = lane / G, gl = lane % G;
     float2 *ginv = reinterpret_cast<float2 *>(smem);
     for (int t = lane; t < KS; t += 32) {
         float2 g = make_float2(0.f, 0.f);
         if (t < P.K) { g.x = P.ga_tree[t]; g.y = 1.0f / ((float)P.nk_frozen[t] + P.betaSum); }
         ginv[t] = g;
     }
-    WarpCtx c; int *ring; unsigned long long *mbar;
-    carve_warp(smem + smem_cta_bytes(KS), KS, 1, MULTI, c, ring, mbar);
-    c.ginv = ginv;
-    c.ginv_sa = smem_u32(smem);
-    __syncwarp();
-    float bsq[J];
-    warp_setup<J, MULTI>(P, c, d, lane, p_row, bsq);
-    const long long b = P.doc_off[P.m][d];
-    const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
-    apply_pair<J, MULTI>(P, c, -1, ot, lane, bsq);
-    for (int t = lane; t < KS; t += 32) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
-    __syncwarp();
-    float cum[J];
-    float lt = lane_weights<J>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), lane, bsq, cum);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) lt += __shfl_xor_sync(0xffffffffu, lt, off);
-    const float total = lt + c.C;
-    for (int t = lane; t < P.K; t += 32) {
-        float wgt = topic_weight(ring[t], c.q[t], P.beta);
-        if (c.C > 0.f && t == P.first_inactive) wgt += c.C;
-        out[t] = (double)(wgt / total);
+    if (MULTI) {
+        float *gaf = reinterpret_cast<float *>(smem + (size_t)KS * 12);
+        for (int i = 0; i < P.M; i++)
+            for (int t = lane; t < KS; t += 32) gaf[(size_t)i * KS + t] = (t < P.K) ? P.ga_full[i][t] : 0.f;
     }
-    if (lane == 0) out[P.K] = (double)(c.C / total);
+    DocCtx c; int *ring; unsigned long long *mbar;
+    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)sub * smem_doc_bytes(KS, 1, MULTI), KS, 1, MULTI, c, ring, mbar);
+    c.gaf = reinterpret_cast<const float *>(smem + (size_t)KS * 12); c.gaf_stride = KS;
+    c.ginv_sa = smem_u32(smem);
+    if (MULTI) c.oc = P.oc_scratch + (size_t)sub * P.Kp;
+    __syncwarp();
+    float bsq[JG];
+    const long long b = P.doc_off[P.m][d];
+    const int len = (int)(P.doc_off[P.m][d + 1] - b);
+    doc_setup<KS, G, MULTI>(P, c, d, len, gl, p_row, false, bsq);
+    const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
+    apply_pair<KS, G, MULTI>(P, c, -1, ot, gl, bsq);
+    for (int t = gl; t < KS; t += G) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
+    __syncwarp();
+    float cum[JG];
+    float lt = lane_weights<JG, G>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), gl, bsq, cum);
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) lt += __shfl_xor_sync(FULL, lt, off, G);
+    const float total = lt + c.C;
+    if (sub == 0) {
+        for (int t = gl; t < P.K; t += G) {
+            float wgt = topic_weight(ring[t], c.q[t], P.beta);
+            if (c.C > 0.f && t == P.first_inactive) wgt += c.C;
+            out[t] = (double)(wgt / total);
+        }
+        if (gl == 0) out[P.K] = (double)(c.C / total);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

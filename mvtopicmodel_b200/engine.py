@@ -149,6 +149,11 @@ class Engine:
         self._ck(self.L.mvtm_row_stride(self.h, C.byref(s)))
         return s.value
 
+    def scan_layout(self):
+        g, j = C.c_int32(), C.c_int32()
+        self._ck(self.L.mvtm_scan_layout(self.h, C.byref(g), C.byref(j)))
+        return g.value, j.value
+
     def delta_begin(self):
         self._ck(self.L.mvtm_delta_begin(self.h))
 

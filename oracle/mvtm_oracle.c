@@ -63,6 +63,7 @@ typedef struct {
     int n_inactive;
     int32_t *inactive;               /* ascending topic ids */
     uint64_t seed;
+    int engine_G;                    /* lanes per document-view of the engine's scan (mvtm_scan_layout) */
     int64_t doc_base, doc_stride;    /* global id of local document d = doc_base + d*doc_stride (keys the RNG) */
     int64_t cnt_new, cnt_doc, cnt_tree, cnt_changed;   /* W:33-35 bucket counters */
     char err[256];
@@ -182,7 +183,7 @@ orc_t *orc_create(int M, int K, int64_t D, const int32_t *V, uint64_t seed)
 {
     if (M < 1 || M > ORC_MAXM || K < 1 || D < 0) return NULL;
     orc_t *o = (orc_t *)calloc(1, sizeof(orc_t));
-    o->M = M; o->K = K; o->D = D; o->seed = seed; o->doc_base = 0; o->doc_stride = 1;
+    o->M = M; o->K = K; o->D = D; o->seed = seed; o->doc_base = 0; o->doc_stride = 1; o->engine_G = 32;
     o->inactive = (int32_t *)calloc((size_t)K, sizeof(int32_t));
     for (int m = 0; m < M; m++) {
         o->V[m] = V[m];
@@ -556,10 +557,16 @@ static void emit_deferred(void *c, const orc_delta *d)
 /* engine-mirror sampler: the engine's target distribution (SURVEY Appendix A "net distribution")     */
 /* evaluated densely in fp64, scanned in the engine's lane-major order with the same Philox uniform.   */
 /* ------------------------------------------------------------------------------------------------ */
-static inline int engine_order_topic(int idx, int J)
-{   /* idx-th topic in scan order: lane-major over (lane, j, e); topic = 4*(lane + 32*j) + e */
-    int e = idx & 3, j = (idx >> 2) % J, lane = (idx >> 2) / J;
-    return 4 * (lane + 32 * j) + e;
+static inline int engine_order_topic(int idx, int JG, int G)
+{   /* idx-th topic in scan order: lane-major over (lane, j, e); topic = 4*(lane + G*j) + e */
+    int e = idx & 3, j = (idx >> 2) % JG, lane = (idx >> 2) / JG;
+    return 4 * (lane + G * j) + e;
+}
+static int engine_slot_size(int K)
+{   /* the engine's slot sizes: 128 * {1,2,3,4,6,8,12,16} */
+    static const int opts[] = { 1, 2, 3, 4, 6, 8, 12, 16 };
+    for (int i = 0; i < 8; i++) if (opts[i] * 128 >= K) return opts[i] * 128;
+    return ((K + 127) / 128) * 128;
 }
 
 /* unnormalised engine weights for token (d, m, pos) given local counts nd (own token already removed),
@@ -586,17 +593,17 @@ static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, cons
     }
 }
 
-int orc_engine_select(const double *wgt, int K, double u, double C, int first_inactive)
+int orc_engine_select_g(const double *wgt, int K, double u, double C, int first_inactive, int G)
 {   /* C bucket first (W:522), then a single scan in engine order; returns the topic */
-    int J = (K + 127) / 128, n = J * 128;
+    int n = engine_slot_size(K), J = n / (4 * G);
     double total = 0;
-    for (int idx = 0; idx < n; idx++) { int t = engine_order_topic(idx, J); if (t < K) total += wgt[t]; }
+    for (int idx = 0; idx < n; idx++) { int t = engine_order_topic(idx, J, G); if (t < K) total += wgt[t]; }
     double s = u * (total + C);
     if (s < C) return first_inactive;
     s -= C;
     double cum = 0; int last = -1;
     for (int idx = 0; idx < n; idx++) {
-        int t = engine_order_topic(idx, J);
+        int t = engine_order_topic(idx, J, G);
         if (t >= K) continue;
         cum += wgt[t];
         if (wgt[t] > 0) last = t;
@@ -604,6 +611,10 @@ int orc_engine_select(const double *wgt, int K, double u, double C, int first_in
     }
     return last;
 }
+
+int orc_engine_select(const double *wgt, int K, double u, double C, int first_inactive)
+{ return orc_engine_select_g(wgt, K, u, C, first_inactive, 32); }
+void orc_set_engine_group(orc_t *o, int G) { o->engine_G = G; }
 
 static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, unsigned flags, orc_scratch *s,
                                   const int32_t *nk_frozen, int32_t *dnk, int64_t cnt[4])
@@ -632,7 +643,7 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
         engine_weights(o, m, w, s->nd, len, p, nk_frozen, s->cum);
         uint32_t x[4];
         orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
-        int new_t = orc_engine_select(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1);
+        int new_t = orc_engine_select_g(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1, o->engine_G);
         o->z[m][b + pos] = new_t;
         s->nd[m * K + new_t]++;
         if (new_t != old_t && !(flags & ORC_F_FROZEN)) {   /* n_wk live, n_k deferred to the end of the view pass (engine semantics) */

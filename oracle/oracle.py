@@ -52,6 +52,7 @@ def lib():
             "orc_get_counts": (i32, [p, i32, p, p]),
             "orc_maxlen": (i32, [p, i32]),
             "orc_set_doc_ids": (None, [p, i64, i64]),
+            "orc_set_engine_group": (None, [p, i32]),
             "orc_set_counts": (i32, [p, i32, p, p]),
             "orc_get_hist": (i32, [p, i32, p]),
             "orc_get_alpha": (i32, [p, i32, p]),
@@ -181,6 +182,10 @@ class Oracle:
         nk = np.zeros(self.K, dtype=np.int32)
         lib().orc_get_counts(self.h, m, _ptr(nwk), _ptr(nk))
         return nwk, nk
+
+    def set_engine_group(self, lanes_per_doc):
+        """scan layout of the engine under test (Engine.scan_layout()[0]) for the F_ENGINE_MIRROR mode"""
+        lib().orc_set_engine_group(self.h, int(lanes_per_doc))
 
     def set_doc_ids(self, base, stride):
         lib().orc_set_doc_ids(self.h, int(base), int(stride))

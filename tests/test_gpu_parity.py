@@ -154,10 +154,9 @@ def test_conditionals_with_inactive_topics_and_sparse_view(engine_lib, oracle_mo
     assert len(ina) <= len(inactive)
 
 
-def _scan_rank(K):
-    """position of every topic in the engine's lane-major scan order (mvtm_kernels.cuh warp_select)."""
-    J = (K + 127) // 128
-    order = [4 * ((i >> 2) // J + 32 * ((i >> 2) % J)) + (i & 3) for i in range(J * 128)]
+def _scan_rank(K, G, JG):
+    """position of every topic in the engine's lane-major scan order (mvtm_scan_layout / group_select)."""
+    order = [4 * ((i >> 2) // JG + G * ((i >> 2) % JG)) + (i & 3) for i in range(4 * G * JG)]
     order = [t for t in order if t < K]
     rank = np.empty(K, dtype=np.int64)
     rank[order] = np.arange(K)
@@ -177,7 +176,9 @@ def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means)
     views = random_corpus(K + 3, 400, K, Vs, means)
     e, o = make_pair(O, K, Vs, views, seed=77)
     e.init_assignments(); o.init_assignments()
-    rank = _scan_rank(K)
+    G, JG = e.scan_layout()
+    o.set_engine_group(G)
+    rank = _scan_rank(K, G, JG)
     D = len(views[0][0]) - 1
     for it in (1, 2):
         if M > 1:

@@ -18,13 +18,22 @@ def run(name, cfg, grid, sweeps=6, warm=2):
                 ms.append(e.stats()["ms_total"])
         bad = e.check_invariants()
         print(json.dumps({"cfg": name, "W": W, "R": R, "ms": round(float(np.mean(ms)), 3), "min_ms": round(float(np.min(ms)), 3),
-                          "Gtok_s": round(ntok / np.mean(ms) / 1e6, 3), "viol": bad}), flush=True)
+                          "Gtok_s": round(ntok / np.mean(ms) / 1e6, 3), "viol": bad, "ms_view": [round(x, 3) for x in e.stats()["ms_view"]],
+                          "tok_view": e.ntok}), flush=True)
         e.close()
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "lda"
     if which in ("lda", "all"):
-        run("lda_100k", "lda_100k", [(16, 4), (19, 4), (20, 3), (23, 3), (24, 2), (16, 2), (12, 4), (8, 4)])
+        run("lda_100k", "lda_100k", [(0, 2), (0, 1), (16, 1), (12, 1)])
+    if which in ("acmtext",):
+        cfg = dict(D=400_000, K=1000, views=[(100_000, 120, 0.5, 1.0, 1024)])
+        run("acm_text_only", cfg, [(0, 0)], sweeps=4, warm=1)
+    if which in ("acm",):
+        run("acm_2v", "acm_2v", [(0, 0), (16, 1), (12, 3)], sweeps=4, warm=1)
+    if which in ("pubmed",):
+        cfg = dict(corpus.CONFIGS["pubmed_3v"]); cfg["D"] = 250_000
+        run("pubmed_3v_quarter", cfg, [(0, 0), (16, 1)], sweeps=4, warm=1)
     if which in ("k1000", "all"):
         cfg = dict(D=100_000, K=1000, views=[(200_000, 200, 0.6, 1.0, 2048)])
-        run("k1000_v200k", cfg, [(16, 2), (12, 3), (10, 4), (8, 5), (8, 3), (6, 6), (16, 1)])
+        run("k1000_v200k", cfg, [(0, 2), (0, 1)])
