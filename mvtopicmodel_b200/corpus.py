@@ -110,6 +110,15 @@ def generate(name_or_cfg, seed=20261018, shard=0, docs=None, support=2048):
     return K, Vs, views
 
 
+def generate_uniform(D, K, V, mean_len, seed=7):
+    """Worst case for the cache hierarchy: words drawn uniformly from V (no Zipf head), fixed-length documents.
+    Every token then reads a different n_wk row, so the sweep is genuinely HBM-bound once V*K*4 >> L2."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    off = np.arange(D + 1, dtype=np.int64) * int(mean_len)
+    words = rng.integers(0, V, size=int(off[-1]), dtype=np.int32)
+    return K, [V], [(off, words)]
+
+
 def shard_views(views, rank, world):
     """Documents rank, rank+world, ... of every view (all views of a document stay together)."""
     out = []

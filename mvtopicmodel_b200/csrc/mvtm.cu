@@ -30,6 +30,8 @@ struct ViewDev {
     float *ga_tree = nullptr, *ga_full = nullptr;
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
+    int tune_step = 0, ring_locked = 0;             // ring-depth autotune over the first sweeps (see ring_for_view)
+    float tune_ms[4] = { 0.f, 0.f, 0.f, 0.f };
 };
 
 }  // namespace
@@ -422,12 +424,29 @@ static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
 
 struct LaunchCfg { int R, W, grid; size_t smem; };
 
-static int choose_launch(mvtm_handle *h, LaunchCfg &lc)
+// Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first four timed sweeps
+// alternate R = 1, 2, 1, 2 and the faster of the last two is kept: cache-resident tables (Zipf corpora) favour R = 1
+// (more resident documents), genuinely HBM-bound ones R = 2 (the row fetch latency is then worth a slot).
+static int ring_for_view(mvtm_handle *h, int m)
+{
+    if (h->cfg_ring > 0) return h->cfg_ring;
+    if (const char *e = getenv("MVTM_RING")) return atoi(e);
+    ViewDev &v = h->v[m];
+    if (v.ring_locked) return v.ring_locked;
+    return (v.tune_step & 1) ? 2 : 1;
+}
+static void ring_record(mvtm_handle *h, int m, float ms)
+{
+    ViewDev &v = h->v[m];
+    if (h->cfg_ring > 0 || getenv("MVTM_RING") || v.ring_locked) return;
+    v.tune_ms[v.tune_step & 3] = ms;
+    if (++v.tune_step == 4) v.ring_locked = (v.tune_ms[3] < v.tune_ms[2]) ? 2 : 1;
+}
+
+static int choose_launch(mvtm_handle *h, int R, LaunchCfg &lc)
 {
     const int KS = h->KS, G = h->G, NSUB = 32 / G, JG = KS / (4 * G);
     const bool multi = h->M > 1;
-    int R = h->cfg_ring > 0 ? h->cfg_ring : 1;        // measured: more resident documents beat a deeper ring
-    if (const char *e = getenv("MVTM_RING")) R = atoi(e);
     R = std::max(1, std::min(R, 8));
     const size_t budget = 227 * 1024 - 1024;
     int docs;
@@ -511,9 +530,11 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
     if (int rc = require_views(h, "mvtm_sweep")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = upload_hyper(h)) return rc;
-    LaunchCfg lc;
-    if (int rc = choose_launch(h, lc)) return rc;
-    if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
+    LaunchCfg lcs[MVTM_MAX_VIEWS];
+    for (int m = 0; m < h->M; m++) {
+        if (int rc = choose_launch(h, ring_for_view(h, m), lcs[m])) return rc;
+        if (int rc = ensure_oc_scratch(h, (size_t)lcs[m].grid * lcs[m].W * (32 / h->G))) return rc;
+    }
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(h, cudaEventRecord(h->ev[0], h->stream));
     int launches = 0;
@@ -525,8 +546,8 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
             CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
             SweepParams P;
             fill_params(h, m, iteration, update_global, P);
-            P.R = lc.R;
-            CK(h, launch_sweep(h, P, lc));
+            P.R = lcs[m].R;
+            CK(h, launch_sweep(h, P, lcs[m]));
             launches++;
         }
         CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
@@ -540,7 +561,11 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
         float ms = 0.f;
         CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
         h->stats.ms_total = ms;
-        for (int m = 0; m < h->M; m++) { CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m])); h->stats.ms_view[m] = ms; }
+        for (int m = 0; m < h->M; m++) {
+            CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m]));
+            h->stats.ms_view[m] = ms;
+            if (h->v[m].n_items > 0) ring_record(h, m, ms);
+        }
         h->stats.kernel_launches = launches;
         if (update_global) if (int rc = activate_sampled_topics(h)) return rc;
     }

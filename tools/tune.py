@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvtopicmodel_b200 import Engine, corpus
 
 def run(name, cfg, grid, sweeps=6, warm=2):
-    K, Vs, views = corpus.generate(cfg)
+    K, Vs, views = cfg if isinstance(cfg, tuple) else corpus.generate(cfg)
     ntok = sum(len(v[1]) for v in views)
     print(f"== {name}: K={K} V={Vs} tokens={ntok}", flush=True)
     for (W, R) in grid:
@@ -26,6 +26,9 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "lda"
     if which in ("lda", "all"):
         run("lda_100k", "lda_100k", [(0, 2), (0, 1), (16, 1), (12, 1)])
+    if which in ("uniform",):
+        run("uniform_k1000_v400k", corpus.generate_uniform(100_000, 1000, 400_000, 200), [(0, 1), (0, 2), (0, 3)], sweeps=4, warm=1)
+        run("uniform_k500_v400k", corpus.generate_uniform(100_000, 500, 400_000, 200), [(0, 1), (0, 2), (0, 3)], sweeps=4, warm=1)
     if which in ("acmtext",):
         cfg = dict(D=400_000, K=1000, views=[(100_000, 120, 0.5, 1.0, 1024)])
         run("acm_text_only", cfg, [(0, 0)], sweeps=4, warm=1)
