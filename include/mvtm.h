@@ -144,6 +144,29 @@ int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out);
  * cumulative scan runs lane-major (all chunks of lane 0, then lane 1, ...). */
 int mvtm_scan_layout(mvtm_handle *h, int32_t *lanes_per_doc, int32_t *chunks_per_lane);
 
+/* ---- hyper-parameter step of estimate() (M:1173-1210), SURVEY 8(f) rank 1 -------------------------------------------
+ * mvtm_optimize_hyper runs, in the reference's order, the selected parts of
+ *   optimizeP (M:2698-2819), optimizeDP (M:2440-2591), optimizeGamma (M:2369-2438), optimizeBeta (M:2288-2367)
+ * on the host from statistics computed on the device, and installs the new alpha / alphaSum / beta / betaSum / gamma /
+ * p_a / p_b / inactive-topic set in the handle (the F+trees the reference rebuilds at M:1209 are implicit here).
+ * Draws come from the handle's Philox stream keyed on `iteration`.  mvtm_p_statistics exposes optimizeP's sufficient
+ * statistic: psum[m*M+i] = sum over documents of pDistr_Mean[m][i][doc] (M:2706-2782), docs_per_view = totalDocsPerModality. */
+#define MVTM_OPT_P     1u
+#define MVTM_OPT_DP    2u
+#define MVTM_OPT_GAMMA 4u
+#define MVTM_OPT_BETA  8u
+#define MVTM_OPT_ALL   15u
+int mvtm_optimize_hyper(mvtm_handle *h, int32_t iteration, uint32_t which);
+int mvtm_p_statistics(mvtm_handle *h, double *psum_out, int64_t *docs_per_view_out);
+int mvtm_get_hyper_full(mvtm_handle *h, double *alpha, double *alpha_sum, double *beta, double *beta_sum, double *gamma,
+                        double *p_a, double *p_b, double *p_mean, double *gamma_root, double *gamma_view, double *tables_cnt);
+
+/* Test hooks for the host-side samplers of the hyper-parameter step (no device work): `which` 0 = uniform, 1 = Gamma(a,1),
+ * 2 = Beta(a,b), 3 = Antoniak(alpha = a, n = b); and MALLET's learnSymmetricConcentration as restated in this build. */
+int mvtm_test_sampler(uint64_t seed, int32_t which, double a, double b, int32_t n, double *out);
+double mvtm_test_learn_symmetric_concentration(const int64_t *count_hist, int32_t n_count, const int64_t *length_hist,
+                                               int32_t n_length, int32_t num_dimensions, double current);
+
 /* Build information: "sm_100a", kernel variants compiled in. */
 const char *mvtm_build_info(void);
 

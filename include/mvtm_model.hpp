@@ -107,12 +107,16 @@ public:
     {
         if (!h_) throw std::logic_error("addInstances must be called before estimate");
         std::fill(p_a.begin(), p_a.end(), 0.2); std::fill(p_b.begin(), p_b.end(), 1.0);     // M:1055-1058
+        pushHyper();
         for (int iteration = 1; iteration <= numIterations; iteration++) {
             if (iteration < burninPeriod && numModalities > 1)
                 std::fill(p_a.begin(), p_a.end(), std::min(iteration / 100.0 + 0.3, 1.1));  // M:1166-1169
-            // iteration > burninPeriod && iteration % optimizeInterval == 0: optimizeP/DP/Gamma/Beta (M:1173-1210) --
-            // host-side "next" work, fed by mvtm_doc_topic_hist / mvtm_get_counts.
-            pushHyper();
+            else if (iteration > burninPeriod && optimizeInterval != 0 && iteration % optimizeInterval == 0) {
+                // optimizeP, optimizeDP, optimizeGamma, optimizeBeta + buildFTrees(false), M:1173-1210
+                ck(mvtm_optimize_hyper(h_, iteration, MVTM_OPT_ALL));
+                pullHyper();
+            }
+            if (iteration < burninPeriod && numModalities > 1) pushHyper();
             ck(mvtm_sweep(h_, iteration, 1));
             if (iteration % 10 == 0 && iteration / 10 < 200) {                               // M:1296-1304
                 std::vector<double> ll = modelLogLikelihood();
@@ -138,6 +142,11 @@ public:
 private:
     mvtm_handle *h_ = nullptr;
     void ck(int rc) { if (rc) throw std::runtime_error(std::string("mvtm status ") + std::to_string(rc) + ": " + mvtm_last_error(h_)); }
+    void pullHyper()
+    {
+        ck(mvtm_get_hyper_full(h_, alpha.data(), alphaSum.data(), beta.data(), betaSum.data(), gamma.data(), p_a.data(), p_b.data(),
+                               nullptr, nullptr, nullptr, nullptr));
+    }
     void pushHyper()
     {
         ck(mvtm_set_hyper(h_, alpha.data(), alphaSum.data(), beta.data(), betaSum.data(), gamma.data(), p_a.data(), p_b.data(), nullptr, -1));

@@ -25,6 +25,7 @@ class MvtmSweepStats(C.Structure):
 
 FLAG_DOC_ORDER = 1
 FLAG_SINGLE_WARP = 2
+OPT_P, OPT_DP, OPT_GAMMA, OPT_BETA, OPT_ALL = 1, 2, 4, 8, 15
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 # name -> (restype, argtypes); must list every function include/mvtm.h declares (tests check this)
@@ -52,6 +53,11 @@ SIGNATURES = {
     "mvtm_delta_import": (_i32, [_vp, _i32]),
     "mvtm_row_stride": (_i32, [_vp, C.POINTER(_i32)]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),
+    "mvtm_p_statistics": (_i32, [_vp, _vp, _vp]),
+    "mvtm_get_hyper_full": (_i32, [_vp] + [_vp] * 11),
+    "mvtm_test_sampler": (_i32, [C.c_uint64, _i32, C.c_double, C.c_double, _i32, _vp]),
+    "mvtm_test_learn_symmetric_concentration": (C.c_double, [_vp, _i32, _vp, _i32, _i32, C.c_double]),
     "mvtm_build_info": (C.c_char_p, []),
 }
 

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -30,6 +31,7 @@ struct ViewDev {
     float *ga_tree = nullptr, *ga_full = nullptr;
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
+    std::vector<unsigned char> h_present;
     int tune_step = 0, ring_locked = 0;             // ring-depth autotune over the first sweeps (see ring_for_view)
     float tune_ms[4] = { 0.f, 0.f, 0.f, 0.f };
 };
@@ -50,6 +52,10 @@ struct mvtm_handle {
     double alphaSum[MVTM_MAX_VIEWS], beta[MVTM_MAX_VIEWS], betaSum[MVTM_MAX_VIEWS], gamma[MVTM_MAX_VIEWS];
     double p_a[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS], p_b[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS];
     std::vector<int> inactive;
+    // hierarchical-DP state of the hyper-parameter step (M:136-139): root/view concentrations and table counts
+    double gammaRoot = 10.0, rootTablesCnt = 0.0;
+    double gammaView[MVTM_MAX_VIEWS] = { 0 }, tablesCnt[MVTM_MAX_VIEWS] = { 0 };
+    double pMean[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS] = { { 0 } };
     bool hyper_dirty = true;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
@@ -234,6 +240,7 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMemcpy(v.doc_off, doc_off, (size_t)(D + 1) * 8, cudaMemcpyHostToDevice));
     if (N > 0) CK(h, cudaMemcpy(v.word, word_id, (size_t)N * 4, cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(v.present, pres.data(), pres.size(), cudaMemcpyHostToDevice));
+    v.h_present = pres;
     if (v.n_items) CK(h, cudaMemcpy(v.order, order.data(), (size_t)v.n_items * 4, cudaMemcpyHostToDevice));
     CK(h, cudaMemset(v.z, 0xff, (size_t)std::max<long long>(N, 1) * 4));       // UNASSIGNED_TOPIC
     CK(h, cudaMemset(v.nwk, 0, (size_t)v.V * Kp * 4));
@@ -849,3 +856,5 @@ extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
     CK(h, cudaStreamSynchronize(h->stream));
     return MVTM_OK;
 }
+
+#include "mvtm_optim.inl"

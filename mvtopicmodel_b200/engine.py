@@ -101,6 +101,27 @@ class Engine:
         self._ck(self.L.mvtm_get_hyper(self.h, _ptr(alpha), _ptr(asum), _ptr(ina), C.byref(n)))
         return alpha, asum, ina[:n.value].copy()
 
+    # --- hyper-parameter step (M:1173-1210) --------------------------------------------------------
+    def optimize_hyper(self, iteration, which=15):
+        self._ck(self.L.mvtm_optimize_hyper(self.h, int(iteration), int(which)))
+
+    def p_statistics(self):
+        psum = np.empty((self.M, self.M), dtype=np.float64)
+        docs = np.empty(self.M, dtype=np.int64)
+        self._ck(self.L.mvtm_p_statistics(self.h, _ptr(psum), _ptr(docs)))
+        return psum, docs
+
+    def get_hyper_full(self):
+        M, K = self.M, self.K
+        d = dict(alpha=np.empty((M, K + 1)), alphaSum=np.empty(M), beta=np.empty(M), betaSum=np.empty(M), gamma=np.empty(M),
+                 p_a=np.empty((M, M)), p_b=np.empty((M, M)), pMean=np.empty((M, M)), gammaRoot=np.empty(1), gammaView=np.empty(M),
+                 tablesCnt=np.empty(M))
+        self._ck(self.L.mvtm_get_hyper_full(self.h, *[_ptr(d[k]) for k in ("alpha", "alphaSum", "beta", "betaSum", "gamma", "p_a", "p_b",
+                                                                              "pMean", "gammaRoot", "gammaView", "tablesCnt")]))
+        d["gammaRoot"] = float(d["gammaRoot"][0])
+        d["inactive"] = self.get_hyper()[2]
+        return d
+
     # --- the hot path ----------------------------------------------------------------------------
     def sweep(self, iteration, update_global=True):
         self._ck(self.L.mvtm_sweep(self.h, int(iteration), int(bool(update_global))))

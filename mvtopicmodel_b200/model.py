@@ -63,6 +63,7 @@ class FastQMVWVParallelTopicModel:
         self.engine = None
         self.device = 0
         self.iterationsSoFar = 0
+        self.gammaRoot, self.gammaView, self.pMean, self.inActiveTopicIndex = 10.0, np.zeros(M), np.eye(M), []
         self.sweep_ms = []
 
     # ---- setters, M:273-335 ------------------------------------------------------------------------
@@ -120,12 +121,13 @@ class FastQMVWVParallelTopicModel:
         if self.engine is None:
             raise RuntimeError("addInstances must be called before estimate")
         self.p_a[:] = 0.2; self.p_b[:] = 1.0                                                        # M:1055-1058
+        self._push_hyper()
         for iteration in range(1, self.numIterations + 1):                                          # M:1146
             if iteration < self.burninPeriod and self.numModalities > 1:
                 self.p_a[:] = min(iteration / 100.0 + 0.3, 1.1)                                     # M:1166-1169
+                self._push_hyper()
             elif iteration > self.burninPeriod and self.optimizeInterval != 0 and iteration % self.optimizeInterval == 0:
                 self.optimizeHyperParameters(iteration)                                            # M:1173-1210
-            self._push_hyper()
             self.engine.sweep(iteration)                                                           # M:1213-1239
             self.sweep_ms.append(self.engine.stats()["ms_total"])
             if iteration % 10 == 0:                                                                # M:1296-1304
@@ -134,13 +136,26 @@ class FastQMVWVParallelTopicModel:
                     for m in range(self.numModalities):
                         self.perplexities[m, iteration // 10] = ll[m] / max(1, self.totalTokens[m])
             self.iterationsSoFar = iteration
-            alpha, alphaSum, _ = self.engine.get_hyper()      # topics activated by the sweep (U:263-270)
-            self.alpha, self.alphaSum = alpha, alphaSum
+            alpha, alphaSum, ina = self.engine.get_hyper()    # topics activated by the sweep (U:263-270)
+            self.alpha, self.alphaSum, self.inActiveTopicIndex = alpha, alphaSum, list(ina)
 
     def optimizeHyperParameters(self, iteration):
-        """optimizeP / optimizeDP / optimizeGamma / optimizeBeta (M:2288-2632, 2698-2819) run on the host from the
-        engine's exported statistics; they are SURVEY 8(f) rank-1 "next" work and not part of this path yet."""
-        return None
+        """optimizeP / optimizeDP / optimizeGamma / optimizeBeta in the reference's order (M:1173-1210), run by the engine's
+        host code from device statistics (mvtm_optimize_hyper); the new values are mirrored into this object."""
+        self.engine.optimize_hyper(iteration)
+        self._pull_hyper()
+
+    def optimizeP(self, appendMetadata=False):
+        self.engine.optimize_hyper(self.iterationsSoFar, 1); self._pull_hyper()
+
+    def optimizeBeta(self):
+        self.engine.optimize_hyper(self.iterationsSoFar, 8); self._pull_hyper()
+
+    def _pull_hyper(self):
+        hf = self.engine.get_hyper_full()
+        self.alpha, self.alphaSum, self.beta, self.betaSum, self.gamma = hf["alpha"], hf["alphaSum"], hf["beta"], hf["betaSum"], hf["gamma"]
+        self.p_a, self.p_b, self.pMean = hf["p_a"], hf["p_b"], hf["pMean"]
+        self.gammaRoot, self.gammaView, self.inActiveTopicIndex = hf["gammaRoot"], hf["gammaView"], list(hf["inactive"])
 
     # ---- readers ---------------------------------------------------------------------------------------
     def modelLogLikelihood(self, quirk_len2=False):

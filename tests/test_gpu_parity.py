@@ -419,3 +419,107 @@ def test_cpp_host_driver_runs(engine_lib, tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     print(r.stdout)
     assert r.returncode == 0 and "OK" in r.stdout
+
+
+# ---- hyper-parameter step ------------------------------------------------------------------------
+def test_p_statistics_match_oracle(engine_lib, oracle_mod):
+    """optimizeP's sufficient statistic (M:2706-2782, incl. the TreeMap collision rule Q11) vs the numpy restatement."""
+    from mvtopicmodel_b200 import Engine
+    from oracle import optim
+    K, Vs = 30, [200, 60, 40]
+    views = random_corpus(55, 400, K, Vs, [9, 4, 4], empty_frac=0.2)      # many equal-length views -> collisions
+    e = Engine(K, Vs, views, seed=4)
+    e.init_assignments()
+    for it in range(1, 4):
+        e.sweep(it)
+    zs = [e.get_assignments(m) for m in range(3)]
+    psum, docs = e.p_statistics()
+    want = optim.p_statistics(views, zs, K)
+    assert np.allclose(psum, want, rtol=1e-12, atol=1e-12)
+    assert np.allclose(psum, psum.T)
+    assert docs.tolist() == [int(((v[0][1:] - v[0][:-1]) > 0).sum()) for v in views]
+    e.optimize_hyper(50, 1)                                                 # optimizeP only
+    hf = e.get_hyper_full()
+    pa, pmean = optim.p_params(want, docs)
+    assert np.allclose(hf["p_a"][np.triu_indices(3, 1)], pa[np.triu_indices(3, 1)], rtol=1e-12)
+    assert np.allclose(hf["pMean"][np.triu_indices(3, 1)], pmean[np.triu_indices(3, 1)], rtol=1e-12)
+    assert np.all(hf["p_b"] == 1.0)
+
+
+def test_optimize_beta_matches_oracle(engine_lib):
+    from mvtopicmodel_b200 import Engine, corpus
+    from oracle import optim
+    K, Vs, views = corpus.generate("small_3v")
+    e = Engine(K, Vs, views, seed=8)
+    e.init_assignments()
+    for it in range(1, 16):
+        e.sweep(it)
+    e.optimize_hyper(60, 8)                                                 # optimizeBeta only
+    hf = e.get_hyper_full()
+    for m in range(3):
+        nwk, nk = e.get_counts(m)
+        beta, bsum = optim.optimize_beta(nwk, nk, Vs[m], 0.01, 0.01 * Vs[m])
+        assert hf["beta"][m] == pytest.approx(beta, rel=1e-10)
+        assert hf["betaSum"][m] == pytest.approx(bsum, rel=1e-10)
+
+
+def test_optimize_dp_and_gamma_properties(engine_lib):
+    """optimizeDP / optimizeGamma are stochastic (M:2369-2591): check the laws' consequences -- alpha is a probability vector
+    over K+1 slots (mean of Dirichlet draws), inactive topics are exactly the topics no document uses, alpha follows the
+    table counts, all concentrations stay positive and finite -- and reproducibility in (seed, iteration)."""
+    from mvtopicmodel_b200 import Engine, corpus
+    K, Vs, views = corpus.generate("small_3v")
+    outs = []
+    for rep in range(2):
+        e = Engine(K, Vs, views, seed=21)
+        e.init_assignments()
+        for it in range(1, 31):
+            e.sweep(it)
+        # empty two topics so that the inactive set is non-trivial
+        zs = [e.get_assignments(m) for m in range(3)]
+        for m in range(3):
+            z = zs[m]; z[(z == 5) | (z == 17)] = 1
+            e.set_assignments(m, z)
+        e.optimize_hyper(50, 2 | 4)
+        hf = e.get_hyper_full()
+        outs.append(hf)
+        assert sorted(hf["inactive"].tolist()) == [5, 17]
+        assert np.allclose(hf["alpha"].sum(axis=1), 1.0, atol=1e-9) and np.allclose(hf["alphaSum"], 1.0, atol=1e-9)
+        assert np.all(hf["alpha"] > 0)
+        assert np.all(hf["gamma"] > 0) and np.all(np.isfinite(hf["gamma"])) and hf["gammaRoot"] > 0 and np.all(hf["gammaView"] > 0)
+        assert np.all(hf["tablesCnt"] > 0)
+        for m in range(3):
+            nk = e.get_counts(m, want_nwk=False)[1].astype(float)
+            a = hf["alpha"][m, :K]
+            assert a[5] < np.median(a) and a[17] < np.median(a)
+            assert np.corrcoef(a, np.sqrt(nk))[0, 1] > 0.5
+        # sweeps keep working with the new prior (alpha over K+1 slots, inactive topics, new-topic bucket)
+        for it in range(51, 56):
+            e.sweep(it)
+        assert e.check_invariants() == 0
+    for k in ("alpha", "gamma", "gammaView"):
+        assert np.array_equal(outs[0][k], outs[1][k])
+
+
+def test_estimate_with_hyper_parameter_step(engine_lib):
+    """estimate() with burn-in 20 / optimise every 10 (the reference's schedule M:1166-1210, shortened): LL/token keeps
+    improving through the optimiser steps and the count invariants hold."""
+    from mvtopicmodel_b200 import corpus
+    from mvtopicmodel_b200.model import FastQMVWVParallelTopicModel, Instance, InstanceList
+    K, Vs, views = corpus.generate("small_3v")
+    D = len(views[0][0]) - 1
+    lists = []
+    for m, (off, w) in enumerate(views):
+        lists.append(InstanceList([Instance(f"d{d}", w[off[d]:off[d + 1]]) for d in range(D) if m == 0 or off[d + 1] > off[d]],
+                                  alphabet_size=Vs[m]))
+    model = FastQMVWVParallelTopicModel(K, 3, 0.1, 0.01)
+    model.setRandomSeed(5); model.setNumIterations(60); model.setBurninPeriod(20); model.setOptimizeInterval(10)
+    model.addInstances(lists, "b", 0, None)
+    ll0 = model.modelLogLikelihood() / np.array(model.totalTokens)
+    model.estimate()
+    assert model.engine.check_invariants() == 0
+    assert np.all(model.p_a[np.triu_indices(3, 1)] > 0) and np.all(model.p_a <= 100)
+    assert np.allclose(model.alphaSum, 1.0, atol=1e-6)
+    assert np.all(model.beta > 0)
+    series = model.perplexities[:, 1:7]
+    assert np.all(series[:, -1] > ll0)
