@@ -466,39 +466,44 @@ def test_optimize_beta_matches_oracle(engine_lib):
 def test_optimize_dp_and_gamma_properties(engine_lib):
     """optimizeDP / optimizeGamma are stochastic (M:2369-2591): check the laws' consequences -- alpha is a probability vector
     over K+1 slots (mean of Dirichlet draws), inactive topics are exactly the topics no document uses, alpha follows the
-    table counts, all concentrations stay positive and finite -- and reproducibility in (seed, iteration)."""
+    table counts, all concentrations stay positive and finite -- and that the step is a deterministic function of
+    (assignments, seed, iteration)."""
     from mvtopicmodel_b200 import Engine, corpus
     K, Vs, views = corpus.generate("small_3v")
-    outs = []
-    for rep in range(2):
-        e = Engine(K, Vs, views, seed=21)
-        e.init_assignments()
-        for it in range(1, 31):
-            e.sweep(it)
-        # empty two topics so that the inactive set is non-trivial
-        zs = [e.get_assignments(m) for m in range(3)]
-        for m in range(3):
-            z = zs[m]; z[(z == 5) | (z == 17)] = 1
-            e.set_assignments(m, z)
-        e.optimize_hyper(50, 2 | 4)
-        hf = e.get_hyper_full()
-        outs.append(hf)
-        assert sorted(hf["inactive"].tolist()) == [5, 17]
-        assert np.allclose(hf["alpha"].sum(axis=1), 1.0, atol=1e-9) and np.allclose(hf["alphaSum"], 1.0, atol=1e-9)
-        assert np.all(hf["alpha"] > 0)
-        assert np.all(hf["gamma"] > 0) and np.all(np.isfinite(hf["gamma"])) and hf["gammaRoot"] > 0 and np.all(hf["gammaView"] > 0)
-        assert np.all(hf["tablesCnt"] > 0)
-        for m in range(3):
-            nk = e.get_counts(m, want_nwk=False)[1].astype(float)
-            a = hf["alpha"][m, :K]
-            assert a[5] < np.median(a) and a[17] < np.median(a)
-            assert np.corrcoef(a, np.sqrt(nk))[0, 1] > 0.5
-        # sweeps keep working with the new prior (alpha over K+1 slots, inactive topics, new-topic bucket)
-        for it in range(51, 56):
-            e.sweep(it)
-        assert e.check_invariants() == 0
-    for k in ("alpha", "gamma", "gammaView"):
-        assert np.array_equal(outs[0][k], outs[1][k])
+    e = Engine(K, Vs, views, seed=21)
+    e.init_assignments()
+    for it in range(1, 31):
+        e.sweep(it)
+    # empty two topics so that the inactive set is non-trivial
+    zs = [e.get_assignments(m) for m in range(3)]
+    for m in range(3):
+        z = zs[m]; z[(z == 5) | (z == 17)] = 1
+        e.set_assignments(m, z)
+    e2 = Engine(K, Vs, views, seed=21)
+    for m in range(3):
+        e2.set_assignments(m, zs[m])
+    e.optimize_hyper(50, 2 | 4); e2.optimize_hyper(50, 2 | 4)
+    hf, hf2 = e.get_hyper_full(), e2.get_hyper_full()
+    for k in ("alpha", "alphaSum", "gamma", "gammaView", "tablesCnt"):
+        assert np.array_equal(hf[k], hf2[k]), k
+    assert hf["gammaRoot"] == hf2["gammaRoot"]
+    assert sorted(hf["inactive"].tolist()) == [5, 17]
+    assert np.allclose(hf["alpha"].sum(axis=1), 1.0, atol=1e-9) and np.allclose(hf["alphaSum"], 1.0, atol=1e-9)
+    assert np.all(hf["alpha"] > 0)
+    assert np.all(hf["gamma"] > 0) and np.all(np.isfinite(hf["gamma"])) and hf["gammaRoot"] > 0 and np.all(hf["gammaView"] > 0)
+    assert np.all(hf["tablesCnt"] > 0)
+    for m in range(3):
+        nk = e.get_counts(m, want_nwk=False)[1].astype(float)
+        a = hf["alpha"][m, :K]
+        assert a[5] < np.median(a) and a[17] < np.median(a)
+        assert np.corrcoef(a, np.sqrt(nk))[0, 1] > 0.5
+    # a different iteration keys a different stream
+    e2.optimize_hyper(60, 2)
+    assert not np.array_equal(e2.get_hyper_full()["alpha"], hf["alpha"])
+    # sweeps keep working with the new prior (alpha over K+1 slots, inactive topics, new-topic bucket)
+    for it in range(51, 56):
+        e.sweep(it)
+    assert e.check_invariants() == 0
 
 
 def test_estimate_with_hyper_parameter_step(engine_lib):
