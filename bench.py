@@ -27,9 +27,17 @@ METRIC = "gibbs_token_updates_per_sec"
 UNIT = "tokens/s"
 
 
-def b_tok(K, mean_len):
-    """Algorithmic bytes per token update, SURVEY.md 8(d) / BASELINE.md section 3 (single view)."""
-    return 4 * K + 4 + 8 + 16 + 8.0 * K / mean_len
+def b_tok(K, mean_lens, tokens):
+    """Algorithmic bytes per token update, SURVEY.md 8(d) / BASELINE.md section 3: per view 4K (row) + 4 (word) + 8 (z r/w)
+    + 16 (two count RMWs) + 8K/N_m (n_k and alpha rows per doc-view) + 4*sum_{i != m} N_i/N_m (other views' z re-read),
+    token-weighted over the views."""
+    tot, acc = float(sum(tokens)), 0.0
+    for m, (n, t) in enumerate(zip(mean_lens, tokens)):
+        if t == 0:
+            continue
+        other = sum(mean_lens[i] for i in range(len(mean_lens)) if i != m)
+        acc += t * (4 * K + 28 + 8.0 * K / n + 4.0 * other / n)
+    return acc / tot
 
 
 def measured_peak():
@@ -124,9 +132,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from mvtopicmodel_b200 import corpus
     cfg = corpus.CONFIGS[args.workload]
-    mean_len = sum(v[1] * v[3] for v in cfg["views"]) / max(1, len(cfg["views"]))
-    wl_desc = (f"{args.workload}: BASELINE configs[1] synthetic single-view LDA shape, D={cfg['D']} docs/GPU, "
-               f"V={cfg['views'][0][0]}, K={cfg['K']}, ~{int(cfg['D'] * cfg['views'][0][1] / 1e6)}M tokens/GPU")
+    cfg_idx = {"lda_100k": 1, "acm_2v": 2, "pubmed_3v": 3, "stress_4v": 4}.get(args.workload, -1)
+    docs_cfg = args.docs if args.docs else cfg["D"]
+    wl_desc = (f"{args.workload}: BASELINE configs[{cfg_idx}] synthetic shape, {docs_cfg} docs/GPU, {len(cfg['views'])} view(s), "
+               f"V={[v[0] for v in cfg['views']]}, K={cfg['K']}, ~{int(docs_cfg * sum(v[1] * v[3] for v in cfg['views']) / 1e6)}M tokens/GPU")
     threads = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -175,7 +184,7 @@ def main():
     def step(it):
         eng.sweep(it)
         if xch:
-            xch.exchange()
+            xch.exchange_sum()          # every rank holds the same global counts at sweep start
 
     it = 0
     for _ in range(args.warmup):
@@ -208,7 +217,18 @@ def main():
         ntok_global = int(n[0])
     else:
         ntok_global, kern_ms_max = ntok_local, kern_ms
-    viol = eng.check_invariants() if world == 1 else 0
+    if world == 1:
+        viol = eng.check_invariants()
+    else:
+        # replicas hold GLOBAL counts: per view, sum_t n_k must equal the token total over all ranks and be identical everywhere
+        viol = 0
+        for m in range(M):
+            nk = torch.from_numpy(eng.get_counts(m, want_nwk=False)[1].astype(np.int64)).cuda()
+            tot = torch.tensor([eng.ntok[m]], device="cuda", dtype=torch.int64)
+            dist.all_reduce(tot)
+            mx, mn = nk.clone(), nk.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            viol += int(nk.sum().item() != tot.item()) + int((mx != mn).sum().item()) + int((nk < 0).sum().item())
     value = ntok_global * args.steps / (ms_total * 1e-3)
 
     # end-to-end: the same sweep through HOST buffers (pinned), H2D + count rebuild + sweep + D2H inside the timing
@@ -224,9 +244,9 @@ def main():
                 for m in range(M):
                     eng.set_assignments(m, zn[m])          # H2D + local rebuild
                 xch.reset(); xch.exchange()                # local counts -> global counts
-                eng.sweep(i); xch.exchange()
+                eng.sweep(i); xch.exchange_sum()
                 for m in range(M):
-                    zn[m][:] = eng.get_assignments(m)      # D2H
+                    eng.get_assignments(m, out=zn[m])      # D2H into the pinned buffer
             else:
                 eng.sweep_host(i, zn)
         e2e_steps = max(3, min(args.steps, 10))
@@ -257,7 +277,8 @@ def main():
         return 0
 
     peak, peak_src = measured_peak()
-    btok = b_tok(K, mean_len)
+    mean_lens = [eng.ntok[m] / max(1, int(((views[m][0][1:] - views[m][0][:-1]) > 0).sum())) for m in range(M)]
+    btok = b_tok(K, mean_lens, eng.ntok)
     kern_s = kern_ms_max * 1e-3
     achieved = btok * ntok_local * args.steps / kern_s / 1e9 if kern_s > 0 else 0.0
     traffic = None

@@ -137,6 +137,12 @@ int mvtm_delta_begin(mvtm_handle *h);
 int mvtm_delta_reset(mvtm_handle *h);      /* snapshot := 0 (the replicas hold purely local counts, e.g. right after a rebuild) */
 int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems);
 int mvtm_delta_import(mvtm_handle *h, int32_t m);
+/* Sum-form of the same exchange, one pass cheaper: when every rank entered the sweep with the same global counts G (true
+ * after any completed exchange), all-reduce the replicas themselves (buffers from mvtm_sum_exchange_buffers) and call
+ * mvtm_sum_exchange_finish, which turns N*G + sum(delta) into G + sum(delta) using the snapshot of G.  Needs
+ * world_size * (largest cell) < 2^31. */
+int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems);
+int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world_size);
 int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out);
 
 /* Scan layout of the sampler (for order-exact checkers): a document-view is sampled by `lanes_per_doc` lanes (8, 16 or

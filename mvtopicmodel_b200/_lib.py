@@ -51,6 +51,8 @@ SIGNATURES = {
     "mvtm_delta_reset": (_i32, [_vp]),
     "mvtm_delta_export": (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
     "mvtm_delta_import": (_i32, [_vp, _i32]),
+    "mvtm_sum_exchange_buffers": (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
+    "mvtm_sum_exchange_finish": (_i32, [_vp, _i32, _i32]),
     "mvtm_row_stride": (_i32, [_vp, C.POINTER(_i32)]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),

@@ -842,6 +842,36 @@ extern "C" int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int
     return MVTM_OK;
 }
 
+extern "C" int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_buffers: bad view %d", m);
+    ViewDev &v = h->v[m];
+    if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_buffers: call mvtm_delta_begin first");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (n_wk_dev) *n_wk_dev = v.nwk;
+    if (n_wk_elems) *n_wk_elems = (long long)v.V * h->Kp;
+    if (n_k_dev) *n_k_dev = v.nk;
+    if (n_k_elems) *n_k_elems = h->Kp;
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world_size)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added || world_size < 1) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_finish: bad argument");
+    ViewDev &v = h->v[m];
+    if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_finish: call mvtm_delta_begin first");
+    CK(h, cudaSetDevice(h->device));
+    const long long n = (long long)v.V * h->Kp;
+    k_finish_sum_exchange<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk, world_size - 1);
+    k_finish_sum_exchange<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk, world_size - 1);
+    CK(h, cudaGetLastError());
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
 extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
 {
     if (!h) return MVTM_ERR_ARG;

@@ -725,3 +725,11 @@ __global__ void k_add_snapshot(long long n, int *a, int *snap)
 {   // a holds the reduced delta: a = snap + a, snap = a
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) { int v = a[i] + snap[i]; a[i] = v; snap[i] = v; }
 }
+// Sum-form exchange: every rank entered the sweep with the same global table G (= snap) and now holds G + delta_r; after
+// an in-place all-reduce a = N*G + sum_r delta_r, so the new global table is a - (N-1)*G.  One fused pass, no export pass.
+__global__ void k_finish_sum_exchange(long long n, int *a, int *snap, int world_minus_1)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int v = a[i] - world_minus_1 * snap[i]; a[i] = v; snap[i] = v;
+    }
+}

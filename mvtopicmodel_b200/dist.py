@@ -47,6 +47,15 @@ class EngineAdapter:
         self.torch.cuda.synchronize(self.dev)      # the all-reduce ran on torch's stream
         self.e.delta_import(m)
 
+    def sum_buffers(self, m):
+        (p1, n1), (p2, n2) = self.e.sum_exchange_buffers(m)
+        t = self.torch
+        return (t.as_tensor(_DevBuf(p1, n1), device=f"cuda:{self.dev}"), t.as_tensor(_DevBuf(p2, n2), device=f"cuda:{self.dev}"))
+
+    def sum_finish(self, m, world):
+        self.torch.cuda.synchronize(self.dev)
+        self.e.sum_exchange_finish(m, world)
+
 
 class CountExchange:
     """Runs the delta protocol over a torch.distributed process group for any adapter with the four methods above."""
@@ -61,6 +70,20 @@ class CountExchange:
 
     def reset(self):
         self.a.delta_reset()
+
+    def exchange_sum(self, views=None):
+        """Sum-form exchange (one memory pass cheaper than `exchange`): valid whenever all ranks entered the sweep with the
+        same global counts, i.e. after any completed exchange.  Adapter needs sum_buffers / sum_finish."""
+        world = self.dist.get_world_size(self.group)
+        total = 0
+        for m in (range(self.a.M) if views is None else views):
+            nwk, nk = self.a.sum_buffers(m)
+            self.dist.all_reduce(nwk, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(nk, op=self.dist.ReduceOp.SUM, group=self.group)
+            total += (nwk.numel() + nk.numel()) * 4
+            self.a.sum_finish(m, world)
+        self.bytes_per_exchange = total
+        return total
 
     def exchange(self, views=None):
         total = 0

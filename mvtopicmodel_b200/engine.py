@@ -68,8 +68,8 @@ class Engine:
             raise ValueError("assignment array length != tokens of the view")
         self._ck(self.L.mvtm_set_assignments(self.h, m, _ptr(z)))
 
-    def get_assignments(self, m):
-        z = np.empty(self.ntok[m], dtype=np.int32)
+    def get_assignments(self, m, out=None):
+        z = np.empty(self.ntok[m], dtype=np.int32) if out is None else out
         self._ck(self.L.mvtm_get_assignments(self.h, m, _ptr(z)))
         return z
 
@@ -185,6 +185,14 @@ class Engine:
         p1, n1, p2, n2 = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
         self._ck(self.L.mvtm_delta_export(self.h, m, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
         return (p1.value, n1.value), (p2.value, n2.value)
+
+    def sum_exchange_buffers(self, m):
+        p1, n1, p2, n2 = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        self._ck(self.L.mvtm_sum_exchange_buffers(self.h, m, C.byref(p1), C.byref(n1), C.byref(p2), C.byref(n2)))
+        return (p1.value, n1.value), (p2.value, n2.value)
+
+    def sum_exchange_finish(self, m, world):
+        self._ck(self.L.mvtm_sum_exchange_finish(self.h, m, int(world)))
 
     def delta_import(self, m):
         self._ck(self.L.mvtm_delta_import(self.h, m))

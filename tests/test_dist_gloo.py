@@ -38,6 +38,16 @@ class OracleAdapter:
         self.buf[m] = (a - self.snap[m][0], b - self.snap[m][1])
         return self.buf[m]
 
+    def sum_buffers(self, m):
+        self.buf[m] = self._cur(m)
+        return self.buf[m]
+
+    def sum_finish(self, m, world):
+        a = self.buf[m][0] - (world - 1) * self.snap[m][0]
+        b = self.buf[m][1] - (world - 1) * self.snap[m][1]
+        self.snap[m] = (a, b)
+        self.o.set_counts(m, a.numpy().reshape(int(self.o.V[m]), self.o.K), b.numpy())
+
     def delta_import(self, m):
         a = self.snap[m][0] + self.buf[m][0]
         b = self.snap[m][1] + self.buf[m][1]
@@ -79,7 +89,7 @@ def _worker(rank, world, port, q):
         # (3) sweeps with the exchange keep the global invariants bit-exact
         for it in range(1, 5):
             o.sweep(it, O.F_ENGINE_MIRROR)
-            nbytes = x.exchange()
+            nbytes = x.exchange() if it % 2 else x.exchange_sum()      # both forms of the protocol
             assert nbytes == sum((Vs[m] * K + K) * 4 for m in range(2))
             zs_all = [None] * world
             dist.all_gather_object(zs_all, [o.get_assignments(m) for m in range(2)])
