@@ -84,6 +84,14 @@ int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, const int32
 int mvtm_init_assignments(mvtm_handle *h);
 int mvtm_set_assignments(mvtm_handle *h, int32_t m, const int32_t *z);
 
+/* Inference on new documents (FastQMVWVTopicInferencer, I:114-330): a handle built over the NEW documents receives the trained
+ * counts (mvtm_set_counts: typeTopicCounts[m] as V_m x K row-major and tokensPerTopic[m]), draws the initial topic of every
+ * in-vocabulary token from the bare topic-word distribution of those counts (mvtm_init_assignments_from_counts, I:186-203;
+ * out-of-vocabulary tokens get topic 0, Q13) and is then swept with update_global = 0 (or 2 for the reference's trees without
+ * gamma*alpha, Q13). */
+int mvtm_set_counts(mvtm_handle *h, int32_t m, const int32_t *n_wk, const int32_t *n_k);
+int mvtm_init_assignments_from_counts(mvtm_handle *h);
+
 /* Hyper-parameters as the worker/updater constructors receive them (W:80-150, U:78-147).  Any pointer may
  * be NULL (= keep).  alpha is M x (K+1) row-major (slot K = new-topic prior), p_a/p_b are M x M;
  * inactive = inActiveTopicIndex (M:95) as a list, n_inactive < 0 = keep.  Defaults after create are the
@@ -95,7 +103,8 @@ int mvtm_get_hyper(mvtm_handle *h, double *alpha, double *alpha_sum, int32_t *in
 
 /* One Gibbs sweep over every view = one iteration of estimate()'s loop body M:1213-1239: the work of all
  * FastQMVWVWorkerRunnable.run (W:186-233, W:301-597) and FastQMVWVUpdaterRunnable.run (U:164-297) threads up to
- * the barrier.  update_global = 0 freezes n_wk / n_k (the inferencer's nut = 0 mode, I:211-256).  Blocking. */
+ * the barrier.  update_global = 0 freezes n_wk / n_k (the inferencer's nut = 0 mode, I:211-256); update_global = 2 does the
+ * same with the inferencer's own trees, which hold phi without gamma*alpha (I:561-576, quirk Q13).  Blocking. */
 int mvtm_sweep(mvtm_handle *h, int32_t iteration, int32_t update_global);
 
 /* The same sweep through HOST buffers: uploads z (one array per view, caller memory, pinned or pageable),

@@ -36,6 +36,8 @@ SIGNATURES = {
     "mvtm_add_view": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "mvtm_init_assignments": (_i32, [_vp]),
     "mvtm_set_assignments": (_i32, [_vp, _i32, _vp]),
+    "mvtm_set_counts": (_i32, [_vp, _i32, _vp, _vp]),
+    "mvtm_init_assignments_from_counts": (_i32, [_vp]),
     "mvtm_set_hyper": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "mvtm_get_hyper": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_i32)]),
     "mvtm_sweep": (_i32, [_vp, _i32, _i32]),

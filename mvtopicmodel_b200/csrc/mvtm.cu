@@ -28,7 +28,7 @@ struct ViewDev {
     unsigned char *present = nullptr;
     int *nwk = nullptr, *nk = nullptr, *nk_snap = nullptr;
     int *order = nullptr;
-    float *ga_tree = nullptr, *ga_full = nullptr;
+    float *ga_tree = nullptr, *ga_full = nullptr, *ga_one = nullptr;   // ga_one: all ones, the inferencer's bare trees (Q13)
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
     std::vector<unsigned char> h_present;
@@ -160,7 +160,7 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
 static void free_view(ViewDev &v)
 {
     cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk); cudaFree(v.nk);
-    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.snap_nwk); cudaFree(v.snap_nk);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk); cudaFree(v.snap_nk);
     v = ViewDev();
 }
 
@@ -237,6 +237,8 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMalloc(&v.nk_snap, Kp * 4));
     CK(h, cudaMalloc(&v.ga_tree, Kp * 4));
     CK(h, cudaMalloc(&v.ga_full, Kp * 4));
+    CK(h, cudaMalloc(&v.ga_one, Kp * 4));
+    { std::vector<float> ones(Kp, 0.f); std::fill(ones.begin(), ones.begin() + h->K, 1.f); CK(h, cudaMemcpy(v.ga_one, ones.data(), Kp * 4, cudaMemcpyHostToDevice)); }
     CK(h, cudaMemcpy(v.doc_off, doc_off, (size_t)(D + 1) * 8, cudaMemcpyHostToDevice));
     if (N > 0) CK(h, cudaMemcpy(v.word, word_id, (size_t)N * 4, cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(v.present, pres.data(), pres.size(), cudaMemcpyHostToDevice));
@@ -304,6 +306,41 @@ extern "C" int mvtm_set_assignments(mvtm_handle *h, int32_t m, const int32_t *z)
         CK(h, cudaMemcpyAsync(v.z, z, (size_t)v.n_tok * 4, cudaMemcpyHostToDevice, h->stream));
     }
     return rebuild_counts_view(h, m);
+}
+
+extern "C" int mvtm_set_counts(mvtm_handle *h, int32_t m, const int32_t *n_wk, const int32_t *n_k)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added || !n_wk || !n_k) FAIL(h, MVTM_ERR_ARG, "mvtm_set_counts: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    ViewDev &v = h->v[m];
+    for (int t = 0; t < h->K; t++) if (n_k[t] < 0) FAIL(h, MVTM_ERR_CORRUPT, "mvtm_set_counts: negative n_k[%d]", t);
+    CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * h->Kp * 4, h->stream));
+    CK(h, cudaMemsetAsync(v.nk, 0, (size_t)h->Kp * 4, h->stream));
+    CK(h, cudaMemcpy2DAsync(v.nwk, (size_t)h->Kp * 4, n_wk, (size_t)h->K * 4, (size_t)h->K * 4, (size_t)v.V, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(v.nk, n_k, (size_t)h->K * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_init_assignments_from_counts(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_views(h, "mvtm_init_assignments_from_counts")) return rc;
+    CK(h, cudaSetDevice(h->device));
+    const int K = h->K;
+    int P2 = 1; while (P2 * 2 <= 2 * K - 1) P2 *= 2;                  // 2^floor(log2(2K-1)): first index of the deepest tree level
+    const int rot = P2 - K;
+    for (int m = 0; m < h->M; m++) {
+        ViewDev &v = h->v[m];
+        if (v.n_tok == 0) continue;
+        int blocks = (int)std::min<long long>((h->D * 32 + 255) / 256, (long long)h->num_sms * 16);
+        k_init_from_phi<<<std::max(blocks, 1), 256, 0, h->stream>>>(m, K, h->Kp, v.V, h->D, v.doc_off, v.word, v.z, v.nwk, v.nk, h->beta[m], h->betaSum[m],
+                                                                   rot, (unsigned)h->seed, (unsigned)(h->seed >> 32), h->doc_id_base, h->doc_id_stride);
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
 }
 
 extern "C" int mvtm_get_assignments(mvtm_handle *h, int32_t m, int32_t *z_out)
@@ -407,7 +444,9 @@ static void fill_params(mvtm_handle *h, int m, int iteration, int update_global,
         P.pa[i] = h->p_a[m][i]; P.pb[i] = h->p_b[m][i];
         P.sparse[i] = (h->beta[i] == 0.0001);                            // W:335-336
     }
-    P.word = v.word; P.nwk = v.nwk; P.nk_frozen = v.nk_snap; P.nk_live = v.nk; P.ga_tree = v.ga_tree;
+    P.word = v.word; P.nwk = v.nwk; P.nk_frozen = v.nk_snap; P.nk_live = v.nk;
+    P.ga_tree = (update_global == 2) ? v.ga_one : v.ga_tree;            // 2 = inferencer mode with bare-phi trees (I:561-576, Q13)
+    if (update_global == 2) update_global = 0;
     P.beta = (float)h->beta[m]; P.betaSum = (float)h->betaSum[m];
     P.n_inactive = (int)h->inactive.size(); P.first_inactive = h->inactive.empty() ? 0 : h->inactive[0];
     P.seed_lo = (unsigned)h->seed; P.seed_hi = (unsigned)(h->seed >> 32); P.iteration = (unsigned)iteration;
@@ -574,7 +613,7 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
             if (h->v[m].n_items > 0) ring_record(h, m, ms);
         }
         h->stats.kernel_launches = launches;
-        if (update_global) if (int rc = activate_sampled_topics(h)) return rc;
+        if (update_global == 1) if (int rc = activate_sampled_topics(h)) return rc;
     }
     return MVTM_OK;
 }

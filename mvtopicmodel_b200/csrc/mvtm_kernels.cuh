@@ -613,6 +613,40 @@ __global__ void k_init_assign(int m, int K, long long n_docs, const long long *o
     }
 }
 
+// inferencer initialisation I:186-203: every in-vocabulary token draws its topic from the bare topic-word distribution
+// phi_t = (n_wk[w][t] + beta) / (n_k[t] + betaSum) of the TRAINED counts (I:561-576 builds the trees without gamma*alpha);
+// out-of-vocabulary tokens keep Java's default 0 (Q13).  FTree.sample (FT:111-136) on the heap-shaped tree walks the leaves
+// in the order "topics rot..K-1, then 0..rot-1" with rot = 2^floor(log2(2K-1)) - K, which this linear scan reproduces.
+__global__ void k_init_from_phi(int m, int K, int Kp, int V, long long n_docs, const long long *off, const int *word, int *z, const int *nwk,
+                                const int *nk, double beta, double betaSum, int rot, unsigned seed_lo, unsigned seed_hi,
+                                long long doc_id_base, long long doc_id_stride)
+{
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long d = wid; d < n_docs; d += nw) {
+        const long long b = off[d]; const int len = (int)(off[d + 1] - b);
+        const uint32_t gdoc = (uint32_t)(doc_id_base + d * doc_id_stride);
+        for (int i = lane; i < len; i += 32) {
+            const int w = word[b + i];
+            if ((unsigned)w >= (unsigned)V) { z[b + i] = 0; continue; }
+            const int *row = nwk + (size_t)w * Kp;
+            double total = 0.0;
+            for (int t = 0; t < K; t++) total += ((double)row[t] + beta) / ((double)nk[t] + betaSum);
+            uint4 x = philox4x32_10((uint32_t)i, gdoc, 0u, ((uint32_t)m << 8) | PURPOSE_INIT, seed_lo, seed_hi);
+            const double target = (double)(x.x >> 8) * (1.0 / 16777216.0) * total;
+            double cum = 0.0; int pick = -1, last = 0;
+            for (int k = 0; k < K; k++) {
+                int t = k + rot; if (t >= K) t -= K;
+                cum += ((double)row[t] + beta) / ((double)nk[t] + betaSum);
+                last = t;
+                if (pick < 0 && target < cum) pick = t;
+            }
+            z[b + i] = pick < 0 ? last : pick;
+        }
+    }
+}
+
 // buildInitialTypeTopicCounts M:600-652: n_wk / n_k from (word, z); n_k through a shared-memory histogram
 __global__ void k_build_counts(long long n_tok, const int *word, const int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad)
 {

@@ -68,6 +68,15 @@ class Engine:
             raise ValueError("assignment array length != tokens of the view")
         self._ck(self.L.mvtm_set_assignments(self.h, m, _ptr(z)))
 
+    def set_counts(self, m, nwk, nk):
+        nwk = np.ascontiguousarray(nwk, dtype=np.int32); nk = np.ascontiguousarray(nk, dtype=np.int32)
+        if nwk.shape != (int(self.V[m]), self.K) or nk.shape != (self.K,):
+            raise ValueError("n_wk must be V_m x K and n_k K")
+        self._ck(self.L.mvtm_set_counts(self.h, m, _ptr(nwk), _ptr(nk)))
+
+    def init_assignments_from_counts(self):
+        self._ck(self.L.mvtm_init_assignments_from_counts(self.h))
+
     def get_assignments(self, m, out=None):
         z = np.empty(self.ntok[m], dtype=np.int32) if out is None else out
         self._ck(self.L.mvtm_get_assignments(self.h, m, _ptr(z)))
@@ -124,7 +133,8 @@ class Engine:
 
     # --- the hot path ----------------------------------------------------------------------------
     def sweep(self, iteration, update_global=True):
-        self._ck(self.L.mvtm_sweep(self.h, int(iteration), int(bool(update_global))))
+        mode = update_global if update_global in (0, 1, 2) else int(bool(update_global))
+        self._ck(self.L.mvtm_sweep(self.h, int(iteration), int(mode)))
 
     def sweep_host(self, iteration, z_arrays):
         """z_arrays: one int32 numpy array per view, updated in place (host buffers in, host buffers out)."""

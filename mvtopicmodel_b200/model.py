@@ -175,7 +175,76 @@ class FastQMVWVParallelTopicModel:
     def getTopicAssignments(self, m):
         return self.engine.get_assignments(m)
 
+    def getInferencer(self):
+        """M:3457-3463"""
+        return FastQMVWVTopicInferencer(self)
+
     def getTopWords(self, m, numWords):
         """Indices of the top words per topic by count (the ranking of M:1792-1890 without the alphabet lookup)."""
         nwk = self.engine.get_counts(m)[0]
         return np.argsort(-nwk, axis=0, kind="stable")[:numWords].T
+
+
+class FastQMVWVTopicInferencer:
+    """Mirror of org.madgik.MVTopicModel.FastQMVWVTopicInferencer (I) for the sampling path: folds NEW documents into a
+    trained model with the global counts frozen (the worker with nut = 0, I:211-256).
+
+    Built from a trained FastQMVWVParallelTopicModel like M:3457-3463 (`model.getInferencer()`).  `inferTopicDistributions`
+    follows I:114-330: join the new documents' views, draw every in-vocabulary token's topic from the trained topic-word
+    distribution (I:186-203), run `numIterations` = 10 sweeps (I:74,561), return the document-topic proportions of I:385-412.
+    quirk_bare_trees=True reproduces Q13 (the inferencer's trees omit gamma*alpha)."""
+
+    def __init__(self, model):
+        self.K, self.M = model.numTopics, model.numModalities
+        self.numTypes = list(model.numTypes)
+        self.counts = [model.engine.get_counts(m) for m in range(self.M)]
+        hf = model.engine.get_hyper_full()
+        self.hyper = {k: hf[k] for k in ("alpha", "alphaSum", "beta", "betaSum", "gamma", "p_a", "p_b")}
+        self.inactive = list(hf["inactive"])
+        self.pMean = hf["pMean"] if model.iterationsSoFar > model.burninPeriod else np.ones((self.M, self.M))
+        self.numIterations = 10
+        self.device = model.device
+        self.seed = model.randomSeed if model.randomSeed != -1 else 1
+        self.engine = None
+
+    def inferTopicDistributions(self, instances, discrWeightPerModality=None, quirk_bare_trees=False):
+        M, K = self.M, self.K
+        entityPosition, docs, names = {}, [], []
+        for m in range(M):
+            for inst in instances[m]:
+                if m != 0 and inst.name in entityPosition:
+                    docs[entityPosition[inst.name]][m] = inst.features
+                else:
+                    row = [None] * M; row[m] = inst.features
+                    docs.append(row); entityPosition[inst.name] = len(docs) - 1; names.append(inst.name)
+        D = len(docs)
+        views = []
+        for m in range(M):
+            lens = np.array([0 if r[m] is None else len(r[m]) for r in docs], dtype=np.int64)
+            off = np.zeros(D + 1, dtype=np.int64); np.cumsum(lens, out=off[1:])
+            words = np.concatenate([r[m] for r in docs if r[m] is not None and len(r[m])]) if off[-1] else np.zeros(0, np.int32)
+            views.append((off, words.astype(np.int32)))
+        self.engine = e = Engine(K, [max(1, v) for v in self.numTypes], views, seed=self.seed, device=self.device)
+        e.set_hyper(inactive=self.inactive, **self.hyper)
+        for m in range(M):
+            e.set_counts(m, *self.counts[m])
+        e.init_assignments_from_counts()
+        for it in range(1, self.numIterations + 1):
+            e.sweep(it, update_global=2 if quirk_bare_trees else 0)
+        w = np.ones(M) if discrWeightPerModality is None else np.asarray(discrWeightPerModality, dtype=np.float64)
+        theta = np.zeros((D, K))
+        norm = np.zeros(D)
+        for m in range(M):
+            off = views[m][0]
+            z = e.get_assignments(m)
+            lens = (off[1:] - off[:-1]).astype(np.float64)
+            has = lens > 0
+            cnt = np.zeros((D, K))
+            np.add.at(cnt, (np.repeat(np.arange(D), (off[1:] - off[:-1])), z), 1.0)
+            wm = (1.0 if m == 0 else w[m]) * self.pMean[0, m]
+            ga = self.hyper["gamma"][m] * self.hyper["alpha"][m][:K]
+            contrib = wm * (cnt + ga) / (lens + self.hyper["gamma"][m] * self.hyper["alphaSum"][m])[:, None]
+            theta[has] += contrib[has]
+            norm[has] += wm
+        theta[norm > 0] /= norm[norm > 0][:, None]
+        return names, theta

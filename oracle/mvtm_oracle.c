@@ -38,7 +38,8 @@
 #define ORC_F_BETA_MALLET   8u   /* Q5: MALLET Randoms.nextBeta law instead of true Beta(a,1)=u^(1/a)    */
 #define ORC_F_ENGINE_MIRROR 16u  /* view-major order, dense single-scan sampler in the engine's order     */
 #define ORC_F_DOC_ORDER     32u  /* (engine mirror) plain document order, no length sort                 */
-#define ORC_F_FROZEN        64u  /* (engine mirror) global counts frozen: the inferencer's nut = 0 mode, I:211-256 */
+#define ORC_F_FROZEN        64u  /* global counts frozen: the inferencer's nut = 0 mode, I:211-256 */
+#define ORC_F_BARE_TREES    128u /* Q13: the inferencer's trees hold phi without gamma*alpha and ignore the inactive set (I:561-576) */
 
 typedef struct {
     int M, K;
@@ -268,12 +269,17 @@ static inline double leaf_value(const orc_t *o, int m, int w, int t)
 {
     return o->gamma[m] * o->alpha[m][t] * ((o->n_wk[m][(size_t)w * o->K + t] + o->beta[m]) / (o->n_k[m][t] + o->betaSum[m]));
 }
-static void build_tree_for_word(const orc_t *o, int m, int w, double *tree, double *tmp)
+static inline double phi_value(const orc_t *o, int m, int w, int t)
+{ return (o->n_wk[m][(size_t)w * o->K + t] + o->beta[m]) / (o->n_k[m][t] + o->betaSum[m]); }
+static void build_tree_for_word_f(const orc_t *o, int m, int w, double *tree, double *tmp, unsigned flags)
 {
     int K = o->K;
-    for (int t = 0; t < K; t++) tmp[t] = (o->n_inactive && is_inactive(o, t)) ? 0.0 : leaf_value(o, m, w, t);
+    if (flags & ORC_F_BARE_TREES) for (int t = 0; t < K; t++) tmp[t] = phi_value(o, m, w, t);          /* I:561-576 */
+    else for (int t = 0; t < K; t++) tmp[t] = (o->n_inactive && is_inactive(o, t)) ? 0.0 : leaf_value(o, m, w, t);
     orc_ftree_build(tree, tmp, K);
 }
+static void build_tree_for_word(const orc_t *o, int m, int w, double *tree, double *tmp)
+{ build_tree_for_word_f(o, m, w, tree, tmp, 0); }
 int orc_rebuild_trees(orc_t *o)
 {   /* buildFTrees, M:2660-2696 */
     int K = o->K;
@@ -334,6 +340,25 @@ int orc_init_assignments(orc_t *o)
         }
     }
     orc_rebuild_counts(o);
+    return 0;
+}
+int orc_init_from_phi(orc_t *o)
+{   /* inferencer initialisation I:186-203: topic = trees[m][type].sample(u) with bare-phi trees; OOV tokens keep 0 (Q13) */
+    int K = o->K;
+    double *tmp = (double *)malloc((size_t)K * 8), *tree = (double *)malloc((size_t)2 * K * 8);
+    for (int64_t d = 0; d < o->D; d++)
+        for (int m = 0; m < o->M; m++) {
+            int64_t b = o->doc_off[m][d], e = o->doc_off[m][d + 1];
+            for (int64_t i = b; i < e; i++) {
+                int w = o->word[m][i];
+                if (w < 0 || w >= o->V[m]) { o->z[m][i] = 0; continue; }
+                build_tree_for_word_f(o, m, w, tree, tmp, ORC_F_BARE_TREES);
+                uint32_t x[4];
+                orc_draw(o, (uint32_t)(i - b), (uint32_t)(o->doc_base + d * o->doc_stride), 0, (uint32_t)m, ORC_PURPOSE_INIT, x);
+                o->z[m][i] = orc_ftree_sample(tree, K, u24(x[0]));
+            }
+        }
+    free(tmp); free(tree);
     return 0;
 }
 int orc_set_assignments(orc_t *o, int m, const int32_t *z)
@@ -505,7 +530,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
             double C = o->n_inactive == 0 ? 0 : Cdoc / K;                /* W:515 */
             const double *tree;
             if (flags & ORC_F_STALE_TREES) tree = o->tree[m] + (size_t)w * 2 * K;
-            else { build_tree_for_word(o, m, w, s->ttree, s->tmp); tree = s->ttree; }
+            else { build_tree_for_word_f(o, m, w, s->ttree, s->tmp, flags); tree = s->ttree; }
             double B = tree[1];
             uint32_t x[4];
             orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
@@ -546,6 +571,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
 typedef struct { orc_t *o; orc_scratch *s; unsigned flags; } emit_ctx;
 static void emit_immediate(void *c, const orc_delta *d)
 { emit_ctx *e = (emit_ctx *)c; apply_delta(e->o, d, 1); }
+static void emit_nothing(void *c, const orc_delta *d) { (void)c; (void)d; }   /* nut = 0: W:587 never enqueues */
 static void emit_deferred(void *c, const orc_delta *d)
 {
     emit_ctx *e = (emit_ctx *)c; orc_scratch *s = e->s;
@@ -571,6 +597,7 @@ static int engine_slot_size(int K)
 
 /* unnormalised engine weights for token (d, m, pos) given local counts nd (own token already removed),
  * other-view state and the frozen topic totals nk_frozen.  out has K entries. */
+static unsigned g_engine_weight_flags = 0;   /* set by the sweep for the duration of a mirror pass (single-threaded) */
 static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, const int len[ORC_MAXM],
                            double p[ORC_MAXM][ORC_MAXM], const int32_t *nk_frozen, double *out)
 {
@@ -588,6 +615,7 @@ static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, cons
             O *= coefm;
         }
         double ga = (o->n_inactive && is_inactive(o, t)) ? 0.0 : o->gamma[m] * o->alpha[m][t];
+        if (g_engine_weight_flags & ORC_F_BARE_TREES) ga = 1.0;
         double phi = (row[t] + o->beta[m]) / (nk_frozen[t] + o->betaSum[m]);
         out[t] = phi * (p[m][m] * nd[m * K + t] + O + ga);
     }
@@ -694,6 +722,7 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
     int64_t cnt[4] = { 0, 0, 0, 0 };
     if (flags & ORC_F_ENGINE_MIRROR) {
         int K = o->K;
+        g_engine_weight_flags = flags;
         int32_t *nk_frozen = (int32_t *)malloc((size_t)K * 4);
         int32_t *dnk = (int32_t *)malloc((size_t)K * 4);
         int64_t *order = (int64_t *)malloc((size_t)(o->D > 0 ? o->D : 1) * 8);
@@ -710,11 +739,12 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
             }
         }
         free(nk_frozen); free(dnk); free(order);
+        g_engine_weight_flags = 0;
         if (!(flags & ORC_F_FROZEN)) activate_sampled_topics(o);
     } else {
         if ((flags & ORC_F_STALE_TREES) && !o->tree[0]) orc_rebuild_trees(o);
         emit_ctx ctx = { o, s, flags };
-        emit_fn emit = (flags & ORC_F_DEFERRED) ? emit_deferred : emit_immediate;
+        emit_fn emit = (flags & ORC_F_FROZEN) ? emit_nothing : ((flags & ORC_F_DEFERRED) ? emit_deferred : emit_immediate);
         for (int64_t d = 0; d < o->D; d++) sample_doc_reference(o, d, iteration, flags, s, emit, &ctx, cnt);
         for (size_t i = 0; i < s->ndq; i++) apply_delta(o, &s->dq[i], 1);
     }

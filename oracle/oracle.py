@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmvtm_oracle.so")
 
-F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER, F_FROZEN = 1, 2, 4, 8, 16, 32, 64
+F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER, F_FROZEN, F_BARE_TREES = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def build(force=False):
@@ -47,6 +47,7 @@ def lib():
             "orc_rebuild_trees": (i32, [p]),
             "orc_rebuild_counts": (i32, [p]),
             "orc_init_assignments": (i32, [p]),
+            "orc_init_from_phi": (i32, [p]),
             "orc_set_assignments": (i32, [p, i32, p]),
             "orc_get_assignments": (i32, [p, i32, p]),
             "orc_get_counts": (i32, [p, i32, p, p]),
@@ -161,6 +162,10 @@ class Oracle:
     def init_assignments(self):
         lib().orc_init_assignments(self.h)
 
+    def init_from_phi(self):
+        """inferencer initialisation (I:186-203) from the counts currently installed (set_counts)"""
+        lib().orc_init_from_phi(self.h)
+
     def set_assignments(self, zs):
         for m, z in enumerate(zs):
             z = np.ascontiguousarray(z, dtype=np.int32)
@@ -241,3 +246,23 @@ class Oracle:
 
     def check_invariants(self):
         return int(lib().orc_check_invariants(self.h))
+
+
+def doc_topic_proportions(views, zs, K, gamma, alpha, alphaSum, p_mean0, weights):
+    """theta_d[t] of the inferencer's output (I:385-412): sum_m w_m*pMean[0][m]*(n_d[m][t]+gamma_m*alpha_m[t])/(len_m+gamma_m*alphaSum_m)
+    over the views the document has, normalised by sum_m w_m*pMean[0][m] (w_0 = 1)."""
+    M, D = len(views), len(views[0][0]) - 1
+    out = np.zeros((D, K))
+    for d in range(D):
+        norm = 0.0
+        for m in range(M):
+            b, e = views[m][0][d], views[m][0][d + 1]
+            if e == b:
+                continue            # Assignments[m] == null (absent view)
+            cnt = np.bincount(zs[m][b:e], minlength=K).astype(np.float64)
+            wm = (1.0 if m == 0 else weights[m]) * p_mean0[m]
+            out[d] += wm * (cnt + gamma[m] * alpha[m][:K]) / ((e - b) + gamma[m] * alphaSum[m])
+            norm += wm
+        if norm > 0:
+            out[d] /= norm
+    return out

@@ -528,3 +528,73 @@ def test_estimate_with_hyper_parameter_step(engine_lib):
     assert np.all(model.beta > 0)
     series = model.perplexities[:, 1:7]
     assert np.all(series[:, -1] > ll0)
+
+
+# ---- inference on new documents --------------------------------------------------------------------
+@pytest.mark.parametrize("bare", [False, True])
+def test_inference_matches_oracle(engine_lib, oracle_mod, bare):
+    """FastQMVWVTopicInferencer path (I:114-330): trained counts installed into a handle over NEW documents, tree-draw
+    initialisation bit-exact vs the oracle's FTree sampling (I:186-203, incl. OOV -> topic 0), ten frozen sweeps tracking the
+    fp64 mirror, document-topic proportions of I:385-412.  bare=True: Q13 (trees without gamma*alpha)."""
+    from mvtopicmodel_b200 import Engine
+    O = oracle_mod
+    K, Vs = 37, [150, 40]           # K not a power of two: the heap-shaped FTree walks its leaves in rotated order
+    train = random_corpus(71, 500, K, Vs, [12, 3])
+    new = random_corpus(72, 120, K, Vs, [10, 3], oov=True)
+    t = Engine(K, Vs, train, seed=3)
+    t.init_assignments()
+    for it in range(1, 11):
+        t.sweep(it)
+    counts = [t.get_counts(m) for m in range(2)]
+    e = Engine(K, Vs, new, seed=9)
+    o = O.Oracle(K, Vs, new, seed=9)
+    for m in range(2):
+        e.set_counts(m, *counts[m]); o.set_counts(m, *counts[m])
+    e.init_assignments_from_counts(); o.init_from_phi()
+    for m in range(2):
+        ze, zo = e.get_assignments(m), o.get_assignments(m)
+        assert np.array_equal(ze, zo)
+        oov = new[m][1] >= Vs[m]
+        assert oov.any() and np.all(ze[oov] == 0)
+    G, JG = e.scan_layout()
+    o.set_engine_group(G)
+    flags = O.F_ENGINE_MIRROR | O.F_FROZEN | (O.F_BARE_TREES if bare else 0)
+    D = len(new[0][0]) - 1
+    for it in range(1, 11):
+        e.sweep(it, update_global=2 if bare else 0); o.sweep(it, flags)
+        zs_o = [o.get_assignments(m) for m in range(2)]
+        bad_docs = 0
+        for d in range(D):
+            if any(not np.array_equal(e.get_assignments(m)[new[m][0][d]:new[m][0][d + 1]], zs_o[m][new[m][0][d]:new[m][0][d + 1]]) for m in range(2)):
+                bad_docs += 1
+        assert bad_docs <= max(2, 0.03 * D), (it, bad_docs)
+        for m in range(2):                      # resynchronise: assignments only, the counts stay the trained ones
+            e.set_assignments(m, zs_o[m]); e.set_counts(m, *counts[m])
+    for m in range(2):
+        a, b = e.get_counts(m)
+        assert np.array_equal(a, counts[m][0]) and np.array_equal(b, counts[m][1])      # frozen
+
+
+def test_inferencer_mirror_proportions(engine_lib, oracle_mod):
+    from mvtopicmodel_b200 import corpus
+    from mvtopicmodel_b200.model import FastQMVWVParallelTopicModel, Instance, InstanceList
+    from oracle import oracle as OO
+    K, Vs, views = corpus.generate("tiny_2v")
+    D = len(views[0][0]) - 1
+    def lists(lo, hi):
+        return [InstanceList([Instance(f"d{d}", w[off[d]:off[d + 1]]) for d in range(lo, hi) if m == 0 or off[d + 1] > off[d]], alphabet_size=Vs[m])
+                for m, (off, w) in enumerate(views)]
+    model = FastQMVWVParallelTopicModel(K, 2, 0.1, 0.01)
+    model.setRandomSeed(4); model.setNumIterations(30); model.setBurninPeriod(50)
+    model.addInstances(lists(0, 250), "train", 0, None)
+    model.estimate()
+    inf = model.getInferencer()
+    names, theta = inf.inferTopicDistributions(lists(250, D))
+    assert len(names) == D - 250 and theta.shape == (D - 250, K)
+    assert np.allclose(theta.sum(axis=1), 1.0, atol=1e-9)         # each view's term is a distribution over K (alphaSum = K*alpha)
+    # same formula through the oracle-side restatement on the engine's final assignments
+    e = inf.engine
+    new_views = [(e_off, e_w) for (e_off, e_w) in [(np.array(v[0][250:] - v[0][250]), v[1][v[0][250]:]) for v in views]]
+    zs = [e.get_assignments(m) for m in range(2)]
+    want = OO.doc_topic_proportions(new_views, zs, K, inf.hyper["gamma"], inf.hyper["alpha"], inf.hyper["alphaSum"], inf.pMean[0], np.ones(2))
+    assert np.allclose(theta, want, rtol=1e-12, atol=1e-15)
