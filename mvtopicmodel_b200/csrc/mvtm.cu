@@ -468,7 +468,7 @@ static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
     return MVTM_OK;
 }
 
-struct LaunchCfg { int R, W, grid; size_t smem; };
+struct LaunchCfg { int R, W, grid, oc_smem; size_t smem; };
 
 // Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first four timed sweeps
 // alternate R = 1, 2, 1, 2 and the faster of the last two is kept: cache-resident tables (Zipf corpora) favour R = 1
@@ -489,15 +489,20 @@ static void ring_record(mvtm_handle *h, int m, float ms)
     if (++v.tune_step == 4) v.ring_locked = (v.tune_ms[3] < v.tune_ms[2]) ? 2 : 1;
 }
 
-static int choose_launch(mvtm_handle *h, int R, LaunchCfg &lc)
+static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
 {
     const int KS = h->KS, G = h->G, NSUB = 32 / G, JG = KS / (4 * G);
     const bool multi = h->M > 1;
+    // The other-view mass can live in shared memory instead of the global scratch (MVTM_OC_SMEM=1).  Measured on
+    // pubmed_3v / acm_2v: the extra 4*KS bytes per document cost more resident documents than the faster reads give
+    // back, even for the side views (5.7 vs 4.8 ms), so the default keeps it in global memory for every view.
+    (void)m;
+    const bool oc_smem = multi && getenv("MVTM_OC_SMEM") && atoi(getenv("MVTM_OC_SMEM")) != 0;
     R = std::max(1, std::min(R, 8));
     const size_t budget = 227 * 1024 - 1024;
     int docs;
     for (;;) {
-        docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0)) / smem_doc_bytes(KS, R, multi));
+        docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0)) / smem_doc_bytes(KS, R, multi, oc_smem));
         if (docs >= NSUB || R == 1) break;
         R--;
     }
@@ -510,8 +515,8 @@ static int choose_launch(mvtm_handle *h, int R, LaunchCfg &lc)
     if (h->cfg_ctas > 0) grid = std::min(grid, h->cfg_ctas);
     if (const char *e = getenv("MVTM_CTAS")) grid = std::max(1, std::min(grid, atoi(e)));
     if (h->flags & MVTM_FLAG_SINGLE_WARP) { W = 1; grid = 1; }
-    lc.R = R; lc.W = W; lc.grid = grid;
-    lc.smem = smem_cta_bytes(KS, multi ? h->M : 0) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi);
+    lc.R = R; lc.W = W; lc.grid = grid; lc.oc_smem = oc_smem ? 1 : 0;
+    lc.smem = smem_cta_bytes(KS, multi ? h->M : 0) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi, oc_smem);
     return MVTM_OK;
 }
 
@@ -578,7 +583,7 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
     if (int rc = upload_hyper(h)) return rc;
     LaunchCfg lcs[MVTM_MAX_VIEWS];
     for (int m = 0; m < h->M; m++) {
-        if (int rc = choose_launch(h, ring_for_view(h, m), lcs[m])) return rc;
+        if (int rc = choose_launch(h, m, ring_for_view(h, m), lcs[m])) return rc;
         if (int rc = ensure_oc_scratch(h, (size_t)lcs[m].grid * lcs[m].W * (32 / h->G))) return rc;
     }
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
@@ -592,7 +597,7 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
             CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
             SweepParams P;
             fill_params(h, m, iteration, update_global, P);
-            P.R = lcs[m].R;
+            P.R = lcs[m].R; P.oc_smem = lcs[m].oc_smem;
             CK(h, launch_sweep(h, P, lcs[m]));
             launches++;
         }

@@ -51,6 +51,7 @@ struct SweepParams {
     int R;                            // ring depth
     unsigned long long *stats;        // [0] tokens, [1] changed, [2] new-topic draws
     float *oc_scratch;                // (multi-view) per resident document slot: Kp floats, see DocCtx::oc
+    int oc_smem;                      // (multi-view) 1: keep DocCtx::oc in shared memory instead (views of short documents)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,16 +128,16 @@ template <bool MULTI>
 __device__ __forceinline__ float q_value(float ndv, bool inS, float ocv, float pri, float coefm, float pmm, float2 gi)
 {
     float v = ndv * pmm;
-    if (MULTI) { if (inS) v += coefm * (ocv + pri); }
+    if (MULTI) v += inS ? coefm * (ocv + pri) : 0.f;
     return (v + gi.x) * gi.y;
 }
 
 template <bool MULTI>
 __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx &c, int t)
-{
+{   // sum_i c_i * gamma_i*alpha_i[t] (W:404); c_i = 0 for the own view and for absent views, so no branch is needed
     float pri = 0.f;
     if (MULTI) {
-        for (int i = 0; i < P.M; i++) { float ci = c.cpar[i]; if (ci != 0.f) pri += ci * c.gaf[(size_t)i * c.gaf_stride + t]; }
+        for (int i = 0; i < P.M; i++) pri = fmaf(c.cpar[i], c.gaf[(size_t)i * c.gaf_stride + t], pri);
     }
     return pri;
 }
@@ -152,9 +153,11 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
     const float ndv = (float)ndv_i;
     bool inS = false; float ocv = 0.f, pri = 0.f;
     if (MULTI) {
+        // branch-light on purpose: the lane groups of a warp hold different documents and would serialise on branches
         const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
         inS = (ndv_i > 0u) || oth;
-        if (inS) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
+        pri = prior_other<MULTI>(P, c, t);
+        if (oth) ocv = c.oc[t];
     }
     c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
     constexpr int LG = ilog2(G);
@@ -366,20 +369,23 @@ __device__ __forceinline__ int group_select(const int4 *row4, const float4 *q4, 
 
 // shared-memory carve-up -------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi) { return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4; }
-__host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi)
+__host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi, bool oc_smem = false)
 {
     size_t b = (size_t)KS * 4 + (size_t)KS * 2;                   // q, nd
     if (multi) b += 256 + 64;                                     // om (<= 64 words), cpar
+    if (multi && oc_smem) b += (size_t)KS * 4;                    // oc in shared memory
     b += (size_t)R * KS * 4 + 128;                                // ring + mbarriers
     return (b + 127) & ~(size_t)127;
 }
 
-__device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bool multi, DocCtx &c, int *&ring, unsigned long long *&mbar)
+__device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bool multi, DocCtx &c, int *&ring, unsigned long long *&mbar,
+                                          bool oc_smem = false)
 {
     unsigned char *p = base;
     ring = reinterpret_cast<int *>(p); p += (size_t)R * KS * 4;
     c.q = reinterpret_cast<float *>(p); p += (size_t)KS * 4;
     c.oc = nullptr;
+    if (multi && oc_smem) { c.oc = reinterpret_cast<float *>(p); p += (size_t)KS * 4; }
     c.nd = reinterpret_cast<unsigned short *>(p); p += (size_t)KS * 2;
     if (multi) { c.om = reinterpret_cast<unsigned *>(p); p += 256; c.cpar = reinterpret_cast<float *>(p); p += 64; }
     else { c.om = nullptr; c.cpar = nullptr; }
@@ -416,9 +422,10 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
         }
     }
     DocCtx c; int *ring; unsigned long long *mbar;
-    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(warp * NSUB + sub) * smem_doc_bytes(KS, R, MULTI), KS, R, MULTI, c, ring, mbar);
+    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(warp * NSUB + sub) * smem_doc_bytes(KS, R, MULTI, P.oc_smem != 0), KS, R, MULTI,
+              c, ring, mbar, P.oc_smem != 0);
     c.gaf = reinterpret_cast<const float *>(smem + (size_t)KS * 12); c.gaf_stride = KS;
-    if (MULTI) c.oc = P.oc_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) * NSUB + (size_t)(warp * NSUB + sub)) * P.Kp;
+    if (MULTI && !P.oc_smem) c.oc = P.oc_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) * NSUB + (size_t)(warp * NSUB + sub)) * P.Kp;
     uint32_t cta_sa = smem_u32(smem);
     asm volatile("" : "+r"(cta_sa));                              // opaque: hold the base in a register
     c.ginv_sa = cta_sa;
@@ -436,29 +443,44 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
     int *zmv = P.zv[m];
     float bsq[JG];
 
-    for (;;) {
-        int item0 = 0;
-        if (lane == 0) item0 = atomicAdd(P.work_counter, NSUB);
-        item0 = __shfl_sync(FULL, item0, 0);
-        if (item0 >= P.n_items) break;
-        const bool have = item0 + sub < P.n_items;                 // the last fetch may leave trailing groups idle
-        const int d = have ? __ldg(P.order + item0 + sub) : 0;
-        const long long b = P.doc_off[m][d];
-        const int len = have ? (int)(P.doc_off[m][d + 1] - b) : 0;
+    // Work items are claimed two documents ahead and the next document's offsets and first tokens are loaded while the
+    // current one is being sampled, so a new document starts with everything in registers (short documents -- side
+    // views, SMS-sized corpora -- would otherwise pay three dependent global-memory latencies each).
+    auto claim = [&]() { int it = 0; if (lane == 0) it = atomicAdd(P.work_counter, NSUB); return it; };
+    int item0 = __shfl_sync(FULL, claim(), 0);
+    int item_next_raw = claim();                                   // lane 0 holds it; broadcast when consumed
+    int d = 0, len = 0, wcur = 0, zcur = -1, wnext = 0, wahead = 0;
+    long long b = 0;
+    {
+        const bool have = item0 + sub < P.n_items;
+        d = have ? __ldg(P.order + item0 + sub) : 0;
+        b = P.doc_off[m][d];
+        len = have ? (int)(P.doc_off[m][d + 1] - b) : 0;
+        wcur = (gl < len) ? __ldg(P.word + b + gl) : 0;
+        zcur = (gl < len) ? zmv[b + gl] : -1;
+        wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
+        wahead = (R + gl < len) ? __ldg(P.word + b + R + gl) : 0;  // word of the token R positions ahead
+    }
+    while (item0 < P.n_items) {
         const int maxlen = (NSUB == 1) ? len : __reduce_max_sync(FULL, len);
         const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
+        // pipeline stage 1: claim the item after next, start loading the next document's id
+        const int item_n = __shfl_sync(FULL, item_next_raw, 0);
+        item_next_raw = claim();
+        const bool have_n = item_n + sub < P.n_items;
+        const int d_n = have_n ? __ldg(P.order + item_n + sub) : 0;
 
-        // first block of tokens; rows of the first R tokens go in flight before the per-document setup
-        int wcur = (gl < len) ? __ldg(P.word + b + gl) : 0;
-        int zcur = (gl < len) ? zmv[b + gl] : -1;
-        int wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
-        int wahead = (R + gl < len) ? __ldg(P.word + b + R + gl) : 0;        // word of the token R positions ahead
+        // rows of the first R tokens go in flight before the per-document setup
         for (int i = 0; i < R; i++) {
             int w = __shfl_sync(FULL, wcur, i, G);
             if ((unsigned)w >= (unsigned)P.V) w = 0;
             if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
         doc_setup<KS, G, MULTI>(P, c, d, len, gl, nullptr, true, bsq);
+        // pipeline stage 2 (d_n has arrived during the setup): next document's extent and first tokens
+        const long long b_n = P.doc_off[m][d_n];
+        const int len_n = have_n ? (int)(P.doc_off[m][d_n + 1] - b_n) : 0;
+        int wcur_n = 0, zcur_n = -1, wnext_n = 0, wahead_n = 0;    // loaded after the first token block (stage 3)
 
         int slot = 0;
         for (int base = 0; base < maxlen; base += G) {
@@ -522,7 +544,21 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             wahead = (base + G + R + gl < len) ? __ldg(P.word + b + base + G + R + gl) : 0;
             zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;
             wnext = (base + 2 * G + gl < len) ? __ldg(P.word + b + base + 2 * G + gl) : 0;
+            if (base == 0) {   // pipeline stage 3: the next document's first tokens (its offsets arrived long ago)
+                wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
+                zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
+                wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
+                wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
+            }
         }
+        if (maxlen == 0) {     // (cannot happen: the work list holds non-empty documents only; keeps the pipeline total)
+            wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
+            zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
+            wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
+            wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
+        }
+        item0 = item_n; d = d_n; b = b_n; len = len_n;
+        wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n;
     }
     if (gl == 0) {
         if (n_tok) atomicAdd(P.stats + 0, n_tok);

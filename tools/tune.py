@@ -29,6 +29,9 @@ if __name__ == "__main__":
     if which in ("uniform",):
         run("uniform_k1000_v400k", corpus.generate_uniform(100_000, 1000, 400_000, 200), [(0, 1), (0, 2), (0, 3)], sweeps=4, warm=1)
         run("uniform_k500_v400k", corpus.generate_uniform(100_000, 500, 400_000, 200), [(0, 1), (0, 2), (0, 3)], sweeps=4, warm=1)
+    if which in ("stress",):
+        cfg = dict(corpus.CONFIGS["stress_4v"]); cfg["D"] = 60_000
+        run("stress_4v_60k", cfg, [(0, 0)], sweeps=4, warm=4)
     if which in ("acmtext",):
         cfg = dict(D=400_000, K=1000, views=[(100_000, 120, 0.5, 1.0, 1024)])
         run("acm_text_only", cfg, [(0, 0)], sweeps=4, warm=1)
