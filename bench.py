@@ -187,6 +187,9 @@ def main():
             xch.exchange_sum()          # every rank holds the same global counts at sweep start
 
     it = 0
+    for _ in range(4):          # set-up: the engine's ring-depth autotune settles over its first four sweeps (not warm-up, not timed)
+        it += 1
+        step(it)
     for _ in range(args.warmup):
         it += 1
         step(it)
@@ -283,7 +286,7 @@ def main():
     achieved = btok * ntok_local * args.steps / kern_s / 1e9 if kern_s > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.workload == "lda_100k" and args.docs is None:      # the capture is of this workload's kernel
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:

@@ -598,3 +598,53 @@ def test_inferencer_mirror_proportions(engine_lib, oracle_mod):
     zs = [e.get_assignments(m) for m in range(2)]
     want = OO.doc_topic_proportions(new_views, zs, K, inf.hyper["gamma"], inf.hyper["alpha"], inf.hyper["alphaSum"], inf.pMean[0], np.ones(2))
     assert np.allclose(theta, want, rtol=1e-12, atol=1e-15)
+
+
+# ---- edge cases: empty and ragged inputs, maximum sizes ----------------------------------------------------------------
+def test_edge_cases_sizes(engine_lib, oracle_mod):
+    from mvtopicmodel_b200 import Engine, MvtmError
+    O = oracle_mod
+    rng = np.random.default_rng(0)
+    # (1) a view in which every document is empty, and a corpus of empty documents only
+    off0 = np.array([0, 3, 3, 7], dtype=np.int64); w0 = rng.integers(0, 9, 7).astype(np.int32)
+    e = Engine(6, [9, 4], [(off0, w0), (np.zeros(4, dtype=np.int64), np.zeros(0, dtype=np.int32))], seed=1)
+    e.init_assignments()
+    for it in range(1, 4):
+        e.sweep(it)
+    assert e.check_invariants() == 0 and e.stats()["tokens"] == 7
+    assert np.isfinite(e.loglik()).all()
+    e = Engine(6, [9], [(np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.int32))], seed=1)
+    e.init_assignments(); e.sweep(1)
+    assert e.check_invariants() == 0 and e.stats()["tokens"] == 0
+    # (2) the longest document this build accepts (65535 tokens) next to one-token documents; one token more is refused
+    lens = np.array([65535, 1, 1, 2], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    w = rng.integers(0, 50, int(off[-1])).astype(np.int32)
+    e = Engine(50, [50], [(off, w)], seed=2)
+    o = O.Oracle(50, [50], [(off, w)], seed=2)
+    e.init_assignments(); o.init_assignments()
+    assert np.array_equal(e.get_assignments(0), o.get_assignments(0))
+    e.sweep(1)
+    assert e.check_invariants() == 0 and e.stats()["tokens"] == int(off[-1])
+    hist = e.doc_topic_hist(0)
+    assert hist.shape == (50, 65536) and hist[:, 1:].sum() >= 4
+    with pytest.raises(MvtmError) as ei:
+        Engine(50, [50], [(np.array([0, 65536], dtype=np.int64), rng.integers(0, 50, 65536).astype(np.int32))])
+    assert ei.value.status == 5
+    # (3) the largest K of this build (2048: 32 lanes x 16 chunks) and a one-word vocabulary
+    views = random_corpus(5, 200, 2048, [1, 30], [15, 3])
+    e = Engine(2048, [1, 30], views, seed=3)
+    o = O.Oracle(2048, [1, 30], views, seed=3)
+    e.init_assignments(); o.init_assignments()
+    for m in range(2):
+        assert np.array_equal(e.get_assignments(m), o.get_assignments(m))
+    for it in range(1, 4):
+        e.sweep(it)
+    assert e.check_invariants() == 0
+    p = np.array([[1.0, 0.25], [0.25, 1.0]])
+    d = int(np.argmax(views[1][0][1:] - views[1][0][:-1]))
+    for m in range(2):
+        e.set_assignments(m, e.get_assignments(m))
+    o.set_assignments([e.get_assignments(m) for m in range(2)])
+    ref, got = o.cond_probs(1, d, 0, p=p), e.cond_probs(1, d, 0, p_row=p[1])
+    assert np.max(np.abs(got[:2048] - ref[:2048]) / ref[:2048]) <= REL_TOL_COND
