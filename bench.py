@@ -126,6 +126,9 @@ def main():
     ap.add_argument("--cpu-sample-docs", type=int, default=25000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange the counts after the sweep instead of under it")
+    ap.add_argument("--reserve-sms", type=int, default=int(os.environ.get("MVTM_RESERVE_SMS", "8")),
+                    help="N > 1 with overlap: SMs the persistent sweep kernel leaves to the collective")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -154,9 +157,13 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # a single view has nothing to hide its exchange under (its next pass needs the result at once): serial there
+    overlap = world > 1 and len(cfg["views"]) > 1 and not args.no_overlap
+    if overlap:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(max(1, args.reserve_sms)))     # the collective lives on the SMs the sweep leaves free
     import torch
     from mvtopicmodel_b200 import Engine
-    from mvtopicmodel_b200.dist import CountExchange, EngineAdapter
+    from mvtopicmodel_b200.dist import CountExchange, EngineAdapter, OverlapAdapter, OverlappedSweep
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -165,15 +172,20 @@ def main():
     K, Vs, views = corpus.generate(args.workload, shard=rank, docs=args.docs)
     M = len(views)
     D_local = len(views[0][0]) - 1
-    eng = Engine(K, Vs, views, seed=2026, device=local_rank, doc_id_base=rank, doc_id_stride=world)
+    n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    eng = Engine(K, Vs, views, seed=2026, device=local_rank, doc_id_base=rank, doc_id_stride=world,
+                 max_ctas=(n_sms - args.reserve_sms) if overlap else 0)
     ntok_local = sum(eng.ntok)
-    xch = None
+    xch, ovl = None, None
     if world > 1:
         xch = CountExchange(EngineAdapter(eng, local_rank))
         xch.reset()
     eng.init_assignments()
     if xch:
         xch.exchange()
+    if overlap:
+        ovl_adapter = OverlapAdapter(eng, local_rank)
+        ovl = OverlappedSweep(ovl_adapter)
 
     def barrier():
         torch.cuda.synchronize()
@@ -182,9 +194,16 @@ def main():
         torch.cuda.synchronize()
 
     def step(it):
+        if ovl:
+            ovl.step(it)                # view m's all-reduce runs under the passes of the following views / next sweep
+            return
         eng.sweep(it)
         if xch:
             xch.exchange_sum()          # every rank holds the same global counts at sweep start
+
+    def drain():
+        if ovl:
+            ovl_adapter.drain()         # the last views' exchange belongs to the timed region
 
     it = 0
     for _ in range(4):          # set-up: the engine's ring-depth autotune settles over its first four sweeps (not warm-up, not timed)
@@ -207,6 +226,7 @@ def main():
         st = eng.stats()
         kern_ms += sum(st["ms_view"])
         changed += st["changed"]
+    drain()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -247,7 +267,7 @@ def main():
                 for m in range(M):
                     eng.set_assignments(m, zn[m])          # H2D + local rebuild
                 xch.reset(); xch.exchange()                # local counts -> global counts
-                eng.sweep(i); xch.exchange_sum()
+                step(i); drain()
                 for m in range(M):
                     eng.get_assignments(m, out=zn[m])      # D2H into the pinned buffer
             else:
@@ -303,7 +323,9 @@ def main():
                          "avg_launch_ms": kern_ms_max / args.steps / M, "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": args.steps * M, "clocks": clocks}
     if xch:
-        line["config"]["allreduce_bytes_per_sweep"] = xch.bytes_per_exchange
+        line["config"]["allreduce_bytes_per_sweep"] = ovl.bytes_per_exchange if ovl else xch.bytes_per_exchange
+        line["config"]["exchange"] = (f"overlapped: view m's all-reduce under the following passes, sweep grid {n_sms - args.reserve_sms} CTAs, "
+                                      f"NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}") if ovl else "after the sweep (serial)"
     if world == 1 and not args.no_cpu_baseline:
         val, ms, ntok_s, _ = cpu_reference_run(args.workload, args.cpu_sample_docs, 3, 1, threads)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

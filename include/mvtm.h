@@ -154,6 +154,25 @@ int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_
 int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world_size);
 int mvtm_row_stride(mvtm_handle *h, int32_t *stride_out);
 
+/* Overlapped exchange.  The reference's barrier M:1231 only requires that view m's counts are complete before view m is
+ * sampled AGAIN, so the exchange of view m may run while the following views (and the next sweep's earlier views) are being
+ * sampled.  The sweep is queued one view pass at a time without host synchronisation:
+ *     for m: mvtm_sweep_view_async(h, it, m, 1)            -- waits (on the device) for anything handed over for view m
+ *            mvtm_stream_wait_view(h, m, comm)              -- the caller's stream `comm` (a cudaStream_t) waits for that pass
+ *            <all-reduce of mvtm_sum_exchange_buffers(m) on comm; n_k follows n_wk in the same allocation, so ONE
+ *             all-reduce of n_wk_elems + n_k_elems ints starting at n_wk_dev covers both>
+ *            mvtm_sum_exchange_finish_async(h, m, N, comm, ctas)   -- the finishing pass, queued on comm
+ *            mvtm_view_wait_stream(h, m, comm)              -- hand view m back: its next pass / any reader waits for comm
+ *     mvtm_sweep_finish(h)                                  -- host side of the barrier: waits for the queued PASSES only
+ *                                                              (not for comm), fills mvtm_stats
+ * The caller leaves SMs free for the collective by creating the handle with mvtm_config.max_ctas < the SM count
+ * (the sweep kernel is persistent and otherwise owns every SM's shared memory until it ends). */
+int mvtm_sweep_view_async(mvtm_handle *h, int32_t iteration, int32_t m, int32_t update_global);
+int mvtm_sweep_finish(mvtm_handle *h);
+int mvtm_stream_wait_view(mvtm_handle *h, int32_t m, void *stream);
+int mvtm_view_wait_stream(mvtm_handle *h, int32_t m, void *stream);
+int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size, void *stream, int32_t max_ctas);
+
 /* Scan layout of the sampler (for order-exact checkers): a document-view is sampled by `lanes_per_doc` lanes (8, 16 or
  * 32); topic t sits in 4-topic chunk c = t/4 owned by lane c % lanes_per_doc as its (c / lanes_per_doc)-th chunk, and the
  * cumulative scan runs lane-major (all chunks of lane 0, then lane 1, ...). */

@@ -56,6 +56,11 @@ SIGNATURES = {
     "mvtm_sum_exchange_buffers": (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
     "mvtm_sum_exchange_finish": (_i32, [_vp, _i32, _i32]),
     "mvtm_row_stride": (_i32, [_vp, C.POINTER(_i32)]),
+    "mvtm_sweep_view_async": (_i32, [_vp, _i32, _i32, _i32]),
+    "mvtm_sweep_finish": (_i32, [_vp]),
+    "mvtm_stream_wait_view": (_i32, [_vp, _i32, _vp]),
+    "mvtm_view_wait_stream": (_i32, [_vp, _i32, _vp]),
+    "mvtm_sum_exchange_finish_async": (_i32, [_vp, _i32, _i32, _vp, _i32]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),
     "mvtm_p_statistics": (_i32, [_vp, _vp, _vp]),

@@ -59,6 +59,10 @@ struct mvtm_handle {
     bool hyper_dirty = true;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
+    cudaEvent_t ev_done[MVTM_MAX_VIEWS], ev_ready[MVTM_MAX_VIEWS];   // hand-over points with a caller-owned stream (async exchange)
+    bool ready_pending[MVTM_MAX_VIEWS] = { false }, pass_queued[MVTM_MAX_VIEWS] = { false };
+    bool sweep_open = false;
+    int open_launches = 0, open_mode = 1;
     int *work_counter = nullptr;
     float *oc_scratch = nullptr;                    // multi-view: Kp floats per resident document slot
     size_t oc_scratch_floats = 0;
@@ -80,6 +84,9 @@ static std::string g_create_err;
         cudaError_t _e = (call);                                                                             \
         if (_e != cudaSuccess) FAIL(h, MVTM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+static int wait_view_ready(mvtm_handle *h, int m);
+static int wait_all_ready(mvtm_handle *h);
 
 static int pick_J(int K)
 {
@@ -149,6 +156,10 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
     h->num_sms = prop.multiProcessorCount;
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &ev : h->ev) CKC(cudaEventCreate(&ev));
+    for (int m = 0; m < MVTM_MAX_VIEWS; m++) {
+        CKC(cudaEventCreateWithFlags(&h->ev_done[m], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&h->ev_ready[m], cudaEventDisableTiming));
+    }
     CKC(cudaMalloc(&h->work_counter, sizeof(int)));
     CKC(cudaMalloc(&h->d_stats, 4 * sizeof(unsigned long long)));
     CKC(cudaMalloc(&h->d_bad, sizeof(int)));
@@ -159,8 +170,9 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
 
 static void free_view(ViewDev &v)
 {
-    cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk); cudaFree(v.nk);
-    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk); cudaFree(v.snap_nk);
+    // nk / snap_nk are row V of the nwk / snap_nwk allocations (one all-reduce covers table and totals)
+    cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk);
     v = ViewDev();
 }
 
@@ -171,6 +183,7 @@ extern "C" int mvtm_destroy(mvtm_handle *h)
     cudaStreamSynchronize(h->stream);
     for (int m = 0; m < h->M; m++) free_view(h->v[m]);
     for (auto &ev : h->ev) cudaEventDestroy(ev);
+    for (int m = 0; m < MVTM_MAX_VIEWS; m++) { cudaEventDestroy(h->ev_done[m]); cudaEventDestroy(h->ev_ready[m]); }
     cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad); cudaFree(h->oc_scratch);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -232,8 +245,8 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMalloc(&v.z, (size_t)std::max<long long>(N, 1) * 4));
     CK(h, cudaMalloc(&v.present, pres.size()));
     CK(h, cudaMalloc(&v.order, (size_t)std::max<int>(v.n_items, 1) * 4));
-    CK(h, cudaMalloc(&v.nwk, (size_t)v.V * Kp * 4));
-    CK(h, cudaMalloc(&v.nk, Kp * 4));
+    CK(h, cudaMalloc(&v.nwk, ((size_t)v.V + 1) * Kp * 4));
+    v.nk = v.nwk + (size_t)v.V * Kp;
     CK(h, cudaMalloc(&v.nk_snap, Kp * 4));
     CK(h, cudaMalloc(&v.ga_tree, Kp * 4));
     CK(h, cudaMalloc(&v.ga_full, Kp * 4));
@@ -262,6 +275,7 @@ static int rebuild_counts_view(mvtm_handle *h, int m)
 {
     ViewDev &v = h->v[m];
     const size_t Kp = (size_t)h->Kp;
+    if (int rc = wait_view_ready(h, m)) return rc;
     CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * Kp * 4, h->stream));
     CK(h, cudaMemsetAsync(v.nk, 0, Kp * 4, h->stream));
     CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
@@ -282,6 +296,7 @@ extern "C" int mvtm_init_assignments(mvtm_handle *h)
     if (!h) return MVTM_ERR_ARG;
     if (int rc = require_views(h, "mvtm_init_assignments")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     for (int m = 0; m < h->M; m++) {
         ViewDev &v = h->v[m];
         if (v.n_tok > 0) {
@@ -313,6 +328,7 @@ extern "C" int mvtm_set_counts(mvtm_handle *h, int32_t m, const int32_t *n_wk, c
     if (!h) return MVTM_ERR_ARG;
     if (m < 0 || m >= h->M || !h->v[m].added || !n_wk || !n_k) FAIL(h, MVTM_ERR_ARG, "mvtm_set_counts: bad argument");
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     ViewDev &v = h->v[m];
     for (int t = 0; t < h->K; t++) if (n_k[t] < 0) FAIL(h, MVTM_ERR_CORRUPT, "mvtm_set_counts: negative n_k[%d]", t);
     CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * h->Kp * 4, h->stream));
@@ -328,6 +344,7 @@ extern "C" int mvtm_init_assignments_from_counts(mvtm_handle *h)
     if (!h) return MVTM_ERR_ARG;
     if (int rc = require_views(h, "mvtm_init_assignments_from_counts")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     const int K = h->K;
     int P2 = 1; while (P2 * 2 <= 2 * K - 1) P2 *= 2;                  // 2^floor(log2(2K-1)): first index of the deepest tree level
     const int rot = P2 - K;
@@ -361,6 +378,7 @@ extern "C" int mvtm_get_counts(mvtm_handle *h, int32_t m, int32_t *n_wk_out, int
     if (!h) return MVTM_ERR_ARG;
     if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_get_counts: bad view %d", m);
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
     ViewDev &v = h->v[m];
     if (n_wk_out)
         CK(h, cudaMemcpy2DAsync(n_wk_out, (size_t)h->K * 4, v.nwk, (size_t)h->Kp * 4, (size_t)h->K * 4, (size_t)v.V, cudaMemcpyDeviceToHost, h->stream));
@@ -576,50 +594,93 @@ static int activate_sampled_topics(mvtm_handle *h)
     return MVTM_OK;
 }
 
-static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool sync_stats)
+// A view's tables may be owned for a while by work the CALLER queued on a stream of its own (the overlapped count exchange
+// of a multi-GPU run, mvtm_view_wait_stream): everything here that touches them first orders the handle's stream behind it.
+static int wait_view_ready(mvtm_handle *h, int m)
 {
+    if (h->ready_pending[m]) {
+        CK(h, cudaStreamWaitEvent(h->stream, h->ev_ready[m], 0));
+        h->ready_pending[m] = false;
+    }
+    return MVTM_OK;
+}
+static int wait_all_ready(mvtm_handle *h)
+{
+    for (int m = 0; m < h->M; m++) if (int rc = wait_view_ready(h, m)) return rc;
+    return MVTM_OK;
+}
+
+// Queues view m's pass (n_k snapshot, work counter reset, k_sweep_view) on the handle's stream; no host synchronisation.
+static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, int m, int *launches)
+{
+    ViewDev &v = h->v[m];
+    LaunchCfg lc;
+    if (int rc = choose_launch(h, m, ring_for_view(h, m), lc)) return rc;
+    if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
+    if (int rc = wait_view_ready(h, m)) return rc;
+    CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
+    if (v.n_items > 0) {
+        CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+        SweepParams P;
+        fill_params(h, m, iteration, update_global, P);
+        P.R = lc.R; P.oc_smem = lc.oc_smem;
+        CK(h, launch_sweep(h, P, lc));
+        (*launches)++;
+    }
+    CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
+    h->pass_queued[m] = true;
+    return MVTM_OK;
+}
+
+static int open_sweep(mvtm_handle *h)
+{
+    if (h->sweep_open) return MVTM_OK;
     if (int rc = require_views(h, "mvtm_sweep")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = upload_hyper(h)) return rc;
-    LaunchCfg lcs[MVTM_MAX_VIEWS];
-    for (int m = 0; m < h->M; m++) {
-        if (int rc = choose_launch(h, m, ring_for_view(h, m), lcs[m])) return rc;
-        if (int rc = ensure_oc_scratch(h, (size_t)lcs[m].grid * lcs[m].W * (32 / h->G))) return rc;
-    }
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(h, cudaEventRecord(h->ev[0], h->stream));
-    int launches = 0;
-    for (int m = 0; m < h->M; m++) {
-        ViewDev &v = h->v[m];
-        CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
-        if (v.n_items > 0) {
-            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
-            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-            SweepParams P;
-            fill_params(h, m, iteration, update_global, P);
-            P.R = lcs[m].R; P.oc_smem = lcs[m].oc_smem;
-            CK(h, launch_sweep(h, P, lcs[m]));
-            launches++;
-        }
-        CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
-    }
+    for (int m = 0; m < h->M; m++) h->pass_queued[m] = false;
+    h->open_launches = 0;
+    h->sweep_open = true;
+    return MVTM_OK;
+}
+
+// Host side of the barrier M:1231: waits for the queued passes, reads the counters and the per-view device times.
+static int close_sweep(mvtm_handle *h, int update_global)
+{
+    if (!h->sweep_open) return MVTM_OK;
+    h->sweep_open = false;
     CK(h, cudaEventRecord(h->ev[1], h->stream));
-    if (sync_stats) {
-        unsigned long long st[4];
-        CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
-        CK(h, cudaStreamSynchronize(h->stream));
-        h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
-        float ms = 0.f;
-        CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        h->stats.ms_total = ms;
-        for (int m = 0; m < h->M; m++) {
-            CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m]));
-            h->stats.ms_view[m] = ms;
-            if (h->v[m].n_items > 0) ring_record(h, m, ms);
-        }
-        h->stats.kernel_launches = launches;
-        if (update_global == 1) if (int rc = activate_sampled_topics(h)) return rc;
+    unsigned long long st[4];
+    CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->stats.ms_total = ms;
+    for (int m = 0; m < h->M; m++) {
+        h->stats.ms_view[m] = 0.0;
+        if (!h->pass_queued[m]) continue;
+        CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m]));
+        h->stats.ms_view[m] = ms;
+        if (h->v[m].n_items > 0) ring_record(h, m, ms);
     }
+    h->stats.kernel_launches = h->open_launches;
+    if (update_global == 1) if (int rc = activate_sampled_topics(h)) return rc;
+    return MVTM_OK;
+}
+
+static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool sync_stats)
+{
+    if (h->sweep_open) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep: passes queued by mvtm_sweep_view_async are still open (call mvtm_sweep_finish)");
+    if (int rc = open_sweep(h)) return rc;
+    for (int m = 0; m < h->M; m++)
+        if (int rc = enqueue_view_pass(h, iteration, update_global, m, &h->open_launches)) { h->sweep_open = false; return rc; }
+    if (sync_stats) return close_sweep(h, update_global);
+    h->sweep_open = false;
+    CK(h, cudaEventRecord(h->ev[1], h->stream));
     return MVTM_OK;
 }
 
@@ -627,6 +688,45 @@ extern "C" int mvtm_sweep(mvtm_handle *h, int32_t iteration, int32_t update_glob
 {
     if (!h) return MVTM_ERR_ARG;
     return sweep_impl(h, iteration, update_global, true);
+}
+
+// ---- non-blocking form: one view pass at a time, so a multi-GPU caller can overlap the count exchange of view m with the
+// sampling of the following views ------------------------------------------------------------------------------
+extern "C" int mvtm_sweep_view_async(mvtm_handle *h, int32_t iteration, int32_t m, int32_t update_global)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_view_async: bad view %d", m);
+    if (update_global < 0 || update_global > 2) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_view_async: bad update_global");
+    if (int rc = open_sweep(h)) return rc;
+    h->open_mode = update_global;
+    return enqueue_view_pass(h, iteration, update_global, m, &h->open_launches);
+}
+
+extern "C" int mvtm_sweep_finish(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    CK(h, cudaSetDevice(h->device));
+    return close_sweep(h, h->open_mode);
+}
+
+extern "C" int mvtm_stream_wait_view(mvtm_handle *h, int32_t m, void *stream)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_stream_wait_view: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaEventRecord(h->ev_done[m], h->stream));
+    CK(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_done[m], 0));
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_view_wait_stream(mvtm_handle *h, int32_t m, void *stream)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_view_wait_stream: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaEventRecord(h->ev_ready[m], (cudaStream_t)stream));
+    h->ready_pending[m] = true;
+    return MVTM_OK;
 }
 
 extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout)
@@ -672,6 +772,7 @@ extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t p
     long long len = v.h_doc_off[(size_t)doc + 1] - v.h_doc_off[(size_t)doc];
     if (pos < 0 || pos >= len) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: position %d outside document of %lld tokens", pos, len);
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     if (int rc = upload_hyper(h)) return rc;
     if (int rc = ensure_oc_scratch(h, (size_t)(32 / h->G))) return rc;
     int w = 0;
@@ -744,6 +845,7 @@ extern "C" int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2)
     if (!ll_out) FAIL(h, MVTM_ERR_ARG, "mvtm_loglik: NULL output");
     if (int rc = require_views(h, "mvtm_loglik")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     const int K = h->K;
     const long long D = h->D;
     double *d_ga = nullptr, *d_tlg = nullptr, *d_doc = nullptr, *d_part = nullptr;
@@ -799,6 +901,7 @@ extern "C" int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out)
     if (!violations_out) FAIL(h, MVTM_ERR_ARG, "mvtm_check_invariants: NULL output");
     if (int rc = require_views(h, "mvtm_check_invariants")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     unsigned long long *d_bad = nullptr;
     CK(h, cudaMalloc(&d_bad, 8));
     cudaError_t e = cudaMemsetAsync(d_bad, 0, 8, h->stream);
@@ -840,10 +943,11 @@ extern "C" int mvtm_delta_begin(mvtm_handle *h)
     if (!h) return MVTM_ERR_ARG;
     if (int rc = require_views(h, "mvtm_delta_begin")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     for (int m = 0; m < h->M; m++) {
         ViewDev &v = h->v[m];
         const size_t n = (size_t)v.V * h->Kp;
-        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, n * 4)); CK(h, cudaMalloc(&v.snap_nk, (size_t)h->Kp * 4)); }
+        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, (n + h->Kp) * 4)); v.snap_nk = v.snap_nwk + n; }
         CK(h, cudaMemcpyAsync(v.snap_nwk, v.nwk, n * 4, cudaMemcpyDeviceToDevice, h->stream));
         CK(h, cudaMemcpyAsync(v.snap_nk, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
     }
@@ -856,10 +960,11 @@ extern "C" int mvtm_delta_reset(mvtm_handle *h)
     if (!h) return MVTM_ERR_ARG;
     if (int rc = require_views(h, "mvtm_delta_reset")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     for (int m = 0; m < h->M; m++) {
         ViewDev &v = h->v[m];
         const size_t n = (size_t)v.V * h->Kp;
-        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, n * 4)); CK(h, cudaMalloc(&v.snap_nk, (size_t)h->Kp * 4)); }
+        if (!v.snap_nwk) { CK(h, cudaMalloc(&v.snap_nwk, (n + h->Kp) * 4)); v.snap_nk = v.snap_nwk + n; }
         CK(h, cudaMemsetAsync(v.snap_nwk, 0, n * 4, h->stream));
         CK(h, cudaMemsetAsync(v.snap_nk, 0, (size_t)h->Kp * 4, h->stream));
     }
@@ -874,6 +979,7 @@ extern "C" int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_export: call mvtm_delta_begin first");
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
     const long long n = (long long)v.V * h->Kp;
     k_sub_inplace<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk);
     k_sub_inplace<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk);
@@ -893,6 +999,7 @@ extern "C" int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_buffers: call mvtm_delta_begin first");
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
     if (n_wk_dev) *n_wk_dev = v.nwk;
     if (n_wk_elems) *n_wk_elems = (long long)v.V * h->Kp;
@@ -908,11 +1015,28 @@ extern "C" int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_finish: call mvtm_delta_begin first");
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
     const long long n = (long long)v.V * h->Kp;
     k_finish_sum_exchange<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk, world_size - 1);
     k_finish_sum_exchange<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk, world_size - 1);
     CK(h, cudaGetLastError());
     CK(h, cudaStreamSynchronize(h->stream));
+    return MVTM_OK;
+}
+
+// The same finishing pass queued on the CALLER's stream (behind its all-reduce), no host synchronisation; table and totals
+// are one allocation, so one launch covers both.  Pair it with mvtm_view_wait_stream so the view's next pass waits for it.
+extern "C" int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size, void *stream, int32_t max_ctas)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added || world_size < 1) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_finish_async: bad argument");
+    ViewDev &v = h->v[m];
+    if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_finish_async: call mvtm_delta_begin first");
+    CK(h, cudaSetDevice(h->device));
+    const long long n = ((long long)v.V + 1) * h->Kp;
+    const int grid = max_ctas > 0 ? max_ctas : h->num_sms * 8;
+    k_finish_sum_exchange4<<<grid, 512, 0, (cudaStream_t)stream>>>(n / 4, (int4 *)v.nwk, (int4 *)v.snap_nwk, world_size - 1);
+    CK(h, cudaGetLastError());
     return MVTM_OK;
 }
 
@@ -923,6 +1047,7 @@ extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_import: call mvtm_delta_begin first");
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
     const long long n = (long long)v.V * h->Kp;
     k_add_snapshot<<<h->num_sms * 8, 256, 0, h->stream>>>(n, v.nwk, v.snap_nwk);
     k_add_snapshot<<<1, 256, 0, h->stream>>>((long long)h->Kp, v.nk, v.snap_nk);

@@ -797,6 +797,14 @@ __global__ void k_add_snapshot(long long n, int *a, int *snap)
 }
 // Sum-form exchange: every rank entered the sweep with the same global table G (= snap) and now holds G + delta_r; after
 // an in-place all-reduce a = N*G + sum_r delta_r, so the new global table is a - (N-1)*G.  One fused pass, no export pass.
+__global__ void k_finish_sum_exchange4(long long n4, int4 *a, int4 *snap, int world_minus_1)
+{   // 128-bit form for the overlapped exchange (row stride is a multiple of 32 ints, so the table is int4-divisible)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        int4 x = a[i]; const int4 g = snap[i];
+        x.x -= world_minus_1 * g.x; x.y -= world_minus_1 * g.y; x.z -= world_minus_1 * g.z; x.w -= world_minus_1 * g.w;
+        a[i] = x; snap[i] = x;
+    }
+}
 __global__ void k_finish_sum_exchange(long long n, int *a, int *snap, int world_minus_1)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -368,6 +368,7 @@ extern "C" int mvtm_optimize_hyper(mvtm_handle *h, int32_t iteration, uint32_t w
     if (!h) return MVTM_ERR_ARG;
     if (int rc = require_views(h, "mvtm_optimize_hyper")) return rc;
     CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
     OptRng g{ h->seed, (uint32_t)iteration, 0 };
     if (which & MVTM_OPT_P) if (int rc = optimize_p(h)) return rc;
     if (which & MVTM_OPT_DP) if (int rc = optimize_dp(h, g)) return rc;

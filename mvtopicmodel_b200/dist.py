@@ -57,6 +57,76 @@ class EngineAdapter:
         self.e.sum_exchange_finish(m, world)
 
 
+class OverlapAdapter:
+    """Engine side of OverlappedSweep: a side stream `comm` for the collective and its finishing pass, hand-over of each
+    view's tables between the engine's stream and `comm` through the mvtm_*_wait_* entry points (device-side waits only)."""
+
+    def __init__(self, engine, device, finish_ctas=0):
+        import contextlib
+        import torch
+        self.e, self.dev, self.torch, self.M = engine, device, torch, engine.M
+        self.comm = torch.cuda.Stream(device=device)
+        self.finish_ctas = finish_ctas
+        self._ctx = contextlib
+        self.bufs = []
+        for m in range(self.M):
+            (p1, n1), (p2, n2) = engine.sum_exchange_buffers(m)
+            assert p2 == p1 + 4 * n1, "n_k must follow n_wk in the same allocation"
+            self.bufs.append(torch.as_tensor(_DevBuf(p1, n1 + n2), device=f"cuda:{device}"))
+
+    def whole_buffer(self, m):
+        return self.bufs[m]
+
+    def sweep_view_async(self, it, m):
+        self.e.sweep_view_async(it, m, 1)
+
+    def comm_wait_view(self, m):
+        self.e.stream_wait_view(m, self.comm.cuda_stream)
+
+    def comm_context(self):
+        return self.torch.cuda.stream(self.comm)
+
+    def finish_async(self, m, world):
+        self.e.sum_exchange_finish_async(m, world, self.comm.cuda_stream, self.finish_ctas)
+
+    def view_wait_comm(self, m):
+        self.e.view_wait_stream(m, self.comm.cuda_stream)
+
+    def sweep_finish(self):
+        self.e.sweep_finish()
+
+    def drain(self):
+        self.comm.synchronize()
+
+
+class OverlappedSweep:
+    """One Gibbs sweep over all views with the count exchange of view m running WHILE the following views (and the next
+    sweep's earlier views) are sampled: view m's global counts are only needed when view m is sampled again (the reference's
+    barrier M:1231 asks no more).  Sum-form protocol, one all-reduce per view (table and totals are one buffer).  Needs
+    identical global counts on every rank at entry (i.e. after any completed exchange) and snapshots (delta_begin/reset)."""
+
+    def __init__(self, adapter, group=None):
+        import torch.distributed as dist
+        self.a, self.dist, self.group = adapter, dist, group
+        self.bytes_per_exchange = 0
+
+    def step(self, it):
+        a, world = self.a, self.dist.get_world_size(self.group)
+        total = 0
+        for m in range(a.M):
+            a.sweep_view_async(it, m)
+            a.comm_wait_view(m)
+            buf = a.whole_buffer(m)
+            with a.comm_context():
+                self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+            a.finish_async(m, world)
+            a.view_wait_comm(m)
+            total += buf.numel() * 4
+        a.sweep_finish()
+        self.bytes_per_exchange = total
+        return total
+
+
 class CountExchange:
     """Runs the delta protocol over a torch.distributed process group for any adapter with the four methods above."""
 

@@ -204,5 +204,21 @@ class Engine:
     def sum_exchange_finish(self, m, world):
         self._ck(self.L.mvtm_sum_exchange_finish(self.h, m, int(world)))
 
+    # overlapped exchange (mvtm.h "Overlapped exchange"): streams are raw cudaStream_t handles (ints)
+    def sweep_view_async(self, iteration, m, update_global=1):
+        self._ck(self.L.mvtm_sweep_view_async(self.h, int(iteration), int(m), int(update_global)))
+
+    def sweep_finish(self):
+        self._ck(self.L.mvtm_sweep_finish(self.h))
+
+    def stream_wait_view(self, m, stream):
+        self._ck(self.L.mvtm_stream_wait_view(self.h, int(m), C.c_void_p(int(stream))))
+
+    def view_wait_stream(self, m, stream):
+        self._ck(self.L.mvtm_view_wait_stream(self.h, int(m), C.c_void_p(int(stream))))
+
+    def sum_exchange_finish_async(self, m, world, stream, max_ctas=0):
+        self._ck(self.L.mvtm_sum_exchange_finish_async(self.h, int(m), int(world), C.c_void_p(int(stream)), int(max_ctas)))
+
     def delta_import(self, m):
         self._ck(self.L.mvtm_delta_import(self.h, m))

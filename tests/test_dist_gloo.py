@@ -55,6 +55,45 @@ class OracleAdapter:
         self.o.set_counts(m, a.numpy().reshape(int(self.o.V[m]), self.o.K), b.numpy())
 
 
+class OracleOverlapAdapter:
+    """The adapter surface OverlappedSweep drives (OverlapAdapter on a GPU), over the CPU oracle: the oracle sweeps all views
+    of a document together, so the whole sweep runs when view 0 is queued; streams collapse to program order."""
+
+    def __init__(self, base):
+        self.b, self.M, self.log = base, base.M, []
+        self.whole = [None] * base.M
+
+    def sweep_view_async(self, it, m):
+        self.log.append(("pass", m))
+        if m == 0:
+            from oracle import oracle as O
+            self.b.o.sweep(it, O.F_ENGINE_MIRROR)
+
+    def comm_wait_view(self, m):
+        self.log.append(("comm_waits_pass", m))
+
+    def whole_buffer(self, m):
+        a, b = self.b._cur(m)
+        self.whole[m] = torch.cat([a, b])
+        return self.whole[m]
+
+    def comm_context(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def finish_async(self, m, world):
+        n = self.whole[m].numel() - self.b.o.K
+        self.b.buf[m] = (self.whole[m][:n], self.whole[m][n:])
+        self.b.sum_finish(m, world)
+        self.log.append(("finish", m))
+
+    def view_wait_comm(self, m):
+        self.log.append(("pass_waits_comm", m))
+
+    def sweep_finish(self):
+        self.log.append(("barrier", -1))
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -101,6 +140,24 @@ def _worker(rank, world, port, q):
                     nwk += a; nk += b
                 a, b = o.get_counts(m)
                 assert np.array_equal(a, nwk) and np.array_equal(b, nk)
+        # (4) the overlapped form (one all-reduce per view over table + totals, hand-over calls in protocol order)
+        from mvtopicmodel_b200.dist import OverlappedSweep
+        oa = OracleOverlapAdapter(x.a)
+        ovl = OverlappedSweep(oa)
+        for it in range(5, 7):
+            assert ovl.step(it) == sum((Vs[m] * K + K) * 4 for m in range(2))
+            zs_all = [None] * world
+            dist.all_gather_object(zs_all, [o.get_assignments(m) for m in range(2)])
+            for m in range(2):
+                nwk = np.zeros((Vs[m], K), dtype=np.int64); nk = np.zeros(K, dtype=np.int64)
+                for r in range(world):
+                    vr = corpus.shard_views(full, r, world)
+                    (a, b), = recount([vr[m]], [zs_all[r][m]], K, [Vs[m]])
+                    nwk += a; nk += b
+                a, b = o.get_counts(m)
+                assert np.array_equal(a, nwk) and np.array_equal(b, nk)
+        per_view = [("pass", 0), ("comm_waits_pass", 0), ("finish", 0), ("pass_waits_comm", 0)]
+        assert oa.log[:4] == per_view and oa.log[8] == ("barrier", -1) and len(oa.log) == 18
         q.put((rank, "ok"))
     except Exception as e:   # pragma: no cover
         import traceback

@@ -648,3 +648,61 @@ def test_edge_cases_sizes(engine_lib, oracle_mod):
     o.set_assignments([e.get_assignments(m) for m in range(2)])
     ref, got = o.cond_probs(1, d, 0, p=p), e.cond_probs(1, d, 0, p_row=p[1])
     assert np.max(np.abs(got[:2048] - ref[:2048]) / ref[:2048]) <= REL_TOL_COND
+
+
+def test_async_view_passes_equal_blocking_sweep(engine_lib):
+    """mvtm_sweep_view_async x M + mvtm_sweep_finish is the same sweep as mvtm_sweep: bit-identical assignments when the
+    pass is sequential (one warp), same stats."""
+    from mvtopicmodel_b200 import Engine
+    K, Vs = 130, [300, 100, 50]
+    views = random_corpus(71, 300, K, Vs, [20, 4, 2])
+    FLAG_SINGLE_WARP = 2
+    a = Engine(K, Vs, views, seed=5, flags=FLAG_SINGLE_WARP)
+    b = Engine(K, Vs, views, seed=5, flags=FLAG_SINGLE_WARP)
+    a.init_assignments(); b.init_assignments()
+    for it in range(1, 4):
+        a.sweep(it)
+        for m in range(3):
+            b.sweep_view_async(it, m)
+        b.sweep_finish()
+        sa, sb = a.stats(), b.stats()
+        assert sa["tokens"] == sb["tokens"] and sa["changed"] == sb["changed"] and sb["kernel_launches"] == 3
+        for m in range(3):
+            assert np.array_equal(a.get_assignments(m), b.get_assignments(m))
+    assert b.check_invariants() == 0
+    with pytest.raises(Exception):          # open passes must be closed before a blocking sweep
+        b.sweep_view_async(4, 0)
+        b.sweep(4)
+    b.sweep_finish()
+
+
+def test_overlapped_exchange_handover_single_rank(engine_lib):
+    """The hand-over protocol of the overlapped exchange with world size 1 (the all-reduce is the identity): a side stream
+    takes each view's tables after its pass, runs the finishing pass, hands them back; counts stay exact, the snapshot
+    follows the table, and readers order themselves behind the side stream."""
+    import torch
+    from mvtopicmodel_b200 import Engine
+    K, Vs = 500, [800, 120]
+    views = random_corpus(72, 1500, K, Vs, [40, 5])
+    e = Engine(K, Vs, views, seed=8, max_ctas=100)
+    e.init_assignments()
+    e.delta_begin()
+    comm = torch.cuda.Stream()
+    for it in range(1, 6):
+        for m in range(2):
+            e.sweep_view_async(it, m)
+            e.stream_wait_view(m, comm.cuda_stream)
+            with torch.cuda.stream(comm):
+                torch.cuda._sleep(2_000_000)          # a slow "collective": the next pass of view m must wait for it
+            e.sum_exchange_finish_async(m, 1, comm.cuda_stream, 8)
+            e.view_wait_stream(m, comm.cuda_stream)
+        e.sweep_finish()
+    assert e.check_invariants() == 0
+    zs = [e.get_assignments(m) for m in range(2)]
+    for m, (nwk, nk) in enumerate(recount(views, zs, K, Vs)):
+        a, b = e.get_counts(m)
+        assert np.array_equal(a, nwk) and np.array_equal(b, nk)
+    # snapshot == table after the finishing pass: a delta export must be all zeros
+    (p1, n1), (p2, n2) = e.delta_export(0)
+    e.delta_import(0)
+    assert e.check_invariants() == 0
