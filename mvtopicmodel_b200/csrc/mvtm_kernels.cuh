@@ -684,7 +684,7 @@ __global__ void k_init_from_phi(int m, int K, int Kp, int V, long long n_docs, c
 }
 
 // buildInitialTypeTopicCounts M:600-652: n_wk / n_k from (word, z); n_k through a shared-memory histogram
-__global__ void k_build_counts(long long n_tok, const int *word, const int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad)
+__global__ void k_build_counts(long long n_tok, const int *word, int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad)
 {
     extern __shared__ int hk[];
     for (int t = threadIdx.x; t < K; t += blockDim.x) hk[t] = 0;
@@ -692,7 +692,7 @@ __global__ void k_build_counts(long long n_tok, const int *word, const int *z, i
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += (long long)gridDim.x * blockDim.x) {
         int t = z[i], w = word[i];
         if (t < 0) continue;                                      // UNASSIGNED_TOPIC, M:634
-        if (t >= K) { atomicAdd(bad, 1); continue; }
+        if (t >= K) { atomicAdd(bad, 1); z[i] = -1; continue; }   // reported by the caller; never left where a sweep could index with it
         atomicAdd(hk + t, 1);
         if ((unsigned)w < (unsigned)V) atomicAdd(nwk + (size_t)w * Kp + t, 1);
     }

@@ -706,3 +706,45 @@ def test_overlapped_exchange_handover_single_rank(engine_lib):
     (p1, n1), (p2, n2) = e.delta_export(0)
     e.delta_import(0)
     assert e.check_invariants() == 0
+
+
+def test_sweep_host_pipeline_equals_resident_sweep(engine_lib):
+    """mvtm_sweep_host (chunked upload / count rebuild / sample / download pipeline) against mvtm_sweep on resident state.
+    Document order + one warp make a pass sequential, and the host form walks the same documents in the same order (its
+    chunks are contiguous document ranges), so the assignments must agree bit for bit; bad topic ids are reported."""
+    import torch
+    from mvtopicmodel_b200 import Engine, MvtmError
+    K, Vs = 130, [300, 100, 50]
+    views = random_corpus(91, 400, K, Vs, [20, 4, 2])
+    FLAGS = 1 | 2                                       # MVTM_FLAG_DOC_ORDER | MVTM_FLAG_SINGLE_WARP
+    a = Engine(K, Vs, views, seed=12, flags=FLAGS)
+    b = Engine(K, Vs, views, seed=12, flags=FLAGS)
+    a.init_assignments(); b.init_assignments()
+    zh = [torch.from_numpy(b.get_assignments(m).copy()).pin_memory() for m in range(3)]
+    zn = [z.numpy() for z in zh]
+    for it in range(1, 4):
+        a.sweep(it)
+        b.sweep_host(it, zn)
+        for m in range(3):
+            assert np.array_equal(a.get_assignments(m), zn[m])
+        sa, sb = a.stats(), b.stats()
+        assert sa["tokens"] == sb["tokens"] and sa["changed"] == sb["changed"]
+    assert b.check_invariants() == 0
+    for m in range(3):
+        na, ka = a.get_counts(m); nb, kb = b.get_counts(m)
+        assert np.array_equal(na, nb) and np.array_equal(ka, kb)
+    zn[1][3] = K + 5
+    with pytest.raises(MvtmError):
+        b.sweep_host(4, zn)
+    zn[1][3] = 0
+    b.sweep_host(5, zn)                                  # the handle stays usable
+    assert b.check_invariants() == 0
+    # full parallelism, many chunks with work: invariants and host/device agreement
+    K2, V2 = 500, [800]
+    views2 = random_corpus(92, 5000, K2, V2, [40])
+    e = Engine(K2, V2, views2, seed=4)
+    e.init_assignments()
+    z2 = [e.get_assignments(0).copy()]
+    for it in range(1, 4):
+        e.sweep_host(it, z2)
+        assert np.array_equal(z2[0], e.get_assignments(0)) and e.check_invariants() == 0
