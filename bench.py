@@ -291,7 +291,7 @@ def main():
             e2e_ms = float(t[0])
         e2e = {"value": ntok_global * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * ntok_local,
                "d2h_bytes_per_step": 4 * ntok_local, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-               "call": "mvtm_sweep_host (pinned host z in/out, count rebuild + sweep inside)" if not xch else
+               "call": "mvtm_sweep_host (pinned host z in/out: chunked upload + count rebuild, sweep, new z stored to the pinned arrays by the kernel)" if not xch else
                        "mvtm_set_assignments + delta all-reduce + mvtm_sweep + delta all-reduce + mvtm_get_assignments"}
 
     if rank != 0:

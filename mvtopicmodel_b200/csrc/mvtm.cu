@@ -30,9 +30,7 @@ struct ViewDev {
     unsigned char *present = nullptr;
     int *nwk = nullptr, *nk = nullptr, *nk_snap = nullptr;
     int *order = nullptr;
-    int *order_chunked = nullptr;                   // mvtm_sweep_host: per-chunk longest-first lists, concatenated
-    std::vector<int> chunk_item_off;                // HOST_CHUNKS + 1 offsets into order_chunked
-    std::vector<long long> chunk_tok_off;           // HOST_CHUNKS + 1 token offsets (chunks are contiguous document ranges)
+    std::vector<long long> chunk_tok_off;           // mvtm_sweep_host: HOST_CHUNKS + 1 token offsets of contiguous document ranges
     float *ga_tree = nullptr, *ga_full = nullptr, *ga_one = nullptr;   // ga_one: all ones, the inferencer's bare trees (Q13)
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
@@ -64,7 +62,7 @@ struct mvtm_handle {
     bool hyper_dirty = true;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;             // mvtm_sweep_host: H2D / D2H of z chunks beside the kernels
-    std::vector<cudaEvent_t> host_ev;               // per (view, chunk): upload done; sampled
+    std::vector<cudaEvent_t> host_ev;               // per (view, chunk): upload done
     cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
     cudaEvent_t ev_done[MVTM_MAX_VIEWS], ev_ready[MVTM_MAX_VIEWS];   // hand-over points with a caller-owned stream (async exchange)
     bool ready_pending[MVTM_MAX_VIEWS] = { false }, pass_queued[MVTM_MAX_VIEWS] = { false };
@@ -179,7 +177,7 @@ static void free_view(ViewDev &v)
 {
     // nk / snap_nk are row V of the nwk / snap_nwk allocations (one all-reduce covers table and totals)
     cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk);
-    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.order_chunked); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk);
     v = ViewDev();
 }
 
@@ -248,28 +246,12 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     if (!(h->flags & MVTM_FLAG_DOC_ORDER))
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return doc_off[a + 1] - doc_off[a] > doc_off[b + 1] - doc_off[b]; });
     v.n_items = (int)order.size();
-    // the same list cut into HOST_CHUNKS contiguous document ranges of about equal token count, each longest-first:
-    // mvtm_sweep_host samples range after range so that a range's assignments travel back while the next is sampled
-    std::vector<int> order_ch;
-    order_ch.reserve(order.size());
-    v.chunk_item_off.assign(1, 0); v.chunk_tok_off.assign(1, 0);
-    {
-        long long dlo = 0;
-        for (int cidx = 1; cidx <= HOST_CHUNKS; cidx++) {
-            long long dhi = D;
-            if (cidx < HOST_CHUNKS) {
-                const long long want = N * cidx / HOST_CHUNKS;
-                dhi = std::lower_bound(doc_off + dlo, doc_off + D, want) - doc_off;
-                dhi = std::min(std::max(dhi, dlo), D);
-            }
-            const size_t first = order_ch.size();
-            for (long long d = dlo; d < dhi; d++) if (doc_off[d + 1] - doc_off[d] > 0) order_ch.push_back((int)d);
-            if (!(h->flags & MVTM_FLAG_DOC_ORDER))
-                std::stable_sort(order_ch.begin() + first, order_ch.end(), [&](int a, int b) { return doc_off[a + 1] - doc_off[a] > doc_off[b + 1] - doc_off[b]; });
-            v.chunk_item_off.push_back((int)order_ch.size());
-            v.chunk_tok_off.push_back(doc_off[dhi]);
-            dlo = dhi;
-        }
+    // HOST_CHUNKS contiguous document ranges of about equal token count: the upload units of mvtm_sweep_host
+    v.chunk_tok_off.assign(1, 0);
+    for (int cidx = 1; cidx <= HOST_CHUNKS; cidx++) {
+        long long dhi = D;
+        if (cidx < HOST_CHUNKS) dhi = std::lower_bound(doc_off, doc_off + D, N * cidx / HOST_CHUNKS) - doc_off;
+        v.chunk_tok_off.push_back(std::max<long long>(v.chunk_tok_off.back(), (long long)doc_off[std::min(dhi, D)]));
     }
     const size_t Kp = (size_t)h->Kp;
     CK(h, cudaMalloc(&v.doc_off, (size_t)(D + 1) * 8));
@@ -277,7 +259,6 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMalloc(&v.z, (size_t)std::max<long long>(N, 1) * 4));
     CK(h, cudaMalloc(&v.present, pres.size()));
     CK(h, cudaMalloc(&v.order, (size_t)std::max<int>(v.n_items, 1) * 4));
-    CK(h, cudaMalloc(&v.order_chunked, (size_t)std::max<int>(v.n_items, 1) * 4));
     CK(h, cudaMalloc(&v.nwk, ((size_t)v.V + 1) * Kp * 4));
     v.nk = v.nwk + (size_t)v.V * Kp;
     CK(h, cudaMalloc(&v.nk_snap, Kp * 4));
@@ -290,7 +271,6 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMemcpy(v.present, pres.data(), pres.size(), cudaMemcpyHostToDevice));
     v.h_present = pres;
     if (v.n_items) CK(h, cudaMemcpy(v.order, order.data(), (size_t)v.n_items * 4, cudaMemcpyHostToDevice));
-    if (v.n_items) CK(h, cudaMemcpy(v.order_chunked, order_ch.data(), (size_t)v.n_items * 4, cudaMemcpyHostToDevice));
     CK(h, cudaMemset(v.z, 0xff, (size_t)std::max<long long>(N, 1) * 4));       // UNASSIGNED_TOPIC
     CK(h, cudaMemset(v.nwk, 0, (size_t)v.V * Kp * 4));
     CK(h, cudaMemset(v.nk, 0, Kp * 4));
@@ -763,12 +743,22 @@ extern "C" int mvtm_view_wait_stream(mvtm_handle *h, int32_t m, void *stream)
     return MVTM_OK;
 }
 
+// device-visible alias of a caller buffer when it is pinned + mapped (cudaHostAlloc / cudaHostRegister under UVA), else NULL
+static int *mapped_alias(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return (int *)a.devicePointer;
+}
+
 extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout)
 {
-    // Pipeline over HOST_CHUNKS contiguous document ranges per view (copies on copy_stream, kernels on stream):
-    //   upload range c  ||  add range c-1 to the counts          (the sampler needs ALL counts, so it starts after the last range)
-    //   sample range c  ||  download range c-1                    (a range's assignments are final once its launch ends)
-    // Views are sampled in view order and n_k is frozen per view pass exactly as in mvtm_sweep.
+    // Upload: HOST_CHUNKS contiguous document ranges per view on copy_stream, each range added to the counts on `stream`
+    // while the next one travels (the sampler needs ALL counts, so it starts after the last range).
+    // Download: when the caller's arrays are pinned and mapped, the sweep kernel itself stores every token block's new
+    // assignments to them next to its store to device memory (posted PCIe writes under the sampling, nothing left to copy
+    // afterwards); pageable arrays get a plain copy after the pass.  One launch per view, exactly as mvtm_sweep.
     if (!h) return MVTM_ERR_ARG;
     if (!z_inout) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: NULL z_inout");
     if (h->sweep_open) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep_host: passes queued by mvtm_sweep_view_async are still open");
@@ -776,13 +766,16 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
     if (!h->copy_stream) CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    const size_t n_ev = (size_t)2 * MVTM_MAX_VIEWS * HOST_CHUNKS;
+    const size_t n_ev = (size_t)MVTM_MAX_VIEWS * HOST_CHUNKS;
     while (h->host_ev.size() < n_ev) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->host_ev.push_back(e); }
     auto ev_up = [&](int m, int cidx) { return h->host_ev[(size_t)(m * HOST_CHUNKS + cidx)]; };
-    auto ev_done = [&](int m, int cidx) { return h->host_ev[(size_t)((MVTM_MAX_VIEWS + m) * HOST_CHUNKS + cidx)]; };
     const size_t Kp = (size_t)h->Kp;
-    for (int m = 0; m < h->M; m++)
+    int *alias[MVTM_MAX_VIEWS];
+    const bool zero_copy = !(getenv("MVTM_HOST_ZEROCOPY") && atoi(getenv("MVTM_HOST_ZEROCOPY")) == 0);
+    for (int m = 0; m < h->M; m++) {
         if (h->v[m].n_tok > 0 && !z_inout[m]) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: NULL z for view %d", m);
+        alias[m] = (zero_copy && h->v[m].n_tok > 0) ? mapped_alias(z_inout[m]) : nullptr;
+    }
     if (int rc = upload_hyper(h)) return rc;
     // the copy stream must not overtake earlier work on the handle's stream that still reads z
     CK(h, cudaEventRecord(h->ev_done[0], h->stream));
@@ -811,26 +804,19 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
         if (int rc = choose_launch(h, m, ring_for_view(h, m), lc)) return rc;
         if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
         CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
-        if (v.n_items > 0) CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
-        for (int cidx = 0; cidx < HOST_CHUNKS; cidx++) {
-            const int i0 = v.chunk_item_off[cidx], ni = v.chunk_item_off[cidx + 1] - i0;
-            const long long t0 = v.chunk_tok_off[cidx], n = v.chunk_tok_off[cidx + 1] - t0;
-            if (ni > 0) {
-                CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-                SweepParams P;
-                fill_params(h, m, iteration, 1, P);
-                P.order = v.order_chunked + i0; P.n_items = ni;
-                P.R = lc.R; P.oc_smem = lc.oc_smem;
-                CK(h, launch_sweep(h, P, lc));
-                launches++;
-            }
-            if (n > 0) {
-                CK(h, cudaEventRecord(ev_done(m, cidx), h->stream));
-                CK(h, cudaStreamWaitEvent(h->copy_stream, ev_done(m, cidx), 0));
-                CK(h, cudaMemcpyAsync(z_inout[m] + t0, v.z + t0, (size_t)n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
-            }
+        if (v.n_items > 0) {
+            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+            SweepParams P;
+            fill_params(h, m, iteration, 1, P);
+            P.R = lc.R; P.oc_smem = lc.oc_smem;
+            P.z_host = alias[m];
+            CK(h, launch_sweep(h, P, lc));
+            launches++;
         }
         CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
+        if (v.n_tok > 0 && !alias[m])
+            CK(h, cudaMemcpyAsync(z_inout[m], v.z, (size_t)v.n_tok * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(h, cudaEventRecord(h->ev[1], h->stream));
     unsigned long long st[4];
@@ -838,8 +824,9 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
     CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    CK(h, cudaStreamSynchronize(h->copy_stream));
-    if (bad) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: the assignments hold %d topic ids >= K", bad);
+    if (bad) {      // those tokens were treated as UNASSIGNED_TOPIC on the device; the caller's arrays may hold their new topics
+        FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: the assignments hold %d topic ids >= K", bad);
+    }
     h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
     float ms = 0.f;
     CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
@@ -847,6 +834,7 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
     for (int m = 0; m < h->M; m++) {
         CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m]));
         h->stats.ms_view[m] = ms;
+        if (h->v[m].n_items > 0) ring_record(h, m, ms);
     }
     h->stats.kernel_launches = launches;
     return activate_sampled_topics(h);

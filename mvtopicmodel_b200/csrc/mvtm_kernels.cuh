@@ -52,6 +52,8 @@ struct SweepParams {
     unsigned long long *stats;        // [0] tokens, [1] changed, [2] new-topic draws
     float *oc_scratch;                // (multi-view) per resident document slot: Kp floats, see DocCtx::oc
     int oc_smem;                      // (multi-view) 1: keep DocCtx::oc in shared memory instead (views of short documents)
+    int *z_host;                      // mvtm_sweep_host: device alias of the caller's pinned array of view m (NULL: none); every
+                                      //   token block's new assignments are stored there too, so no copy follows the pass
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -539,7 +541,10 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                 __syncwarp();
                 if (act) slot = (slot + 1 == R) ? 0 : slot + 1;
             }
-            if (gl < nblk) zmv[b + base + gl] = znew;
+            if (gl < nblk) {
+                zmv[b + base + gl] = znew;
+                if (P.z_host) P.z_host[b + base + gl] = znew;       // posted write over PCIe, one 4*G-byte run per block
+            }
             wcur = wnext;
             wahead = (base + G + R + gl < len) ? __ldg(P.word + b + base + G + R + gl) : 0;
             zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;

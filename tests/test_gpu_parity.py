@@ -711,14 +711,15 @@ def test_overlapped_exchange_handover_single_rank(engine_lib):
 def test_sweep_host_pipeline_equals_resident_sweep(engine_lib):
     """mvtm_sweep_host (chunked upload / count rebuild / sample / download pipeline) against mvtm_sweep on resident state.
     Document order + one warp make a pass sequential, and the host form walks the same documents in the same order (its
-    chunks are contiguous document ranges), so the assignments must agree bit for bit; bad topic ids are reported."""
+    chunks are contiguous document ranges), so the assignments must agree bit for bit (K > 1024: one document per warp --
+    with several documents per warp the chunk boundaries would regroup them); bad topic ids are reported."""
     import torch
     from mvtopicmodel_b200 import Engine, MvtmError
-    K, Vs = 130, [300, 100, 50]
+    K, Vs = 1100, [300, 100, 50]
     views = random_corpus(91, 400, K, Vs, [20, 4, 2])
     FLAGS = 1 | 2                                       # MVTM_FLAG_DOC_ORDER | MVTM_FLAG_SINGLE_WARP
-    a = Engine(K, Vs, views, seed=12, flags=FLAGS)
-    b = Engine(K, Vs, views, seed=12, flags=FLAGS)
+    a = Engine(K, Vs, views, seed=12, flags=FLAGS, ring_depth=1)     # same prefetch distance in both (no autotune)
+    b = Engine(K, Vs, views, seed=12, flags=FLAGS, ring_depth=1)
     a.init_assignments(); b.init_assignments()
     zh = [torch.from_numpy(b.get_assignments(m).copy()).pin_memory() for m in range(3)]
     zn = [z.numpy() for z in zh]
