@@ -104,6 +104,18 @@ __device__ __forceinline__ float2 lds_f2(uint32_t a)
 { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void reds_add(uint32_t a, int v)
 { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// per-document state through ONE 32-bit base held in a register (DocCtx::sa) + compile-time offsets: the hot loop otherwise
+// re-derives every address from %tid and the ring depth on each token (ptxas rematerialises them: ~45 instructions per step)
+__device__ __forceinline__ int4 lds_i4(uint32_t a)
+{ int4 v; asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{ float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned lds_u16(uint32_t a)
+{ unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned v)
+{ asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v)
+{ asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 #define FULL 0xffffffffu
 __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
@@ -114,6 +126,7 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 // lane gl = c % G and is that lane's j = c / G -th chunk (JG = KS / (4 G) chunks per lane).
 // ------------------------------------------------------------------------------------------------
 struct DocCtx {
+    uint32_t sa;           // .shared address of the document's area: q at +0, n_d at +4*KS (see carve_doc)
     float *q;              // KS
     unsigned short *nd;    // KS
     float *oc;             // Kp, GLOBAL scratch (MULTI) sum_i c_i * n_d[i][t]; only entries whose `om` bit is set are
@@ -150,8 +163,9 @@ template <int KS, int G, bool MULTI>
 __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl, int gl, float (&bsq)[KS / (4 * G)])
 {
     constexpr int JG = KS / (4 * G);
-    const unsigned ndv_i = (unsigned)((int)c.nd[t] + dl);
-    c.nd[t] = (unsigned short)ndv_i;
+    const uint32_t nd_a = c.sa + (uint32_t)KS * 4u + 2u * (uint32_t)t;
+    const unsigned ndv_i = (unsigned)((int)lds_u16(nd_a) + dl);
+    sts_u16(nd_a, ndv_i);
     const float ndv = (float)ndv_i;
     bool inS = false; float ocv = 0.f, pri = 0.f;
     if (MULTI) {
@@ -161,10 +175,10 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
         pri = prior_other<MULTI>(P, c, t);
         if (oth) ocv = c.oc[t];
     }
-    c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
+    sts_f32(c.sa + 4u * (uint32_t)t, q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t)));
     constexpr int LG = ilog2(G);
     const int j = t >> (2 + LG);
-    const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];   // own store is visible in program order
+    const float4 qq = lds_f4(c.sa + 16u * (uint32_t)(gl + G * j));      // own store is visible in program order
     const float v = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
 #pragma unroll
     for (int jj = 0; jj < JG; jj++) if (jj == j) bsq[jj] = v;
@@ -311,13 +325,13 @@ __device__ __forceinline__ float topic_weight(int n, float q, float beta) { retu
 // per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, each topic weighted (n + beta) * q,
 // evaluated as beta*sum(q) (registers, bsq) + sum n*q.  Returns the lane total (= cum[JG-1]).
 template <int JG, int G>
-__device__ __forceinline__ float lane_weights(const int4 *row4, const float4 *q4, int gl, const float (&bsq)[JG], float (&cum)[JG])
-{
+__device__ __forceinline__ float lane_weights(uint32_t row_gl_sa, uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG])
+{   // row_gl_sa / q_gl_sa: .shared address of the lane's first chunk (base + 16*gl); chunk j sits 16*G*j bytes further
     float tot = 0.f;
 #pragma unroll
     for (int j = 0; j < JG; j++) {
-        const int4 r = row4[gl + G * j];
-        const float4 qq = q4[gl + G * j];
+        const int4 r = lds_i4(row_gl_sa + 16u * G * j);
+        const float4 qq = lds_f4(q_gl_sa + 16u * G * j);
         float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
         a = fmaf(__int2float_rn(r.y), qq.y, a);
         a = fmaf(__int2float_rn(r.z), qq.z, a);
@@ -335,10 +349,10 @@ __device__ __forceinline__ float next_below(float x) { return __int_as_float(__f
 // exceeds target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket (W:522).  Every lane of the warp
 // must call it (full-mask shuffles); groups whose document is exhausted compute on stale data and ignore the result.
 template <int JG, int G>
-__device__ __forceinline__ int group_select(const int4 *row4, const float4 *q4, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
+__device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
 {
     float cum[JG];
-    const float lane_total = lane_weights<JG, G>(row4, q4, gl, bsq, cum);
+    const float lane_total = lane_weights<JG, G>(row_gl_sa, q_gl_sa, bsq, cum);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
@@ -357,8 +371,8 @@ __device__ __forceinline__ int group_select(const int4 *row4, const float4 *q4, 
 #pragma unroll
     for (int j = 0; j < JG - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
     const int cidx = gl + G * jsel;
-    const int4 rr = row4[cidx];
-    const float4 qq = q4[cidx];
+    const int4 rr = lds_i4(row_gl_sa + 16u * G * (uint32_t)jsel);
+    const float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
     const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
     const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
     const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
@@ -371,27 +385,30 @@ __device__ __forceinline__ int group_select(const int4 *row4, const float4 *q4, 
 
 // shared-memory carve-up -------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi) { return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4; }
+// per-document area: [q KS*4][n_d KS*2][om 256 + cpar 64 (multi)][mbarriers 128][ring R*KS*4][oc KS*4 (multi, optional)]
+// -- everything the hot loop addresses sits at a compile-time offset from the area's base, the ring (whose size depends on
+// the run-time depth R) comes last
+__host__ __device__ constexpr uint32_t doc_off_mbar(int KS, bool multi) { return (uint32_t)KS * 6u + (multi ? 320u : 0u); }
+__host__ __device__ constexpr uint32_t doc_off_ring(int KS, bool multi) { return doc_off_mbar(KS, multi) + 128u; }
 __host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi, bool oc_smem = false)
 {
-    size_t b = (size_t)KS * 4 + (size_t)KS * 2;                   // q, nd
-    if (multi) b += 256 + 64;                                     // om (<= 64 words), cpar
+    size_t b = doc_off_ring(KS, multi) + (size_t)R * KS * 4;
     if (multi && oc_smem) b += (size_t)KS * 4;                    // oc in shared memory
-    b += (size_t)R * KS * 4 + 128;                                // ring + mbarriers
     return (b + 127) & ~(size_t)127;
 }
 
 __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bool multi, DocCtx &c, int *&ring, unsigned long long *&mbar,
                                           bool oc_smem = false)
 {
-    unsigned char *p = base;
-    ring = reinterpret_cast<int *>(p); p += (size_t)R * KS * 4;
-    c.q = reinterpret_cast<float *>(p); p += (size_t)KS * 4;
-    c.oc = nullptr;
-    if (multi && oc_smem) { c.oc = reinterpret_cast<float *>(p); p += (size_t)KS * 4; }
-    c.nd = reinterpret_cast<unsigned short *>(p); p += (size_t)KS * 2;
-    if (multi) { c.om = reinterpret_cast<unsigned *>(p); p += 256; c.cpar = reinterpret_cast<float *>(p); p += 64; }
+    c.sa = smem_u32(base);
+    c.q = reinterpret_cast<float *>(base);
+    c.nd = reinterpret_cast<unsigned short *>(base + (size_t)KS * 4);
+    if (multi) { c.om = reinterpret_cast<unsigned *>(base + (size_t)KS * 6); c.cpar = reinterpret_cast<float *>(base + (size_t)KS * 6 + 256); }
     else { c.om = nullptr; c.cpar = nullptr; }
-    mbar = reinterpret_cast<unsigned long long *>(p);
+    mbar = reinterpret_cast<unsigned long long *>(base + doc_off_mbar(KS, multi));
+    ring = reinterpret_cast<int *>(base + doc_off_ring(KS, multi));
+    c.oc = nullptr;
+    if (multi && oc_smem) c.oc = reinterpret_cast<float *>(base + doc_off_ring(KS, multi) + (size_t)R * KS * 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -438,7 +455,9 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
     __syncthreads();
 
     const uint32_t row_bytes = (uint32_t)P.Kp * 4u;
-    const uint32_t ring_u32 = smem_u32(ring), mbar_u32 = smem_u32(mbar);
+    asm volatile("" : "+r"(c.sa));                                // opaque: ONE register carries the document area's base
+    const uint32_t mbar_u32 = c.sa + doc_off_mbar(KS, MULTI), ring_u32 = c.sa + doc_off_ring(KS, MULTI);
+    const uint32_t q_gl_sa = c.sa + 16u * (uint32_t)gl;
     unsigned phasebits = 0u;
     unsigned long long n_tok = 0, n_changed = 0, n_new = 0;
     const int m = P.m;
@@ -514,8 +533,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                     phasebits ^= 1u << slot;
                 }
                 __syncwarp();
-                int nt = group_select<JG, G>(reinterpret_cast<const int4 *>(ring + (size_t)slot * KS), reinterpret_cast<const float4 *>(c.q),
-                                             lane, gl, P.beta, bsq, u, c.C);
+                int nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
                 if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
                 else nt = ot;
                 __syncwarp();
@@ -613,7 +631,7 @@ __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d
     for (int t = gl; t < KS; t += G) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
     __syncwarp();
     float cum[JG];
-    float lt = lane_weights<JG, G>(reinterpret_cast<const int4 *>(ring), reinterpret_cast<const float4 *>(c.q), gl, bsq, cum);
+    float lt = lane_weights<JG, G>(smem_u32(ring) + 16u * (uint32_t)gl, c.sa + 16u * (uint32_t)gl, bsq, cum);
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) lt += __shfl_xor_sync(FULL, lt, off, G);
     const float total = lt + c.C;

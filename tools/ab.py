@@ -1,0 +1,31 @@
+"""A/B two builds of libmvtm.so on the same box: python tools/ab.py libA.so libB.so [workload[:docs] ...]
+Each (library, workload) runs in its own process; prints the mean device ms per view pass of sweeps 5..12."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import os, sys
+sys.path.insert(0, %r)
+import mvtopicmodel_b200._lib as L
+L.SO_PATH = sys.argv[1]
+from mvtopicmodel_b200 import Engine, corpus
+wl, docs = sys.argv[2], (int(sys.argv[3]) if sys.argv[3] != "0" else None)
+K, Vs, views = corpus.generate(wl, docs=docs)
+e = Engine(K, Vs, views, seed=1); e.init_assignments()
+acc = [0.0] * len(views); n = 0
+for it in range(1, 13):
+    e.sweep(it)
+    if it >= 5:
+        st = e.stats(); n += 1
+        for m in range(len(views)): acc[m] += st["ms_view"][m]
+assert e.check_invariants() == 0
+tok = sum(e.ntok)
+print("%%s %%s ms/view %%s  total %%.3f ms  %%.3f Gtok/s" %% (os.path.basename(sys.argv[1]), wl, [round(a / n, 3) for a in acc], sum(acc) / n, tok / (sum(acc) / n) / 1e6))
+''' % ROOT
+libs = [a for a in sys.argv[1:] if a.endswith(".so")]
+wls = [a for a in sys.argv[1:] if not a.endswith(".so")] or ["lda_100k"]
+for wl in wls:
+    name, _, docs = wl.partition(":")
+    for rep in range(2):
+        for lib in libs:
+            out = subprocess.run([sys.executable, "-c", CHILD, os.path.abspath(lib), name, docs or "0"], capture_output=True, text=True)
+            print(out.stdout.strip() or out.stderr[-400:], flush=True)
