@@ -3,12 +3,14 @@
 `FastQMVWVParallelTopicModel` keeps the method names, argument meaning and the iteration schedule of
 org.madgik.MVTopicModel.FastQMVWVParallelTopicModel (M) for the calls on the hot path -- constructor M:183-247,
 setters M:273-335, addInstances M:396-533, estimate M:1033-1356, modelLogLikelihood M:3322-3452 -- and routes
-them to the C ABI (include/mvtm.h).  Everything outside the path (hyper-parameter optimisers, DB output,
-diagnostics, embeddings) is out of scope and raises NotImplementedError instead of
-silently doing something else.
+them to the C ABI (include/mvtm.h).  The readers that turn the sampled state into the reference's text files
+(printState M:3269-3320, printTypeTopicCounts M:2076-2102, printTopicWordWeights M:2104-2129, top words M:1792-1890)
+are host code in state_io.py.  Everything outside the path (DB output, diagnostics, embeddings) is out of scope
+ and raises NotImplementedError instead of silently doing something else.
 """
 import numpy as np
 
+from . import state_io
 from .engine import Engine
 
 
@@ -65,6 +67,9 @@ class FastQMVWVParallelTopicModel:
         self.iterationsSoFar = 0
         self.gammaRoot, self.gammaView, self.pMean, self.inActiveTopicIndex = 10.0, np.zeros(M), np.eye(M), []
         self.sweep_ms = []
+        self.saveStateInterval, self.stateFilename = 0, None
+        self.alphabet = [None] * M      # per view: object with lookup_object(i) (ingest.Alphabet) or None -> the id as text
+        self.views, self.present = None, None
 
     # ---- setters, M:273-335 ------------------------------------------------------------------------
     def setNumIterations(self, n): self.numIterations = int(n)
@@ -74,7 +79,7 @@ class FastQMVWVParallelTopicModel:
     def setOptimizeInterval(self, interval): self.optimizeInterval = int(interval)
     def setNumThreads(self, threads): self.numThreads = int(threads)   # kept for API parity; the GPU bounds asynchrony itself
     def setSymmetricAlpha(self, b): pass
-    def setSaveState(self, interval, filename): raise NotImplementedError("state files are out of scope (SURVEY 8f rank 3)")
+    def setSaveState(self, interval, filename): self.saveStateInterval, self.stateFilename = int(interval), filename    # M:320-323
     def setSaveSerializedModel(self, interval, filename): raise NotImplementedError("Java serialisation is out of scope")
 
     # ---- addInstances, M:396-533 ---------------------------------------------------------------------
@@ -108,6 +113,9 @@ class FastQMVWVParallelTopicModel:
             present.append(np.array([r[m] is not None for r in docs], dtype=np.uint8))
             self.totalTokens[m] = int(off[-1])
         seed = self.randomSeed if self.randomSeed != -1 else int(np.random.SeedSequence().entropy % (1 << 63))
+        for m in range(M):
+            self.alphabet[m] = getattr(training[m], "alphabet", None)
+        self.views, self.present = views, present
         self.engine = Engine(K, [max(1, v) for v in self.numTypes], views, seed=seed, device=self.device, present=present)
         self._push_hyper()
         self.engine.init_assignments()          # M:465-515 + buildInitialTypeTopicCounts M:600-652
@@ -123,6 +131,8 @@ class FastQMVWVParallelTopicModel:
         self.p_a[:] = 0.2; self.p_b[:] = 1.0                                                        # M:1055-1058
         self._push_hyper()
         for iteration in range(1, self.numIterations + 1):                                          # M:1146
+            if self.saveStateInterval != 0 and iteration % self.saveStateInterval == 0:             # M:1154-1155 (before the sweep)
+                self.printState(f"{self.stateFilename}.{iteration}")
             if iteration < self.burninPeriod and self.numModalities > 1:
                 self.p_a[:] = min(iteration / 100.0 + 0.3, 1.1)                                     # M:1166-1169
                 self._push_hyper()
@@ -179,10 +189,56 @@ class FastQMVWVParallelTopicModel:
         """M:3457-3463"""
         return FastQMVWVTopicInferencer(self)
 
-    def getTopWords(self, m, numWords):
-        """Indices of the top words per topic by count (the ranking of M:1792-1890 without the alphabet lookup)."""
-        nwk = self.engine.get_counts(m)[0]
-        return np.argsort(-nwk, axis=0, kind="stable")[:numWords].T
+    # ---- text readers (state_io.py) -------------------------------------------------------------------
+    def _lookup(self, m):
+        a = self.alphabet[m]
+        return (lambda i: str(a.lookup_object(int(i)))) if a is not None else (lambda i: str(int(i)))
+
+    def _lookups(self):
+        return [self._lookup(m) for m in range(self.numModalities)]
+
+    def getSortedWords(self, modality):
+        """M:1792-1809: per topic the (type, count) pairs with positive count in MALLET IDSorter order."""
+        nwk = self.engine.get_counts(modality)[0]
+        return [state_io.sorted_words(nwk, t) for t in range(self.numTopics)]
+
+    def getTopWords(self, numWords, modality):
+        """M:1819-1845 (argument order as in the reference: numWords, modality)."""
+        return state_io.top_words(self.engine.get_counts(modality)[0], numWords, self._lookup(modality))
+
+    def displayTopWords(self, numWords, numLabels=0, usingNewLines=False):
+        """M:1851-1888"""
+        return state_io.display_top_words(self.typeTopicCounts, self.alpha, self._lookups(), numWords, usingNewLines)
+
+    def printState(self, f):
+        """M:3269-3320: path -> gzip file (printState(File)); file object -> plain text (printState(PrintStream))."""
+        zs = [self.engine.get_assignments(m) for m in range(self.numModalities)]
+        args = (self.views, zs, self.present, self._lookups(), self.gamma, self.alpha, self.beta)
+        if isinstance(f, (str, bytes)):
+            state_io.write_state_gz(f, *args)
+        else:
+            state_io.write_state(f, *args)
+
+    def readState(self, f):
+        """Restores the assignments from a printState file of the same corpus (a Java run's or our own) and rebuilds the
+        counts (the initialisation path M:534-573 takes for saved states)."""
+        zs, header = state_io.read_state(f, self.views, self.present)
+        for m in range(self.numModalities):
+            self.engine.set_assignments(m, zs[m])
+        return header
+
+    def printTypeTopicCounts(self, path):
+        """M:2076-2102"""
+        with open(path, "w", encoding="utf-8") as out:
+            state_io.write_type_topic_counts(out, self.typeTopicCounts, self._lookups())
+
+    def printTopicWordWeights(self, f):
+        """M:2104-2129"""
+        if isinstance(f, (str, bytes)):
+            with open(f, "w", encoding="utf-8") as out:
+                state_io.write_topic_word_weights(out, self.typeTopicCounts, self.beta, self._lookups())
+        else:
+            state_io.write_topic_word_weights(f, self.typeTopicCounts, self.beta, self._lookups())
 
 
 class FastQMVWVTopicInferencer:

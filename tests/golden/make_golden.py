@@ -3,10 +3,9 @@
   oracle_tiny.json  -- a tiny two-view corpus with the oracle's initial assignments, its assignments after a few
                        reference-faithful sweeps and the resulting log-likelihood (drift guard for the oracle and an
                        integer golden vector for the engine's bit-exact initialisation).
-  sms_corpus.npz    -- BASELINE configs[0]: SampleData/SMSSpamCollection2.txt (id \\t label \\t text) through an
-                       approximation of the reference's text pipeline (S:1809-1817, S:1843-1845): lower-case, letter
-                       tokens, stoplists/en.txt, drop tokens shorter than 3 characters, drop types seen < round(0.001*D)
-                       times.  MALLET's SimpleTokenizer is binary-only, so the vocabulary is approximate.
+  sms_corpus.npz    -- BASELINE configs[0]: SampleData/SMSSpamCollection2.txt (id \\t label \\t text) through the reference's
+  sms_vocab.json       text pipeline (S:1800-1851, GenerateStoplist S:631-730) as restated in mvtopicmodel_b200/ingest.py, with
+                       MALLET's SimpleTokenizer / FeatureCountPipe rules recovered from the jar's bytecode (tools/jclass.py).
 """
 import json
 import os
@@ -40,30 +39,24 @@ def make_oracle_tiny():
 
 
 def make_sms():
+    """BASELINE configs[0] through the reference's own text pipeline as restated in mvtopicmodel_b200/ingest.py
+    (S:1800-1851 with PruneCntPerc = 0.001 of src/main/resources/config.properties:14; MALLET's SimpleTokenizer recovered
+    from bytecode).  Also stores a tokenizer known-answer table (input line -> tokens) for the CPU tests."""
+    from mvtopicmodel_b200 import ingest
     ref = "/root/reference"
-    path = os.path.join(ref, "SampleData", "SMSSpamCollection2.txt")
-    stop = set(w.strip().lower() for w in open(os.path.join(ref, "stoplists", "en.txt"), encoding="utf-8", errors="ignore") if w.strip())
-    docs = []
-    for line in open(path, encoding="utf-8", errors="ignore"):
-        parts = line.rstrip("\n").split("\t", 2)
-        if len(parts) < 3:
-            continue
-        toks = [t for t in re.findall(r"[^\W\d_]+", parts[2].lower()) if len(t) >= 3 and t not in stop]
-        docs.append(toks)
-    D = len(docs)
-    from collections import Counter
-    cnt = Counter(t for d in docs for t in d)
-    prune = int(round(0.001 * D))
-    vocab = sorted(t for t, c in cnt.items() if c >= prune)
-    idx = {t: i for i, t in enumerate(vocab)}
+    docs = ingest.read_sms_collection(os.path.join(ref, "SampleData", "SMSSpamCollection2.txt"))
+    stop = ingest.load_stoplist(os.path.join(ref, "stoplists", "en.txt"))
+    lists, alphabets = ingest.import_instances([docs], 1, prune_cnt_perc=0.001, prune_lbl_cnt_perc=0.001, prune_max_perc=10.0,
+                                               text_stoplist=stop)
+    il, alpha = lists[0], alphabets[0]
+    D = len(il)
     off = np.zeros(D + 1, dtype=np.int64)
-    words = []
-    for d, toks in enumerate(docs):
-        ids = [idx[t] for t in toks if t in idx]
-        words.extend(ids)
-        off[d + 1] = len(words)
-    np.savez_compressed(os.path.join(HERE, "sms_corpus.npz"), doc_off=off, word_id=np.array(words, dtype=np.int32), V=np.int32(len(vocab)))
-    print("sms_corpus.npz: docs", D, "types", len(vocab), "tokens", len(words), "max len", int((off[1:] - off[:-1]).max()))
+    np.cumsum([len(i.features) for i in il], out=off[1:])
+    words = np.concatenate([i.features for i in il]).astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "sms_corpus.npz"), doc_off=off, word_id=words, V=np.int32(len(alpha)))
+    json.dump({"vocab": alpha.entries, "first_docs": [[alpha.lookup_object(int(w)) for w in il[d].features] for d in range(12)]},
+              open(os.path.join(HERE, "sms_vocab.json"), "w"))
+    print("sms_corpus.npz: docs", D, "types", len(alpha), "tokens", len(words), "max len", int((off[1:] - off[:-1]).max()))
 
 
 if __name__ == "__main__":

@@ -749,3 +749,45 @@ def test_sweep_host_pipeline_equals_resident_sweep(engine_lib):
     for it in range(1, 4):
         e.sweep_host(it, z2)
         assert np.array_equal(z2[0], e.get_assignments(0)) and e.check_invariants() == 0
+
+
+def test_model_state_files_round_trip(engine_lib, tmp_path):
+    """SURVEY 8f ranks 3-4 end to end: text -> ingest.import_instances -> addInstances/estimate (with setSaveState) ->
+    printState; a second model over the same corpus reads the file back and holds identical counts; top words are strings."""
+    import gzip
+    from mvtopicmodel_b200 import ingest
+    from mvtopicmodel_b200.model import FastQMVWVParallelTopicModel
+    rng = np.random.default_rng(5)
+    vocab = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "theta", "iota", "kappa", "lambda", "sigma", "omega"]
+    labels = ["Deep Learning", "Topic Models", "Gibbs Sampling", "Bayesian Stats"]
+    texts = [("doc%d" % d, " ".join(rng.choice(vocab, size=rng.integers(3, 15)))) for d in range(200)]
+    side = [("doc%d" % d, ",".join(rng.choice(labels, size=rng.integers(1, 3)))) for d in range(0, 200, 2)]
+    lists, alphas = ingest.import_instances([texts, side], 2, prune_cnt_perc=0.0, prune_lbl_cnt_perc=0.0)
+    def build():
+        m = FastQMVWVParallelTopicModel(8, 2, alpha=0.1, beta=0.01)
+        m.setRandomSeed(11); m.setNumIterations(6); m.setBurninPeriod(100); m.setOptimizeInterval(0)
+        m.addInstances(lists)
+        return m
+    a = build()
+    a.setSaveState(3, str(tmp_path / "state"))
+    a.estimate()
+    assert (tmp_path / "state.3").exists() and (tmp_path / "state.6").exists()          # M:1154-1155
+    p = str(tmp_path / "final.gz")
+    a.printState(p)
+    lines = gzip.open(p, "rt").read().splitlines()
+    assert lines[0] == "#doc source pos typeindex type topic" and lines[1] == "#alpha : modality:0"
+    assert len(lines) == 5 + a.totalTokens[0] + a.totalTokens[1]
+    first = lines[5].split(" ")
+    assert first[0] == "0" and first[1] == "NA" and first[4] == alphas[0].lookup_object(int(first[3]))
+    b = build()
+    header = b.readState(p)
+    assert header["beta0"] == 0.01
+    for m in range(2):
+        na, ka = a.engine.get_counts(m); nb, kb = b.engine.get_counts(m)
+        assert np.array_equal(na, nb) and np.array_equal(ka, kb)
+        assert np.array_equal(a.getTopicAssignments(m), b.getTopicAssignments(m))
+    tw = a.getTopWords(3, 0)
+    assert len(tw) == 8 and all(isinstance(w, str) and w in vocab for t in tw for w in t)
+    assert a.displayTopWords(4).count("\n") == 8
+    a.printTypeTopicCounts(str(tmp_path / "ttc.txt"))
+    assert len(open(tmp_path / "ttc.txt").read().splitlines()) == len(alphas[0]) + len(alphas[1])

@@ -1,0 +1,159 @@
+"""CPU tests of the host code either side of the sampling path: ingestion rules recovered from
+MALLET's bytecode, the reference's pruning flow, Java number formatting, the text state formats and their reader."""
+import gzip
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mvtopicmodel_b200 import ingest, state_io
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_simple_tokenizer_rules():
+    """cc.mallet.pipe.SimpleTokenizer.pipe, hand-derived from the bytecode (tools/jclass.py): letters, marks and '_' extend a
+    token; separators / punctuation close it; digits, symbols and control characters vanish WITHOUT closing it."""
+    tok = ingest.simple_tokenize
+    assert tok("go until jurong point, crazy.. available") == ["go", "until", "jurong", "point", "crazy", "available"]
+    assert tok("abc123def") == ["abcdef"]                       # digits are dropped, the token continues
+    assert tok("abc\tdef\nghi") == ["abcdefghi"]                 # TAB / NEWLINE are control characters (type 15): dropped
+    assert tok("don't stop") == ["don", "t", "stop"]             # apostrophe = OTHER_PUNCTUATION closes
+    assert tok("snake_case-word") == ["snake_case", "word"]      # '_' extends, '-' (DASH_PUNCTUATION) closes
+    assert tok("a+b=c $5 ok") == ["abc", "ok"]                   # MATH / CURRENCY symbols dropped without closing
+    assert tok("café não") == ["café", "não"]   # non-ASCII letters and combining marks extend
+    assert tok("the cat and the hat", {"the", "and"}) == ["cat", "hat"]
+    assert tok("x" * 2500) == ["x" * 1000, "x" * 1000, "x" * 500]     # 1000-code-point buffer flushes
+    assert tok("") == [] and tok("123 456") == []
+    assert tok("“quoted” (paren) [x]") == ["quoted", "paren", "x"]
+
+
+def test_generate_stoplist_and_import_flow():
+    """S:631-730 + S:1800-1905 on a hand-checkable buffer."""
+    texts = [("d%d" % i, t) for i, t in enumerate([
+        "alpha beta gamma alpha", "alpha beta delta", "beta gamma nullity", "alpha xy gamma figure", "beta alpha-beta gamma",
+        "Alpha BETA", "gamma beta alpha", "alpha", "beta", "gamma", "unique", "alpha beta gamma"])]
+    side = [("d%d" % i, s) for i, s in enumerate([
+        "Deep Learning,Topic Models,ab,and", "Topic Models,Gibbs", "Deep Learning", "", "Topic Models,Rare Label", "x", "y", "z",
+        "Deep Learning,Topic Models", "Gibbs", "Gibbs", "Deep Learning"])]
+    lists, alphas = ingest.import_instances([texts, side], 2, prune_cnt_perc=0.25, prune_lbl_cnt_perc=0.17, prune_max_perc=10.0,
+                                            csv_stoplist={"gibbs"})
+    # text: prune_count = round(12 * 0.25) = 3 -> delta(1), nullity(1, also contains "null"), figure(1, contains "fig"),
+    # xy (length < 3), unique(1) are stopped; "alpha-beta" is tokenised as two words
+    assert alphas[0].entries == ["alpha", "beta", "gamma"]
+    assert [list(i.features) for i in lists[0]][:5] == [[0, 1, 2, 0], [0, 1], [1, 2], [0, 2], [1, 0, 1, 2]]
+    assert list(lists[0][5].features) == [0, 1]                                  # lower-cased before tokenising
+    assert lists[0].alphabet_size() == 3 and lists[0][10].features.size == 0
+    # side view: tokens longer than 3 chars and not stop words ("Gibbs" is stopped case-insensitively); prune threshold
+    # round(12 * 0.17) = 2 drops "Rare Label" (1); the new alphabet is numbered by first surviving occurrence
+    assert alphas[1].entries == ["Deep Learning", "Topic Models"]
+    assert [list(i.features) for i in lists[1]][:5] == [[0, 1], [1], [0], [], [1]]
+    assert [i.name for i in lists[1]] == [n for n, _ in side]
+    assert ingest._java_round(2.5) == 3 and ingest._java_round(-2.5) == -2 and ingest._java_round(0.49) == 0
+
+
+def test_java_split_and_csv_rules():
+    assert ingest._java_split("a,b,,c,,", ",") == ["a", "b", "", "c"]
+    assert ingest._java_split(",a", ",") == ["", "a"]
+    a = ingest.Alphabet()
+    assert list(ingest.csv_to_features("abcd;abc;ABCDE;abcd", a, ";")) == [0, 1, 0] and a.entries == ["abcd", "ABCDE"]
+    assert ingest.csv_to_features("", a).size == 0
+
+
+def test_sms_fixture_matches_pipeline_when_reference_is_present():
+    """tests/golden/sms_corpus.npz + sms_vocab.json are BASELINE configs[0] through ingest.import_instances; regenerate and compare
+    where the reference data exists (the build container), check the committed fixture's shape everywhere."""
+    f = np.load(os.path.join(GOLDEN, "sms_corpus.npz"))
+    g = json.load(open(os.path.join(GOLDEN, "sms_vocab.json")))
+    off, words, V = f["doc_off"], f["word_id"], int(f["V"])
+    assert len(off) - 1 == 5574 and V == len(g["vocab"]) == 1170 and len(words) == off[-1] == 25249
+    assert words.min() >= 0 and words.max() == V - 1
+    for d, toks in enumerate(g["first_docs"]):
+        assert [g["vocab"][w] for w in words[off[d]:off[d + 1]]] == toks
+    assert g["first_docs"][0] == ["point", "crazy", "bugis", "great", "world", "cine", "wat"]
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "SampleData", "SMSSpamCollection2.txt")):
+        return
+    docs = ingest.read_sms_collection(os.path.join(ref, "SampleData", "SMSSpamCollection2.txt"))
+    stop = ingest.load_stoplist(os.path.join(ref, "stoplists", "en.txt"))
+    lists, alphas = ingest.import_instances([docs], 1, prune_cnt_perc=0.001, text_stoplist=stop)
+    assert alphas[0].entries == g["vocab"]
+    assert np.array_equal(np.concatenate([i.features for i in lists[0]]), words)
+
+
+def test_java_number_text():
+    """Double.toString / NumberFormat(max 5 fraction digits) known answers (JLS 'Double.toString'; DecimalFormat HALF_EVEN)."""
+    d2s = state_io.java_double_to_string
+    for x, s in [(0.1, "0.1"), (1.0, "1.0"), (100.0, "100.0"), (1e7, "1.0E7"), (9999999.0, "9999999.0"), (1e-3, "0.001"),
+                 (9.9e-4, "9.9E-4"), (1e-4, "1.0E-4"), (12345678.9, "1.23456789E7"), (-2.5, "-2.5"), (0.0, "0.0"), (-0.0, "-0.0"),
+                 (1 / 3, "0.3333333333333333"), (1.5e-300, "1.5E-300"), (float("nan"), "NaN"), (float("-inf"), "-Infinity"),
+                 (0.01 + 3, "3.01"), (123456.789, "123456.789")]:
+        assert d2s(x) == s, (x, d2s(x), s)
+    nf = state_io.java_number_format
+    for x, s in [(0.1, "0.1"), (1.0, "1"), (1234.5678912, "1,234.56789"), (0.000005, "0.00001"), (0.0000049, "0"), (0.125, "0.125"),
+                 (1234567.0, "1,234,567"), (-0.5, "-0.5"), (2.000004, "2"), (0.33333333, "0.33333"), (-1e-9, "-0")]:
+        assert nf(x) == s, (x, nf(x), s)
+
+
+def test_sorted_words_follow_idsorter_order():
+    """cc.mallet.types.IDSorter.compareTo (bytecode): larger weight first; on ties the LARGER id first."""
+    nwk = np.array([[5, 0], [7, 1], [5, 1], [0, 0], [5, 3]])
+    assert state_io.sorted_words(nwk, 0) == [(1, 7), (4, 5), (2, 5), (0, 5)]
+    assert state_io.sorted_words(nwk, 1) == [(4, 3), (2, 1), (1, 1)]
+    assert state_io.top_words(nwk, 2, lambda i: "w%d" % i) == [["w1", "w4"], ["w4", "w2"]]
+    txt = state_io.display_top_words([nwk], np.array([[0.1, 0.25, 1.0]]), [lambda i: "w%d" % i], 3)
+    assert txt == "0\t0.1\tw1; w4; \n1\t0.25\tw4; w2; \n"            # numWords - 1 words: the reference's loop starts at 1
+    txt = state_io.display_top_words([nwk], np.array([[0.1, 0.25, 1.0]]), [lambda i: "w%d" % i], 2, True)
+    assert txt == "0\t0.1\nw1\t7\n\n1\t0.25\nw4\t3\n\n"
+
+
+def _tiny_state():
+    views = [(np.array([0, 2, 2, 5], dtype=np.int64), np.array([3, 1, 0, 3, 2], dtype=np.int32)),
+             (np.array([0, 1, 2, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32))]
+    zs = [np.array([1, 0, 2, 2, 1], dtype=np.int32), np.array([0, 2], dtype=np.int32)]
+    present = [np.array([1, 1, 1], dtype=np.uint8), np.array([1, 1, 0], dtype=np.uint8)]
+    look = [lambda i: "t%d" % i, lambda i: "k%d" % i]
+    alpha = np.array([[0.1, 0.2, 0.3, 0.4], [0.5, 0.25, 0.125, 0.1]])
+    return views, zs, present, look, np.array([1.0, 2.0]), alpha, np.array([0.01, 0.02])
+
+
+def test_state_text_format_and_round_trip(tmp_path):
+    views, zs, present, look, gamma, alpha, beta = _tiny_state()
+    buf = io.StringIO()
+    state_io.write_state(buf, views, zs, present, look, gamma, alpha, beta)
+    want = ("#doc source pos typeindex type topic\n"
+            "#alpha : modality:0\n"
+            "0.1 0.2 0.3 modality:1\n"
+            "1.0 0.5 0.25 \n"
+            "#beta[0] : 0.01\n"
+            "0 NA 0 3 t3 1\n0 NA 1 1 t1 0\n0 NA 0 1 k1 0\n"
+            "1 NA 0 0 k0 2\n"
+            "2 NA 0 0 t0 2\n2 NA 1 3 t3 2\n2 NA 2 2 t2 1\n")
+    assert buf.getvalue() == want                                      # M:3276-3320, byte for byte
+    back, header = state_io.read_state(io.StringIO(want), views, present)
+    assert all(np.array_equal(a, b) for a, b in zip(back, zs)) and header["beta0"] == 0.01
+    assert header["alpha_lines"] == ["#alpha : modality:0", "0.1 0.2 0.3 modality:1", "1.0 0.5 0.25 "]
+    p = str(tmp_path / "state.gz")
+    state_io.write_state_gz(p, views, zs, present, look, gamma, alpha, beta)
+    assert gzip.open(p, "rt").read() == want                           # printState(File) = the same text, gzipped
+    back, _ = state_io.read_state(p, views, present)
+    assert all(np.array_equal(a, b) for a, b in zip(back, zs))
+    with pytest.raises(ValueError):
+        state_io.read_state(io.StringIO(want.replace("2 NA 2 2 t2 1\n", "")), views, present)     # truncated
+    with pytest.raises(ValueError):
+        state_io.read_state(io.StringIO(want.replace("0 NA 1 1 t1 0", "0 NA 1 2 t2 0")), views, present)   # other corpus
+
+
+def test_count_dump_formats():
+    views, zs, present, look, gamma, alpha, beta = _tiny_state()
+    nwk = [np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0], [0, 1, 1]]), np.array([[0, 0, 1], [1, 0, 0]])]
+    buf = io.StringIO()
+    state_io.write_type_topic_counts(buf, nwk, look)                    # M:2076-2102
+    assert buf.getvalue().splitlines()[:2] == ["0 t0 0:0 1:0 2:1", "1 t1 0:1 1:0 2:0"] and len(buf.getvalue().splitlines()) == 6
+    buf = io.StringIO()
+    state_io.write_topic_word_weights(buf, nwk, beta, look)             # M:2113-2129
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "0\tt0\t0.01" and lines[1] == "0\tt1\t1.01" and lines[4] == "0\tk0\t0.02" and lines[5] == "0\tk1\t1.02"
+    assert len(lines) == 3 * 6
