@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: exchange the counts after the sweep instead of under it")
+    ap.add_argument("--narrow-all", action="store_true", help="N > 1 with overlap: every view's exchange on the CTA-limited communicator")
     ap.add_argument("--reserve-sms", type=int, default=int(os.environ.get("MVTM_RESERVE_SMS", "8")),
                     help="N > 1 with overlap: SMs the persistent sweep kernel leaves to the collective")
     args = ap.parse_args()
@@ -159,8 +160,6 @@ def main():
 
     # a single view has nothing to hide its exchange under (its next pass needs the result at once): serial there
     overlap = world > 1 and len(cfg["views"]) > 1 and not args.no_overlap
-    if overlap:
-        os.environ.setdefault("NCCL_MAX_CTAS", str(max(1, args.reserve_sms)))     # the collective lives on the SMs the sweep leaves free
     import torch
     from mvtopicmodel_b200 import Engine
     from mvtopicmodel_b200.dist import CountExchange, EngineAdapter, OverlapAdapter, OverlappedSweep
@@ -184,8 +183,16 @@ def main():
     if xch:
         xch.exchange()
     if overlap:
+        # two communicators: exchanges hidden under another view's pass live on the SMs the sweep leaves free (max_ctas);
+        # the exchange of the view with the longest pass cannot be hidden (only the short passes separate two of its own),
+        # so it runs on the default communicator, which may spread over the SMs that are idle while it is waited for
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = max(1, args.reserve_sms)
+        opts.config.min_ctas = 1
+        narrow = dist.new_group(pg_options=opts)
+        critical = int(np.argmax(eng.ntok))
         ovl_adapter = OverlapAdapter(eng, local_rank)
-        ovl = OverlappedSweep(ovl_adapter)
+        ovl = OverlappedSweep(ovl_adapter, view_groups={m: narrow for m in range(M) if m != critical or args.narrow_all})
 
     def barrier():
         torch.cuda.synchronize()
@@ -325,7 +332,7 @@ def main():
     if xch:
         line["config"]["allreduce_bytes_per_sweep"] = ovl.bytes_per_exchange if ovl else xch.bytes_per_exchange
         line["config"]["exchange"] = (f"overlapped: view m's all-reduce under the following passes, sweep grid {n_sms - args.reserve_sms} CTAs, "
-                                      f"NCCL_MAX_CTAS={os.environ.get('NCCL_MAX_CTAS')}") if ovl else "after the sweep (serial)"
+                                      f"hidden exchanges on a communicator with max_ctas={args.reserve_sms}, view {critical}'s on the default one") if ovl else "after the sweep (serial)"
     if world == 1 and not args.no_cpu_baseline:
         val, ms, ntok_s, _ = cpu_reference_run(args.workload, args.cpu_sample_docs, 3, 1, threads)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

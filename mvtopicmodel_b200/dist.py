@@ -105,9 +105,13 @@ class OverlappedSweep:
     barrier M:1231 asks no more).  Sum-form protocol, one all-reduce per view (table and totals are one buffer).  Needs
     identical global counts on every rank at entry (i.e. after any completed exchange) and snapshots (delta_begin/reset)."""
 
-    def __init__(self, adapter, group=None):
+    def __init__(self, adapter, group=None, view_groups=None):
+        """view_groups: optional {view: process group} overriding `group` per view.  A view whose exchange cannot be hidden
+        (the view with the longest pass: only the other, shorter passes lie between two of its own) should use a
+        communicator that may take every SM, the hidden ones a communicator limited to the SMs the sweep leaves free."""
         import torch.distributed as dist
         self.a, self.dist, self.group = adapter, dist, group
+        self.view_groups = dict(view_groups or {})
         self.bytes_per_exchange = 0
 
     def step(self, it):
@@ -118,7 +122,7 @@ class OverlappedSweep:
             a.comm_wait_view(m)
             buf = a.whole_buffer(m)
             with a.comm_context():
-                self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+                self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.view_groups.get(m, self.group))
             a.finish_async(m, world)
             a.view_wait_comm(m)
             total += buf.numel() * 4
