@@ -360,16 +360,36 @@ __device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa
     float target = u * (total + C);
     const bool newbucket = (C > 0.f) && (target < C);
     target -= C;
+    // the target is kept strictly below the total, so some lane always satisfies incl > target and the first one that does
+    // has positive weight (lanes of weight zero repeat their predecessor's inclusive sum)
+    target = fminf(target, next_below(total));
     const unsigned sh = (unsigned)(lane - gl);                                  // first lane of my group
     const unsigned gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
     const unsigned hit = (__ballot_sync(FULL, incl > target) >> sh) & gmask;
-    const unsigned pos = (__ballot_sync(FULL, lane_total > 0.f) >> sh) & gmask;
-    const int L = hit ? (__ffs(hit) - 1) : (pos ? 31 - __clz(pos) : 0);
+    const int L = __ffs(hit) - 1;
     // residual inside the lane, clamped strictly below the lane total so that the chunk found has positive weight
     const float r = fminf(target - (incl - lane_total), next_below(lane_total));
-    int jsel = 0; float base = 0.f;                                             // chunk: number of running sums <= r
+    // chunk: jsel = number of running sums <= r, base = the last of them (0 if none).  Binary search over the register-resident
+    // sums: one compare per level, the candidates of the next level chosen by selects (JG-1-log2 selects instead of 2 per sum)
+    int jsel = 0; float base = 0.f;
+    if (G == 32) {
+        constexpr int P2 = (JG <= 1) ? 1 : (JG <= 2) ? 2 : (JG <= 4) ? 4 : (JG <= 8) ? 8 : 16;
+        float win[P2];                                                          // thresholds cum[0..JG-2], +inf padded
 #pragma unroll
-    for (int j = 0; j < JG - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
+        for (int j = 0; j < P2; j++) win[j] = (j < JG - 1) ? cum[j] : __int_as_float(0x7f800000);
+#pragma unroll
+        for (int half = P2 / 2; half >= 1; half >>= 1) {
+            const float t = win[half - 1];
+            const bool ge = (r >= t);
+            base = ge ? t : base;
+            jsel += ge ? half : 0;
+#pragma unroll
+            for (int j = 0; j + 1 < half; j++) win[j] = ge ? win[half + j] : win[j];
+        }
+    } else {                    // several documents per warp: the independent compares of the linear form schedule better (measured)
+#pragma unroll
+        for (int j = 0; j < JG - 1; j++) { const bool ge = (r >= cum[j]); jsel += ge ? 1 : 0; base = ge ? cum[j] : base; }
+    }
     const int cidx = gl + G * jsel;
     const int4 rr = lds_i4(row_gl_sa + 16u * G * (uint32_t)jsel);
     const float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
@@ -459,7 +479,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
     const uint32_t mbar_u32 = c.sa + doc_off_mbar(KS, MULTI), ring_u32 = c.sa + doc_off_ring(KS, MULTI);
     const uint32_t q_gl_sa = c.sa + 16u * (uint32_t)gl;
     unsigned phasebits = 0u;
-    unsigned long long n_tok = 0, n_changed = 0, n_new = 0;
+    unsigned n_tok = 0, n_changed = 0, n_new = 0;                 // per lane group: far below 2^32 per launch
     const int m = P.m;
     int *zmv = P.zv[m];
     float bsq[JG];
@@ -519,12 +539,14 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             const int znext = (base + G < len) ? zmv[b + base + G] : -1;
             const int wnext0 = __shfl_sync(FULL, wnext, 0, G);
             const int ot_nextblk = ((unsigned)wnext0 < (unsigned)P.V && base + G < len) ? znext : -1;
+            int ot_carry = __shfl_sync(FULL, zeff, 0, G);
             for (int i = 0; i < nblk_max; i++) {
                 const bool act = i < nblk;
                 const int w = __shfl_sync(FULL, wcur, i, G);
-                const int ot = __shfl_sync(FULL, zeff, i, G);
+                const int ot = ot_carry;                                       // = zeff of token i (shuffled one step earlier)
                 const float u = __shfl_sync(FULL, umine, i, G);
                 int otn = __shfl_sync(FULL, zeff, (i + 1) & (G - 1), G);
+                ot_carry = otn;
                 if (i + 1 == G) otn = ot_nextblk;
                 int wa = __shfl_sync(FULL, wahead, i, G);                      // word of token base+i+R (ring refill)
                 const bool valid = act && (ot != -2);
@@ -584,9 +606,9 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
         wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n;
     }
     if (gl == 0) {
-        if (n_tok) atomicAdd(P.stats + 0, n_tok);
-        if (n_changed) atomicAdd(P.stats + 1, n_changed);
-        if (n_new) atomicAdd(P.stats + 2, n_new);
+        if (n_tok) atomicAdd(P.stats + 0, (unsigned long long)n_tok);
+        if (n_changed) atomicAdd(P.stats + 1, (unsigned long long)n_changed);
+        if (n_new) atomicAdd(P.stats + 2, (unsigned long long)n_new);
     }
     __syncthreads();
     if (P.update_global) {

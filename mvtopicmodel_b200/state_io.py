@@ -198,10 +198,15 @@ def read_state(inp, views, present=None):
             raise ValueError(f"malformed state line: {line!r}")
         if not advance():
             raise ValueError("state file holds more token lines than the corpus")
-        doc, pos, typeindex, topic = int(f[0]), int(f[-4]), int(f[-3]), int(f[-1])
+        # `source` and the word itself may hold blanks (side-view labels such as "Deep Learning"), so the line is not split
+        # blindly: doc is the first field, topic the last, and the (pos, typeindex) pair expected at this corpus position must
+        # appear as two consecutive fields in between
         b = int(views[m][0][d])
-        if doc != d or pos != pi or typeindex != int(views[m][1][b + pi]):
+        want = (str(pi), str(int(views[m][1][b + pi])))
+        ok = f[0] == str(d) and any((f[i], f[i + 1]) == want for i in range(2, len(f) - 2))
+        if not ok:
             raise ValueError(f"state line {line!r} does not match corpus position doc {d} view {m} pos {pi}")
+        topic = int(f[-1])
         zs[m][b + pi] = topic
         pi += 1
     if advance():
