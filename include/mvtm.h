@@ -126,6 +126,16 @@ int mvtm_doc_topic_hist(mvtm_handle *h, int32_t m, int32_t *hist_out, int32_t *m
  * reproduces Q18 (phantom topic-0 tokens of documents shorter than two tokens). */
 int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2);
 
+/* Held-out evaluation by document completion.  The reference constructs MALLET's MarginalProbEstimator (M:3470-3478) but never
+ * calls it (S:191 hard-codes perplexity = 0), so the estimator is this build's own and is applied identically to the CPU oracle:
+ * the handle holds the OBSERVED part of every held-out document (folded in with mvtm_set_counts + mvtm_init_assignments_from_counts
+ * + frozen sweeps, I:114-330), eval_off / eval_word is a doc-aligned CSR of the evaluation tokens of view m, and every
+ * in-vocabulary evaluation token w of document d scores
+ *     log sum_t (n_wk[w][t] + beta) / (n_k[t] + betaSum) * (n_d[t] + gamma*alpha[t]) / (N_obs + sum_t gamma*alpha[t])      (fp64)
+ * with n_d from the document's observed tokens of view m at their current assignments and gamma*alpha = 0 on inactive topics.
+ * *ll_out = sum of the logs, *n_out = tokens scored; perplexity = exp(-ll / n). */
+int mvtm_heldout_loglik(mvtm_handle *h, int32_t m, const int64_t *eval_off, const int32_t *eval_word, double *ll_out, int64_t *n_out);
+
 /* Parity probe: the conditional distribution of token (m, doc, pos) on the current (frozen) counts, computed
  * by the same device code the sweep uses.  p_row = row m of the view-coupling matrix p (W:327-337), M entries
  * (NULL = identity).  probs_out[0..K) normalised, probs_out[K] = share of the new-topic bucket (W:515). */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mvtm_get_counts": (_i32, [_vp, _i32, _vp, _vp]),
     "mvtm_doc_topic_hist": (_i32, [_vp, _i32, _vp, C.POINTER(_i32)]),
     "mvtm_loglik": (_i32, [_vp, _vp, _i32]),
+    "mvtm_heldout_loglik": (_i32, [_vp, _i32, _vp, _vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "mvtm_cond_probs": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "mvtm_check_invariants": (_i32, [_vp, C.POINTER(_i64)]),
     "mvtm_stats": (_i32, [_vp, C.POINTER(MvtmSweepStats)]),

@@ -1019,6 +1019,53 @@ extern "C" int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out)
     return MVTM_OK;
 }
 
+// held-out evaluation by document completion (see include/mvtm.h)
+extern "C" int mvtm_heldout_loglik(mvtm_handle *h, int32_t m, const int64_t *eval_off, const int32_t *eval_word, double *ll_out, int64_t *n_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added || !eval_off || !ll_out || !n_out) FAIL(h, MVTM_ERR_ARG, "mvtm_heldout_loglik: bad argument");
+    const long long D = h->D;
+    if (eval_off[0] != 0) FAIL(h, MVTM_ERR_ARG, "mvtm_heldout_loglik: eval_off[0] must be 0");
+    for (long long d = 0; d < D; d++) if (eval_off[d + 1] < eval_off[d]) FAIL(h, MVTM_ERR_ARG, "mvtm_heldout_loglik: eval_off not monotone at doc %lld", d);
+    const long long NE = eval_off[D];
+    if (NE > 0 && !eval_word) FAIL(h, MVTM_ERR_ARG, "mvtm_heldout_loglik: NULL eval_word");
+    *ll_out = 0.0; *n_out = 0;
+    if (D == 0 || NE == 0) return MVTM_OK;
+    CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_view_ready(h, m)) return rc;
+    ViewDev &v = h->v[m];
+    const int K = h->K;
+    std::vector<double> ga((size_t)K);
+    double ga_sum = 0.0;
+    for (int t = 0; t < K; t++) ga[(size_t)t] = h->gamma[m] * h->alpha[(size_t)m * (K + 1) + t];
+    for (int t : h->inactive) ga[(size_t)t] = 0.0;                      // as the sampler's prior mass (M:2670-2671)
+    for (int t = 0; t < K; t++) ga_sum += ga[(size_t)t];
+    long long *d_eoff = nullptr; int *d_eword = nullptr, *d_n = nullptr; double *d_ga = nullptr, *d_ll = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaMalloc(&d_eoff, (size_t)(D + 1) * 8)); step(cudaMalloc(&d_eword, (size_t)NE * 4)); step(cudaMalloc(&d_ga, (size_t)K * 8));
+    step(cudaMalloc(&d_ll, (size_t)D * 8)); step(cudaMalloc(&d_n, (size_t)D * 4));
+    step(cudaMemcpyAsync(d_eoff, eval_off, (size_t)(D + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    step(cudaMemcpyAsync(d_eword, eval_word, (size_t)NE * 4, cudaMemcpyHostToDevice, h->stream));
+    step(cudaMemcpyAsync(d_ga, ga.data(), (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> ll((size_t)D); std::vector<int> n((size_t)D);
+    if (e == cudaSuccess) {
+        const int warps = 4;
+        k_heldout_docs<<<h->num_sms * 4, warps * 32, (size_t)warps * K * 4, h->stream>>>(D, v.doc_off, v.z, d_eoff, d_eword, v.V, K, h->Kp, v.nwk, v.nk,
+                                                                                        d_ga, ga_sum, h->beta[m], h->betaSum[m], d_ll, d_n);
+        step(cudaGetLastError());
+    }
+    step(cudaMemcpyAsync(ll.data(), d_ll, (size_t)D * 8, cudaMemcpyDeviceToHost, h->stream));
+    step(cudaMemcpyAsync(n.data(), d_n, (size_t)D * 4, cudaMemcpyDeviceToHost, h->stream));
+    step(cudaStreamSynchronize(h->stream));
+    cudaFree(d_eoff); cudaFree(d_eword); cudaFree(d_ga); cudaFree(d_ll); cudaFree(d_n);
+    CK(h, e);
+    double tot = 0.0; long long cnt = 0;
+    for (long long d = 0; d < D; d++) { tot += ll[(size_t)d]; cnt += n[(size_t)d]; }      // fixed order: deterministic
+    *ll_out = tot; *n_out = cnt;
+    return MVTM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // multi-GPU delta plumbing: snapshot, export local delta in place, import reduced delta
 // ------------------------------------------------------------------------------------------------

@@ -801,6 +801,47 @@ __global__ void k_loglik_docs(long long n_docs, const long long *off, const int 
     }
 }
 
+// held-out scoring by document completion (mvtm_heldout_loglik): one warp per document; n_d from the handle's own tokens of the
+// view (the observed part, at their current assignments), every evaluation token w scored as
+//   log sum_t (n_wk[w][t] + beta) / (n_k[t] + betaSum) * (n_d[t] + ga[t]) / (N_obs + sum_t ga[t])          (fp64)
+__global__ void k_heldout_docs(long long n_docs, const long long *off, const int *z, const long long *eoff, const int *eword, int V, int K,
+                               int Kp, const int *nwk, const int *nk, const double *ga, double ga_sum, double beta, double betaSum,
+                               double *doc_ll, int *doc_n)
+{
+    extern __shared__ int sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int *cnt = sm + (size_t)warp * K;
+    for (int t = lane; t < K; t += 32) cnt[t] = 0;
+    __syncwarp();
+    for (long long d = (long long)blockIdx.x * nwarp + warp; d < n_docs; d += (long long)gridDim.x * nwarp) {
+        const long long b = off[d]; const int len = (int)(off[d + 1] - b);
+        const long long eb = eoff[d]; const int elen = (int)(eoff[d + 1] - eb);
+        if (elen == 0) { if (lane == 0) { doc_ll[d] = 0.0; doc_n[d] = 0; } continue; }
+        int nobs = 0;
+        for (int i = lane; i < len; i += 32) { int t = z[b + i]; if (t >= 0 && t < K) { atomicAdd(cnt + t, 1); nobs++; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
+        __syncwarp();
+        const double denom = (double)nobs + ga_sum;
+        double ll = 0.0; int n = 0;
+        for (int i = 0; i < elen; i++) {
+            const int w = eword[eb + i];
+            if ((unsigned)w >= (unsigned)V) continue;                     // out-of-vocabulary: not scored (W:427-428 skips it too)
+            const int *row = nwk + (size_t)w * Kp;
+            double acc = 0.0;
+            for (int t = lane; t < K; t += 32)
+                acc += ((double)row[t] + beta) / ((double)nk[t] + betaSum) * ((double)cnt[t] + ga[t]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            ll += log(acc / denom); n++;
+        }
+        if (lane == 0) { doc_ll[d] = ll; doc_n[d] = n; }
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) { int t = z[b + i]; if (t >= 0 && t < K) cnt[t] = 0; }
+        __syncwarp();
+    }
+}
+
 // topic-word part M:3389-3415: per-block partial sums of lgamma(beta + n) over cells with n > 0 and their count
 __global__ void k_loglik_cells(int V, int K, int Kp, const int *nwk, double beta, double *part_sum, long long *part_nnz)
 {

@@ -162,6 +162,15 @@ class Engine:
         self._ck(self.L.mvtm_loglik(self.h, _ptr(out), int(quirk_len2)))
         return out
 
+    def heldout_loglik(self, m, eval_off, eval_word):
+        """(sum of log p(w | d) over the evaluation tokens of view m, tokens scored) -- document completion, see mvtm.h."""
+        eo = np.ascontiguousarray(eval_off, dtype=np.int64); ew = np.ascontiguousarray(eval_word, dtype=np.int32)
+        if len(eo) != self.D + 1 or eo[-1] != len(ew):
+            raise ValueError("eval CSR must be aligned with the handle's documents")
+        ll, n = C.c_double(), C.c_int64()
+        self._ck(self.L.mvtm_heldout_loglik(self.h, int(m), _ptr(eo), _ptr(ew), C.byref(ll), C.byref(n)))
+        return ll.value, n.value
+
     def doc_topic_hist(self, m):
         ml = C.c_int32()
         self._ck(self.L.mvtm_doc_topic_hist(self.h, m, None, C.byref(ml)))

@@ -241,6 +241,24 @@ class FastQMVWVParallelTopicModel:
             state_io.write_topic_word_weights(f, self.typeTopicCounts, self.beta, self._lookups())
 
 
+def split_for_completion(views):
+    """Document completion split: within every document-view the tokens at even positions are OBSERVED (folded in), those at
+    odd positions are EVALUATED.  Returns (observed views, evaluation views), both doc-aligned CSR like the input."""
+    obs, ev = [], []
+    for off, w in views:
+        lens = (off[1:] - off[:-1]).astype(np.int64)
+        pos = np.arange(len(w), dtype=np.int64) - np.repeat(off[:-1], lens)
+        is_obs = (pos % 2) == 0
+        for keep, dst in ((is_obs, obs), (~is_obs, ev)):
+            cnt = np.zeros(len(off) - 1, dtype=np.int64)
+            if len(w):
+                np.add.at(cnt, np.repeat(np.arange(len(off) - 1), lens), keep.astype(np.int64))
+            noff = np.zeros(len(off), dtype=np.int64)
+            np.cumsum(cnt, out=noff[1:])
+            dst.append((noff, np.ascontiguousarray(w[keep], dtype=np.int32)))
+    return obs, ev
+
+
 class FastQMVWVTopicInferencer:
     """Mirror of org.madgik.MVTopicModel.FastQMVWVTopicInferencer (I) for the sampling path: folds NEW documents into a
     trained model with the global counts frozen (the worker with nut = 0, I:211-256).
@@ -262,6 +280,65 @@ class FastQMVWVTopicInferencer:
         self.device = model.device
         self.seed = model.randomSeed if model.randomSeed != -1 else 1
         self.engine = None
+
+    def _join(self, instances):
+        """Views of the new documents joined by name exactly as addInstances does (M:437-455) -> (names, CSR views)."""
+        M = self.M
+        entityPosition, docs, names = {}, [], []
+        for m in range(M):
+            for inst in instances[m]:
+                if m != 0 and inst.name in entityPosition:
+                    docs[entityPosition[inst.name]][m] = inst.features
+                else:
+                    row = [None] * M; row[m] = inst.features
+                    docs.append(row); entityPosition[inst.name] = len(docs) - 1; names.append(inst.name)
+        D = len(docs)
+        views = []
+        for m in range(M):
+            lens = np.array([0 if r[m] is None else len(r[m]) for r in docs], dtype=np.int64)
+            off = np.zeros(D + 1, dtype=np.int64); np.cumsum(lens, out=off[1:])
+            words = np.concatenate([r[m] for r in docs if r[m] is not None and len(r[m])]) if off[-1] else np.zeros(0, np.int32)
+            views.append((off, words.astype(np.int32)))
+        return names, views
+
+    def _fold_in(self, views, quirk_bare_trees=False):
+        """I:114-330: trained counts frozen, tree-draw initialisation, numIterations sweeps over `views`."""
+        self.engine = e = Engine(self.K, [max(1, v) for v in self.numTypes], views, seed=self.seed, device=self.device)
+        e.set_hyper(inactive=self.inactive, **self.hyper)
+        for m in range(self.M):
+            e.set_counts(m, *self.counts[m])
+        e.init_assignments_from_counts()
+        for it in range(1, self.numIterations + 1):
+            e.sweep(it, update_global=2 if quirk_bare_trees else 0)
+        return e
+
+    def heldOutPerplexity(self, instances, numSamples=1, lastSweeps=1):
+        """Per-view held-out perplexity by document completion (this build's estimator: the reference never evaluates one,
+        S:191): even-position tokens of every held-out document-view are folded in with the inferencer's frozen sweeps,
+        odd-position tokens are scored by mvtm_heldout_loglik.  One fold-in is a single Gibbs sample; `numSamples` fold-ins
+        with different seeds x the last `lastSweeps` sweeps of each are averaged (in the log domain) to cut its variance.
+        Returns (perplexity[M], tokens scored[M])."""
+        _, views = self._join(instances)
+        obs, ev = split_for_completion(views)
+        acc, cnt, seed0 = np.zeros(self.M), np.zeros(self.M, dtype=np.int64), self.seed
+        for s in range(int(numSamples)):
+            self.seed = seed0 + s
+            self.engine = e = Engine(self.K, [max(1, v) for v in self.numTypes], obs, seed=self.seed, device=self.device)
+            e.set_hyper(inactive=self.inactive, **self.hyper)
+            for m in range(self.M):
+                e.set_counts(m, *self.counts[m])
+            e.init_assignments_from_counts()
+            for it in range(1, self.numIterations + 1):
+                e.sweep(it, update_global=0)
+                if it > self.numIterations - int(lastSweeps):
+                    for m in range(self.M):
+                        ll, n = e.heldout_loglik(m, ev[m][0], ev[m][1])
+                        cnt[m] = n
+                        acc[m] += ll / max(n, 1)
+        self.seed = seed0
+        ppl = np.exp(-acc / (int(numSamples) * int(lastSweeps)))
+        ppl[cnt == 0] = np.nan
+        return ppl, cnt
 
     def inferTopicDistributions(self, instances, discrWeightPerModality=None, quirk_bare_trees=False):
         M, K = self.M, self.K

@@ -266,3 +266,26 @@ def doc_topic_proportions(views, zs, K, gamma, alpha, alphaSum, p_mean0, weights
         if norm > 0:
             out[d] /= norm
     return out
+
+
+def heldout_loglik(obs_view, z_obs, nwk, nk, eval_view, ga, beta, betaSum):
+    """Document-completion score of ONE view, the restatement of mvtm_heldout_loglik (include/mvtm.h) in numpy fp64:
+    sum over in-vocabulary evaluation tokens of log( phi[w] . (n_d + ga) / (N_obs + sum ga) ), n_d from the observed tokens.
+    ga = gamma*alpha[0..K) with zeros on inactive topics.  Returns (sum of logs, tokens scored)."""
+    off, _ = obs_view
+    eoff, ew = eval_view
+    V, K = nwk.shape
+    phi = (nwk.astype(np.float64) + beta) / (nk.astype(np.float64) + betaSum)[None, :]
+    ga = np.asarray(ga, dtype=np.float64)
+    ll, n = 0.0, 0
+    for d in range(len(off) - 1):
+        words = ew[eoff[d]:eoff[d + 1]]
+        words = words[(words >= 0) & (words < V)]
+        if len(words) == 0:
+            continue
+        zd = z_obs[off[d]:off[d + 1]]
+        zd = zd[(zd >= 0) & (zd < K)]
+        theta = (np.bincount(zd, minlength=K).astype(np.float64) + ga) / (len(zd) + ga.sum())
+        ll += float(np.log(phi[words] @ theta).sum())
+        n += len(words)
+    return ll, n

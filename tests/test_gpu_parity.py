@@ -791,3 +791,101 @@ def test_model_state_files_round_trip(engine_lib, tmp_path):
     assert a.displayTopWords(4).count("\n") == 8
     a.printTypeTopicCounts(str(tmp_path / "ttc.txt"))
     assert len(open(tmp_path / "ttc.txt").read().splitlines()) == len(alphas[0]) + len(alphas[1])
+
+
+# ---- held-out perplexity by document completion (north_star correctness check c) ------------------------------------------
+def test_heldout_scoring_matches_oracle_restatement(engine_lib, oracle_mod):
+    """mvtm_heldout_loglik against the numpy fp64 restatement on the SAME state: 1e-10 relative."""
+    from mvtopicmodel_b200 import Engine
+    from mvtopicmodel_b200.model import split_for_completion
+    O = oracle_mod
+    K, Vs = 130, [300, 100, 50]
+    train = random_corpus(81, 600, K, Vs, [20, 4, 2])
+    new = random_corpus(82, 200, K, Vs, [18, 5, 3], oov=True)
+    t = Engine(K, Vs, train, seed=3); t.init_assignments()
+    for it in range(1, 8):
+        t.sweep(it)
+    counts = [t.get_counts(m) for m in range(3)]
+    obs, ev = split_for_completion(new)
+    for m in range(3):          # the split is a partition of every document-view, even positions observed
+        assert len(obs[m][1]) + len(ev[m][1]) == len(new[m][1])
+        lens = new[m][0][1:] - new[m][0][:-1]
+        assert np.array_equal(obs[m][0][1:] - obs[m][0][:-1], (lens + 1) // 2)
+    e = Engine(K, Vs, obs, seed=9)
+    alpha = np.random.default_rng(1).uniform(0.02, 0.3, size=(3, K + 1))
+    gamma = np.array([1.0, 0.7, 1.5])
+    e.set_hyper(alpha=alpha, alphaSum=alpha.sum(1), gamma=gamma, inactive=[5, 77])
+    for m in range(3):
+        e.set_counts(m, *counts[m])
+    e.init_assignments_from_counts()
+    for it in range(1, 4):
+        e.sweep(it, update_global=0)
+    for m in range(3):
+        ga = gamma[m] * alpha[m][:K].copy(); ga[[5, 77]] = 0.0
+        ll, n = e.heldout_loglik(m, ev[m][0], ev[m][1])
+        ll_o, n_o = O.heldout_loglik(obs[m], e.get_assignments(m), counts[m][0], counts[m][1], ev[m], ga, 0.01, 0.01 * Vs[m])
+        assert n == n_o and n > 0
+        assert ll == pytest.approx(ll_o, rel=1e-10)
+    with pytest.raises(Exception):
+        e.heldout_loglik(0, ev[0][0][:-1], ev[0][1])
+
+
+def test_heldout_perplexity_trajectory_within_one_percent(engine_lib, oracle_mod):
+    """north_star (c), second half: held-out perplexity after fixed numbers of sweeps, engine-trained vs oracle-trained
+    (sequential, reference-faithful stale trees), each through its own fold-in (frozen sweeps over the observed halves) and the
+    same document-completion estimator.  One fold-in is a single Gibbs sample: on this corpus two fold-in seeds over the SAME
+    counts differ by ~1 % (text, 15 K scored tokens) and 2-4 % (side views, 1-2 K tokens), so the estimate is averaged over 4
+    seeds x the last 3 fold-in sweeps.  Tolerance: 1 % on the text view, 3 % on the two small side views."""
+    from mvtopicmodel_b200 import Engine, corpus
+    from mvtopicmodel_b200.model import split_for_completion
+    O = oracle_mod
+    K, Vs, views = corpus.generate("small_3v")
+    D = len(views[0][0]) - 1
+    cut = 2000
+    def part(lo, hi):
+        return [(np.ascontiguousarray(off[lo:hi + 1] - off[lo]), np.ascontiguousarray(w[off[lo]:off[hi]])) for off, w in views]
+    train, held = part(0, cut), part(cut, D)
+    obs, ev = split_for_completion(held)
+    SEEDS, LAST = (5, 6, 7, 8), (8, 9, 10)
+    e = Engine(K, Vs, train, seed=21, max_ctas=16, warps_per_cta=4); e.init_assignments()      # production-like in-flight share
+    o = O.Oracle(K, Vs, train, seed=21); o.init_assignments(); o.rebuild_trees()
+    def ppl_engine(counts):
+        acc = np.zeros(3)
+        for seed in SEEDS:
+            f = Engine(K, Vs, obs, seed=seed)
+            for m in range(3):
+                f.set_counts(m, *counts[m])
+            f.init_assignments_from_counts()
+            for it in range(1, 11):
+                f.sweep(it, update_global=0)
+                if it in LAST:
+                    for m in range(3):
+                        ll, n = f.heldout_loglik(m, ev[m][0], ev[m][1]); acc[m] += ll / n
+        return np.exp(-acc / (len(SEEDS) * len(LAST)))
+    def ppl_oracle(counts):
+        acc = np.zeros(3)
+        for seed in SEEDS:
+            f = O.Oracle(K, Vs, obs, seed=seed)
+            for m in range(3):
+                f.set_counts(m, *counts[m])
+            f.init_from_phi()
+            for it in range(1, 11):
+                f.sweep(it, O.F_FROZEN)
+                if it in LAST:
+                    for m in range(3):
+                        ll, n = O.heldout_loglik(obs[m], f.get_assignments(m), counts[m][0], counts[m][1], ev[m], np.full(K, 0.1), 0.01, 0.01 * Vs[m])
+                        acc[m] += ll / n
+        return np.exp(-acc / (len(SEEDS) * len(LAST)))
+    it = 0
+    for stop in (30, 60, 100):
+        while it < stop:
+            it += 1
+            e.sweep(it); o.sweep(it, O.F_STALE_TREES)
+        pe = ppl_engine([e.get_counts(m) for m in range(3)])
+        po = ppl_oracle([o.get_counts(m) for m in range(3)])
+        print("held-out perplexity after", stop, "sweeps: engine", pe, "oracle", po)
+        rel = np.abs(pe - po) / po
+        assert rel[0] < REL_TOL_LL, (stop, pe, po)
+        assert np.all(rel[1:] < 0.03), (stop, pe, po)
+    # sanity: a trained model predicts held-out text far better than the uniform distribution over the vocabulary
+    assert pe[0] < 0.6 * Vs[0]
