@@ -269,14 +269,23 @@ def main():
         for m in range(M):
             zn[m][:] = eng.get_assignments(m)
 
+        if xch:
+            from mvtopicmodel_b200.dist import _DevBuf
+            whole = []
+            for m in range(M):
+                (p1, n1), (p2, n2) = eng.sum_exchange_buffers(m)
+                whole.append(torch.as_tensor(_DevBuf(p1, n1 + n2), device=f"cuda:{local_rank}"))
+                eng.set_host_mirror(m, zn[m])              # the sweep kernel keeps the pinned arrays current
+
         def e2e_step(i):
             if xch:
                 for m in range(M):
-                    eng.set_assignments(m, zn[m])          # H2D + local rebuild
-                xch.reset(); xch.exchange()                # local counts -> global counts
-                step(i); drain()
+                    eng.set_assignments(m, zn[m])          # H2D + rebuild of the LOCAL counts
                 for m in range(M):
-                    eng.get_assignments(m, out=zn[m])      # D2H into the pinned buffer
+                    dist.all_reduce(whole[m])              # local counts -> global counts (table and totals, one buffer)
+                torch.cuda.synchronize()
+                eng.delta_begin()                          # snapshot = global counts
+                step(i); drain()                           # new z lands in zn through the host mirror
             else:
                 eng.sweep_host(i, zn)
         e2e_steps = max(3, min(args.steps, 10))
@@ -299,7 +308,11 @@ def main():
         e2e = {"value": ntok_global * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * ntok_local,
                "d2h_bytes_per_step": 4 * ntok_local, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                "call": "mvtm_sweep_host (pinned host z in/out: chunked upload + count rebuild, sweep, new z stored to the pinned arrays by the kernel)" if not xch else
-                       "mvtm_set_assignments + delta all-reduce + mvtm_sweep + delta all-reduce + mvtm_get_assignments"}
+                       "mvtm_set_assignments (H2D + local counts) + count all-reduce + sweep with mvtm_set_host_mirror (kernel-written D2H) + count exchange"}
+        if xch:
+            for m in range(M):
+                assert np.array_equal(zn[m], eng.get_assignments(m)), "host mirror out of date"
+                eng.set_host_mirror(m, None)
 
     if rank != 0:
         if dist:

@@ -112,6 +112,13 @@ int mvtm_sweep(mvtm_handle *h, int32_t iteration, int32_t update_global);
  * stateless host (a JVM holding topicSequence arrays) makes; bench.py's e2e number times it. */
 int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout);
 
+/* Host mirror of the assignments: z_host (caller-owned, tokens-of-view-m ints, PINNED and MAPPED host memory -- cudaHostAlloc or
+ * cudaHostRegister) receives every new assignment that subsequent sweeps of view m store, written by the sweep kernel itself
+ * next to its store to device memory (posted PCIe writes under the sampling).  A JVM-side topicSequence buffer thus stays
+ * current without a copy after the sweep; the array is complete when the sweep call returns (mvtm_sweep) or mvtm_sweep_finish
+ * has returned.  Tokens the sweep skips (out-of-vocabulary words) are not rewritten.  NULL stops mirroring. */
+int mvtm_set_host_mirror(mvtm_handle *h, int32_t m, int32_t *z_host);
+
 /* Readers.  z: LabelSequence.getFeatures() of every doc concatenated in CSR order; n_wk: typeTopicCounts[m]
  * as V_m x K row-major by word (M:584); n_k: tokensPerTopic[m]. */
 int mvtm_get_assignments(mvtm_handle *h, int32_t m, int32_t *z_out);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "mvtm_get_hyper": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_i32)]),
     "mvtm_sweep": (_i32, [_vp, _i32, _i32]),
     "mvtm_sweep_host": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "mvtm_set_host_mirror": (_i32, [_vp, _i32, _vp]),
     "mvtm_get_assignments": (_i32, [_vp, _i32, _vp]),
     "mvtm_get_counts": (_i32, [_vp, _i32, _vp, _vp]),
     "mvtm_doc_topic_hist": (_i32, [_vp, _i32, _vp, C.POINTER(_i32)]),

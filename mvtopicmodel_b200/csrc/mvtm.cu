@@ -30,6 +30,7 @@ struct ViewDev {
     unsigned char *present = nullptr;
     int *nwk = nullptr, *nk = nullptr, *nk_snap = nullptr;
     int *order = nullptr;
+    int *z_mirror = nullptr;                        // device alias of a caller-owned pinned array that mirrors z (mvtm_set_host_mirror)
     std::vector<long long> chunk_tok_off;           // mvtm_sweep_host: HOST_CHUNKS + 1 token offsets of contiguous document ranges
     float *ga_tree = nullptr, *ga_full = nullptr, *ga_one = nullptr;   // ga_one: all ones, the inferencer's bare trees (Q13)
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
@@ -639,6 +640,7 @@ static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, i
         SweepParams P;
         fill_params(h, m, iteration, update_global, P);
         P.R = lc.R; P.oc_smem = lc.oc_smem;
+        P.z_host = v.z_mirror;
         CK(h, launch_sweep(h, P, lc));
         (*launches)++;
     }
@@ -750,6 +752,19 @@ static int *mapped_alias(const void *p)
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
     return (int *)a.devicePointer;
+}
+
+extern "C" int mvtm_set_host_mirror(mvtm_handle *h, int32_t m, int32_t *z_host)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_set_host_mirror: bad view %d", m);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (!z_host) { h->v[m].z_mirror = nullptr; return MVTM_OK; }
+    int *alias = mapped_alias(z_host);
+    if (!alias) FAIL(h, MVTM_ERR_ARG, "mvtm_set_host_mirror: the array is not pinned + mapped host memory (cudaHostAlloc / cudaHostRegister)");
+    h->v[m].z_mirror = alias;
+    return MVTM_OK;
 }
 
 extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout)

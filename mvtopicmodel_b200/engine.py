@@ -144,6 +144,12 @@ class Engine:
             ptrs[m] = z.ctypes.data
         self._ck(self.L.mvtm_sweep_host(self.h, int(iteration), ptrs))
 
+    def set_host_mirror(self, m, z_host):
+        """z_host: pinned int32 numpy array (e.g. torch.empty(n, dtype=torch.int32).pin_memory().numpy()) or None."""
+        if z_host is not None:
+            assert z_host.dtype == np.int32 and z_host.flags["C_CONTIGUOUS"] and len(z_host) == self.ntok[m]
+        self._ck(self.L.mvtm_set_host_mirror(self.h, int(m), None if z_host is None else C.c_void_p(z_host.ctypes.data)))
+
     def stats(self):
         s = MvtmSweepStats()
         self._ck(self.L.mvtm_stats(self.h, C.byref(s)))

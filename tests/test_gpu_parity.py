@@ -889,3 +889,33 @@ def test_heldout_perplexity_trajectory_within_one_percent(engine_lib, oracle_mod
         assert np.all(rel[1:] < 0.03), (stop, pe, po)
     # sanity: a trained model predicts held-out text far better than the uniform distribution over the vocabulary
     assert pe[0] < 0.6 * Vs[0]
+
+
+def test_host_mirror_follows_sweeps(engine_lib):
+    """mvtm_set_host_mirror: a pinned host array receives every new assignment from the sweep kernel itself; after each sweep it
+    equals the device assignments (tokens of out-of-vocabulary words are never rewritten and keep what the host put there)."""
+    import torch
+    from mvtopicmodel_b200 import Engine, MvtmError
+    K, Vs = 500, [800, 120]
+    views = random_corpus(93, 3000, K, Vs, [40, 5], oov=True)
+    e = Engine(K, Vs, views, seed=4)
+    e.init_assignments()
+    mir = [torch.empty(n, dtype=torch.int32).pin_memory().numpy() for n in e.ntok]
+    for m in range(2):
+        mir[m][:] = e.get_assignments(m)
+        e.set_host_mirror(m, mir[m])
+    for it in range(1, 5):
+        if it % 2:
+            e.sweep(it)
+        else:
+            for m in range(2):
+                e.sweep_view_async(it, m)
+            e.sweep_finish()
+        for m in range(2):
+            assert np.array_equal(mir[m], e.get_assignments(m))
+    e.set_host_mirror(0, None)
+    before = mir[0].copy()
+    e.sweep(5)
+    assert np.array_equal(mir[0], before) and np.array_equal(mir[1], e.get_assignments(1))
+    with pytest.raises(MvtmError):
+        e.set_host_mirror(0, np.zeros(e.ntok[0], dtype=np.int32))          # pageable memory is refused
