@@ -222,6 +222,13 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
 
 // Build n_d, (MULTI: oc/om/cpar), q and beta*sum(q) for document d of view P.m (len == 0: nothing to do, but every
 // lane still walks the same __syncwarp sequence -- the groups of a warp hold different documents).
+//
+// Cost is O(KS/G) cheap vector work + O(tokens of the document, all views): q starts as the document-independent vector
+// ga[t] / (n_k[t] + betaSum) (topics outside S, W:495-513) and only the topics some token of the document holds are
+// recomputed; the other views' counts are histogrammed INTO the (still empty) n_d array and consumed by exchange, which
+// leaves it empty again, so nothing is scanned densely.  (The first version zeroed, histogrammed and scanned all KS
+// topics per other view and evaluated the full q expression for every topic: ~4000 instructions per document at
+// K = 1000 -- more than sampling the 6-12 tokens of a side view.)
 template <int KS, int G, bool MULTI>
 __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d, int len, int gl, const double *p_override,
                                           bool skip_first, float (&bsq)[KS / (4 * G)])
@@ -231,14 +238,22 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
     const long long b = P.doc_off[m][d];
     const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
     unsigned *nd32 = reinterpret_cast<unsigned *>(c.nd);
-#pragma unroll 4
-    for (int k = gl; k < KS / 2; k += G) nd32[k] = 0u;
+    {   // n_d = 0 (128-bit stores) and q = ga * ginv for every topic
+        uint4 *nd128 = reinterpret_cast<uint4 *>(c.nd);
+#pragma unroll
+        for (int k = 0; k < (KS / 8 + G - 1) / G; k++) { const int i = gl + G * k; if (i < KS / 8) nd128[i] = make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll(MULTI ? 2 : JG)
+        for (int j = 0; j < JG; j++) {
+            const int cidx = gl + G * j;
+            const float4 g01 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx), g23 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx + 16u);
+            reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(g01.x * g01.y, g01.z * g01.w, g23.x * g23.y, g23.z * g23.w);
+        }
+    }
     c.pmm = 1.f; c.coefm = (float)len + P.gas[m]; c.C = 0.f;
     if (MULTI) {
         c.pmm = draw_p(P, m, gdoc, p_override);
         for (int k = gl; k < KS / 32; k += G) c.om[k] = 0u;
         float cdoc = 0.f;
-        unsigned *tmp32 = reinterpret_cast<unsigned *>(c.q);      // q is built last: reuse it as u16 scratch
         for (int i = 0; i < P.M; i++) {                           // uniform trip count; per-group work is predicated
             const long long bi = P.doc_off[i][d];
             const int leni = (int)(P.doc_off[i][d + 1] - bi);
@@ -249,25 +264,22 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
             const float ci = other ? pmi / denom : 0.f;           // W:403-404
             __syncwarp();
             if (gl == 0) c.cpar[i] = ci;
-            if (other) {
-#pragma unroll 4
-                for (int k = gl; k < KS / 2; k += G) tmp32[k] = 0u;
-            }
-            __syncwarp();
-            if (other) {
+            if (other) {                                          // histogram of view i into the empty n_d array
                 const int *zi = P.zv[i] + bi;
-                for (int k = gl; k < leni; k += G) { int t = zi[k]; if (t >= 0) atomicAdd(&tmp32[t >> 1], 1u << ((t & 1) * 16)); }
+                for (int k = gl; k < leni; k += G) { int t = zi[k]; if (t >= 0) atomicAdd(&nd32[t >> 1], 1u << ((t & 1) * 16)); }
             }
             __syncwarp();
-            if (other) {
-                const unsigned short *tmp16 = reinterpret_cast<const unsigned short *>(tmp32);
-#pragma unroll 2
-                for (int k = gl; k < KS; k += G) {
-                    unsigned cnt = tmp16[k];
-                    if (cnt) {        // first writer of a topic stores, later views accumulate (each k has one owner lane)
-                        const bool seen = (c.om[k >> 5] >> (k & 31)) & 1u;
-                        c.oc[k] = (seen ? c.oc[k] : 0.f) + ci * (float)cnt;
-                        if (!seen) atomicOr(&c.om[k >> 5], 1u << (k & 31));
+            if (other) {                                          // consume it: the first lane to reach a topic takes its count
+                const int *zi = P.zv[i] + bi;
+                for (int k = gl; k < leni; k += G) {
+                    const int t = zi[k];
+                    if (t < 0) continue;
+                    const unsigned sh = (unsigned)(t & 1) * 16u;
+                    const unsigned cnt = (atomicAnd(&nd32[t >> 1], ~(0xffffu << sh)) >> sh) & 0xffffu;
+                    if (cnt) {        // first view to hold the topic stores, later views accumulate (one lane per topic and view)
+                        const bool seen = (c.om[t >> 5] >> (t & 31)) & 1u;
+                        c.oc[t] = (seen ? c.oc[t] : 0.f) + ci * (float)cnt;
+                        if (!seen) atomicOr(&c.om[t >> 5], 1u << (t & 31));
                     }
                 }
             }
@@ -288,33 +300,31 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         }
     }
     __syncwarp();
-    // q for every topic, four per lane per step (kept rolled in the multi-view build: it runs once per document and
-    // the unrolled body would push the hot loop out of the instruction cache)
-#pragma unroll(MULTI ? 1 : JG)
-    for (int j = 0; j < JG; j++) {
-        const int cidx = gl + G * j, t0 = cidx * 4;
-        const uint2 n2 = reinterpret_cast<const uint2 *>(c.nd)[cidx];
-        const float2 gi[4] = { lds_f2(c.ginv_sa + 8u * (uint32_t)t0), lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 1)),
-                               lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 2)), lds_f2(c.ginv_sa + 8u * (uint32_t)(t0 + 3)) };
-        const float ndv[4] = { (float)(n2.x & 0xffffu), (float)(n2.x >> 16), (float)(n2.y & 0xffffu), (float)(n2.y >> 16) };
-        float out[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
+    // q of the topics some token of the document holds (S of W:376-391 plus, harmlessly, the skipped first token's topic):
+    // one token per lane, duplicates recompute the same value
+    for (int i = 0; i < (MULTI ? P.M : 1); i++) {
+        const int vi = MULTI ? i : m;
+        const long long bi = P.doc_off[vi][d];
+        const int leni = (len != 0) ? (int)(P.doc_off[vi][d + 1] - bi) : 0;
+        const int *zi = P.zv[vi] + bi;
+        for (int k = gl; k < leni; k += G) {
+            const int t = zi[k];
+            if (t < 0) continue;
+            const float ndv = (float)c.nd[t];
             bool inS = false; float ocv = 0.f, pri = 0.f;
             if (MULTI) {
-                int t = t0 + e;
                 const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
-                inS = (ndv[e] > 0.f) || oth;
-                if (inS && t < P.K) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
+                inS = (ndv > 0.f) || oth;
+                if (inS) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
             }
-            out[e] = q_value<MULTI>(ndv[e], inS, ocv, pri, c.coefm, c.pmm, gi[e]);
+            c.q[t] = q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
         }
-        reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(out[0], out[1], out[2], out[3]);
-        const float v = P.beta * ((out[0] + out[1]) + (out[2] + out[3]));
-        if (MULTI) {
+    }
+    __syncwarp();
 #pragma unroll
-            for (int jj = 0; jj < JG; jj++) if (jj == j) bsq[jj] = v;
-        } else bsq[j] = v;
+    for (int j = 0; j < JG; j++) {
+        const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];
+        bsq[j] = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
     }
     __syncwarp();
 }

@@ -20,5 +20,26 @@ for K, Vs, means in [(50, [120], [7]), (130, [150, 40, 30], [12, 3, 2]), (600, [
     e.loglik(); e.doc_topic_hist(0); e.p_statistics(); e.optimize_hyper(5, 15)
     e.sweep(6)
     assert e.check_invariants() == 0
+    # round-2 paths: pipelined host sweep (pageable arrays), async view passes + hand-over, host mirror, held-out scoring
+    zs = [e.get_assignments(m).copy() for m in range(len(Vs))]
+    e.sweep_host(7, zs)
+    import torch
+    comm = torch.cuda.Stream()
+    e.delta_begin()
+    mir = [torch.empty(n, dtype=torch.int32).pin_memory().numpy() for n in e.ntok]
+    for m in range(len(Vs)):
+        mir[m][:] = e.get_assignments(m); e.set_host_mirror(m, mir[m])
+    for m in range(len(Vs)):
+        e.sweep_view_async(8, m)
+        e.stream_wait_view(m, comm.cuda_stream)
+        e.sum_exchange_finish_async(m, 1, comm.cuda_stream, 4)
+        e.view_wait_stream(m, comm.cuda_stream)
+    e.sweep_finish()
+    e.sweep_host(9, mir)                                 # pinned arrays: the kernel writes them
+    for m in range(len(Vs)):
+        assert np.array_equal(mir[m], e.get_assignments(m))
+        e.set_host_mirror(m, None)
+    e.heldout_loglik(0, views[0][0], views[0][1])
+    assert e.check_invariants() == 0
     e.close()
 print("sanitize case done")
