@@ -132,6 +132,10 @@ int mvtm_doc_topic_hist(mvtm_handle *h, int32_t m, int32_t *hist_out, int32_t *m
 /* modelLogLikelihood M:3322-3452 with MALLET's logGammaStirling; ll_out has M entries.  quirk_len2 != 0
  * reproduces Q18 (phantom topic-0 tokens of documents shorter than two tokens). */
 int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2);
+/* The same value split for multi-rank hosts: doc_part sums over THIS handle's documents (M:3341-3373), word_part is the
+ * topic-word part (M:3389-3441), a function of the count tables only -- identical on every rank once the counts are global.
+ * Global log-likelihood = sum over ranks of doc_part + word_part of any one rank. */
+int mvtm_loglik_parts(mvtm_handle *h, double *doc_part_out, double *word_part_out, int32_t quirk_len2);
 
 /* Held-out evaluation by document completion.  The reference constructs MALLET's MarginalProbEstimator (M:3470-3478) but never
  * calls it (S:191 hard-codes perplexity = 0), so the estimator is this build's own and is applied identically to the CPU oracle:
@@ -208,6 +212,14 @@ int mvtm_scan_layout(mvtm_handle *h, int32_t *lanes_per_doc, int32_t *chunks_per
 #define MVTM_OPT_BETA  8u
 #define MVTM_OPT_ALL   15u
 int mvtm_optimize_hyper(mvtm_handle *h, int32_t iteration, uint32_t which);
+/* Multi-rank hyper-parameter step ("at optimise steps, the doc-topic histogram").  The statistics that
+ * mvtm_optimize_hyper gathers from THIS handle's documents -- optimizeP's overlap sums and per-view document counts, the longest
+ * document, the doc-topic histograms of optimizeDP, docLengthCounts of optimizeGamma -- are passed to `fn` before use:
+ * op 0 = replace each element by its sum over all ranks, op 1 = by its maximum; `ints` / `reals` may be NULL with a zero count;
+ * return 0 on success.  With an all-reduce behind `fn`, the same seed and the same iteration every rank installs identical
+ * hyper-parameters.  optimizeBeta needs no reduction: it reads the (already global) count tables.  fn = NULL (default): single handle. */
+typedef int (*mvtm_stat_reducer)(void *ctx, int32_t op, int64_t *ints, int64_t n_ints, double *reals, int64_t n_reals);
+int mvtm_set_stat_reducer(mvtm_handle *h, mvtm_stat_reducer fn, void *ctx);
 int mvtm_p_statistics(mvtm_handle *h, double *psum_out, int64_t *docs_per_view_out);
 int mvtm_get_hyper_full(mvtm_handle *h, double *alpha, double *alpha_sum, double *beta, double *beta_sum, double *gamma,
                         double *p_a, double *p_b, double *p_mean, double *gamma_root, double *gamma_view, double *tables_cnt);

@@ -28,6 +28,7 @@ FLAG_SINGLE_WARP = 2
 OPT_P, OPT_DP, OPT_GAMMA, OPT_BETA, OPT_ALL = 1, 2, 4, 8, 15
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+STAT_REDUCER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_double), C.c_int64)
 # name -> (restype, argtypes); must list every function include/mvtm.h declares (tests check this)
 SIGNATURES = {
     "mvtm_create": (_i32, [C.POINTER(MvtmConfig), C.POINTER(_vp)]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "mvtm_get_counts": (_i32, [_vp, _i32, _vp, _vp]),
     "mvtm_doc_topic_hist": (_i32, [_vp, _i32, _vp, C.POINTER(_i32)]),
     "mvtm_loglik": (_i32, [_vp, _vp, _i32]),
+    "mvtm_loglik_parts": (_i32, [_vp, _vp, _vp, _i32]),
     "mvtm_heldout_loglik": (_i32, [_vp, _i32, _vp, _vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "mvtm_cond_probs": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "mvtm_check_invariants": (_i32, [_vp, C.POINTER(_i64)]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "mvtm_sum_exchange_finish_async": (_i32, [_vp, _i32, _i32, _vp, _i32]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),
+    "mvtm_set_stat_reducer": (_i32, [_vp, STAT_REDUCER, _vp]),
     "mvtm_p_statistics": (_i32, [_vp, _vp, _vp]),
     "mvtm_get_hyper_full": (_i32, [_vp] + [_vp] * 11),
     "mvtm_test_sampler": (_i32, [C.c_uint64, _i32, C.c_double, C.c_double, _i32, _vp]),

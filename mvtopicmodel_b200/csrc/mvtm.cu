@@ -61,6 +61,8 @@ struct mvtm_handle {
     double gammaView[MVTM_MAX_VIEWS] = { 0 }, tablesCnt[MVTM_MAX_VIEWS] = { 0 };
     double pMean[MVTM_MAX_VIEWS][MVTM_MAX_VIEWS] = { { 0 } };
     bool hyper_dirty = true;
+    mvtm_stat_reducer reducer = nullptr;            // multi-rank hyper-parameter step (mvtm_set_stat_reducer)
+    void *reducer_ctx = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;             // mvtm_sweep_host: H2D / D2H of z chunks beside the kernels
     std::vector<cudaEvent_t> host_ev;               // per (view, chunk): upload done
@@ -938,10 +940,24 @@ static double host_log_gamma_stirling(double z)
     return r;
 }
 
+static int loglik_impl(mvtm_handle *h, double *ll_out, double *doc_out, double *word_out, int32_t quirk_len2);
+
 extern "C" int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2)
 {
     if (!h) return MVTM_ERR_ARG;
     if (!ll_out) FAIL(h, MVTM_ERR_ARG, "mvtm_loglik: NULL output");
+    return loglik_impl(h, ll_out, nullptr, nullptr, quirk_len2);
+}
+
+extern "C" int mvtm_loglik_parts(mvtm_handle *h, double *doc_part_out, double *word_part_out, int32_t quirk_len2)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (!doc_part_out || !word_part_out) FAIL(h, MVTM_ERR_ARG, "mvtm_loglik_parts: NULL output");
+    return loglik_impl(h, nullptr, doc_part_out, word_part_out, quirk_len2);
+}
+
+static int loglik_impl(mvtm_handle *h, double *ll_out, double *doc_out, double *word_out, int32_t quirk_len2)
+{
     if (int rc = require_views(h, "mvtm_loglik")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
@@ -981,13 +997,16 @@ extern "C" int mvtm_loglik(mvtm_handle *h, double *ll_out, int32_t quirk_len2)
         double ll = 0.0; long long modalityCnt = 0;
         for (long long d = 0; d < D; d++) { ll += doc_ll[(size_t)d]; modalityCnt += counted[(size_t)d]; }
         ll += (double)modalityCnt * host_log_gamma_stirling(gas);                                 // M:3373
+        const double doc_part = ll;                      // everything above sums over THIS handle's documents
         long long nnz = 0;
         for (int bidx = 0; bidx < cell_blocks; bidx++) { ll += part[(size_t)bidx]; nnz += nnzp[(size_t)bidx]; }
         const double bV = h->beta[m] * v.V;
         for (int t = 0; t < K; t++) ll -= host_log_gamma_stirling(bV + nk[(size_t)t]);           // M:3417-3419
         ll += host_log_gamma_stirling(bV) * K;                                                    // M:3438
         ll -= host_log_gamma_stirling(h->beta[m]) * (double)nnz;                                  // M:3441
-        ll_out[m] = ll;
+        if (ll_out) ll_out[m] = ll;
+        if (doc_out) doc_out[m] = doc_part;
+        if (word_out) word_out[m] = ll - doc_part;      // the topic-word terms: functions of the (global) count tables only
     }
     cudaFree(d_ga); cudaFree(d_tlg); cudaFree(d_doc); cudaFree(d_cnt); cudaFree(d_part); cudaFree(d_nnz);
     CK(h, e);

@@ -187,13 +187,37 @@ __global__ void k_value_hist(int V, int K, int Kp, const int *nwk, int max_value
 }
 
 // ---- host -------------------------------------------------------------------------------------------------------
-static int doc_topic_hist_host(mvtm_handle *h, int m, std::vector<int> &hist, int &stride)
+// Multi-rank runs: the statistics gathered from this handle's documents pass through the caller's reducer (sum / max over
+// the ranks) before they are used, so every rank derives the same hyper-parameters (mvtm_set_stat_reducer).
+static int reduce_stats(mvtm_handle *h, int op, long long *ints, long long n_ints, double *reals, long long n_reals)
 {
-    int ml = 0;
-    if (int rc = mvtm_doc_topic_hist(h, m, nullptr, &ml)) return rc;
+    if (!h->reducer) return MVTM_OK;
+    if (h->reducer(h->reducer_ctx, op, (int64_t *)ints, n_ints, reals, n_reals) != 0)
+        FAIL(h, MVTM_ERR_STATE, "mvtm_optimize_hyper: the statistics reducer reported a failure");
+    return MVTM_OK;
+}
+static int global_max_len(mvtm_handle *h, int m, int &ml)
+{
+    long long v = h->v[m].max_len;
+    if (int rc = reduce_stats(h, 1, &v, 1, nullptr, 0)) return rc;
+    ml = (int)v;
+    return MVTM_OK;
+}
+
+// topicDocCounts of view m over ALL ranks' documents: K x (global max length + 1)
+static int doc_topic_hist_host(mvtm_handle *h, int m, std::vector<long long> &hist, int &stride)
+{
+    int ml_local = 0, ml = 0;
+    if (int rc = mvtm_doc_topic_hist(h, m, nullptr, &ml_local)) return rc;
+    if (int rc = global_max_len(h, m, ml)) return rc;
+    const int ls = ml_local + 1;
+    std::vector<int> local((size_t)h->K * ls, 0);
+    if (int rc = mvtm_doc_topic_hist(h, m, local.data(), &ml_local)) return rc;
     stride = ml + 1;
     hist.assign((size_t)h->K * stride, 0);
-    return mvtm_doc_topic_hist(h, m, hist.data(), &ml);
+    for (int t = 0; t < h->K; t++)
+        for (int i = 1; i < ls; i++) hist[(size_t)t * stride + i] = local[(size_t)t * ls + i];      // bins c >= 1 (bin 0 is never read, M:2461)
+    return reduce_stats(h, 0, hist.data(), (long long)hist.size(), nullptr, 0);
 }
 
 extern "C" int mvtm_p_statistics(mvtm_handle *h, double *psum_out, int64_t *docs_per_view_out)
@@ -225,11 +249,14 @@ static int optimize_p(mvtm_handle *h)
 {   // M:2698-2819
     const int M = h->M;
     std::vector<double> psum((size_t)M * M);
+    std::vector<long long> docs((size_t)M);
     if (int rc = mvtm_p_statistics(h, psum.data(), nullptr)) return rc;
+    for (int m = 0; m < M; m++) docs[(size_t)m] = h->v[m].docs_present;
+    if (int rc = reduce_stats(h, 0, docs.data(), M, psum.data(), (long long)M * M)) return rc;
     for (int m = 0; m < M; m++) {
         h->pMean[m][m] = 1.0;
         for (int i = m + 1; i < M; i++) {
-            const double denom = (double)std::min(h->v[m].docs_present, h->v[i].docs_present);
+            const double denom = (double)std::min(docs[(size_t)m], docs[(size_t)i]);
             const double mean = psum[(size_t)m * M + i] / denom;                            // M:2793
             h->pMean[m][i] = h->pMean[i][m] = mean;
             const double a = (mean == 1.0) ? 5000.0 : -1.0 / std::log(mean);                // M:2797
@@ -246,13 +273,13 @@ static int optimize_dp(mvtm_handle *h, OptRng &g)
     std::vector<std::vector<double>> mk((size_t)M, std::vector<double>((size_t)K + 1, 0.0));
     std::vector<double> mk_root((size_t)K + 1, 0.0);
     std::vector<char> active((size_t)K, 0);
-    std::vector<int> hist; int stride = 0;
+    std::vector<long long> hist; int stride = 0;
     for (int m = 0; m < M; m++) {
         if (int rc = doc_topic_hist_host(h, m, hist, stride)) return rc;
         for (int t = 0; t < K; t++) {
             const double ga = h->gamma[m] * h->alpha[(size_t)m * (K + 1) + t];
             for (int i = 1; i < stride; i++) {
-                const int cnt = hist[(size_t)t * stride + i];
+                const long long cnt = hist[(size_t)t * stride + i];
                 if (cnt <= 0) continue;
                 active[(size_t)t] = 1;
                 if (i > 1) {
@@ -304,11 +331,14 @@ static int optimize_gamma(mvtm_handle *h, OptRng &g)
     }
     for (int m = 0; m < h->M; m++) {
         ViewDev &v = h->v[m];
-        std::vector<long long> lencnt((size_t)v.max_len + 1, 0);                          // docLengthCounts, M:626
+        int gml = 0;
+        if (int rc = global_max_len(h, m, gml)) return rc;
+        std::vector<long long> lencnt((size_t)gml + 1, 0);                                // docLengthCounts, M:626 (all ranks)
         for (long long d = 0; d < h->D; d++) {
             const long long len = v.h_doc_off[(size_t)d + 1] - v.h_doc_off[(size_t)d];
             if (len > 0 || v.h_present[(size_t)d]) lencnt[(size_t)len]++;
         }
+        if (int rc = reduce_stats(h, 0, lencnt.data(), (long long)lencnt.size(), nullptr, 0)) return rc;
         for (int r = 0; r < R; r++) {
             const double prev = h->gamma[m];
             const double eta = rand_beta(g, h->gammaView[m] + 1, h->tablesCnt[m]);
@@ -360,6 +390,13 @@ static int optimize_beta(mvtm_handle *h)
             else { h->betaSum[m] = prevBetaSum; h->beta[m] = prevBetaSum / v.V; }
         } else { h->betaSum[m] = bs; h->beta[m] = bs / v.V; }
     }
+    return MVTM_OK;
+}
+
+extern "C" int mvtm_set_stat_reducer(mvtm_handle *h, mvtm_stat_reducer fn, void *ctx)
+{
+    if (!h) return MVTM_ERR_ARG;
+    h->reducer = fn; h->reducer_ctx = ctx;
     return MVTM_OK;
 }
 

@@ -17,6 +17,26 @@ def shard_doc_ids(num_docs, rank, world):
     return rank, world, len(range(rank, num_docs, world))
 
 
+def make_stat_reducer(group=None, device=None):
+    """The callback mvtm_set_stat_reducer expects, over torch.distributed: all-reduce (sum / max) of the optimiser's host-side
+    statistics, in place.  `device`: stage through that CUDA device (NCCL groups cannot reduce host tensors); None for gloo."""
+    def fn(op, ints, reals):
+        import torch
+        import torch.distributed as dist
+        rop = dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX
+        for arr in (ints, reals):
+            if arr is None:
+                continue
+            t = torch.from_numpy(arr)
+            if device is None:
+                dist.all_reduce(t, op=rop, group=group)
+            else:
+                g = t.to(device)
+                dist.all_reduce(g, op=rop, group=group)
+                t.copy_(g.cpu())
+    return fn
+
+
 class _DevBuf:
     """Wraps a raw device pointer for torch.as_tensor via __cuda_array_interface__ (no copy)."""
 
@@ -169,3 +189,79 @@ class CountExchange:
             self.a.delta_import(m)
         self.bytes_per_exchange = total
         return total
+
+
+class ShardedTrainer:
+    """One rank of a multi-GPU `estimate()` (M:1146-1239): this rank's shard of the documents (strided: rank, rank+world, ...),
+    replicated count tables exchanged after every sweep (overlapped with sampling for multi-view corpora when `overlap`),
+    the hyper-parameter step on statistics reduced over all ranks (mvtm_set_stat_reducer), the log-likelihood summed over ranks.
+    Every rank ends each iteration with identical counts and hyper-parameters.
+
+    `views` are the shard's views (corpus.shard_views); `group` / `narrow_group`: process groups for the exchanges (the narrow one
+    is the CTA-limited communicator of the hidden views, see OverlappedSweep); `stage_device`: CUDA device to stage host
+    statistics through when the group is NCCL (None for gloo)."""
+
+    def __init__(self, K, Vs, views, rank, world, device=0, seed=1, group=None, narrow_group=None, overlap=False, reserve_sms=8,
+                 stage_device=None, max_ctas=0, warps_per_cta=0):
+        import torch
+        import torch.distributed as dist
+        from .engine import Engine
+        self.K, self.M, self.rank, self.world, self.dist, self.group, self.torch = K, len(views), rank, world, dist, group, torch
+        self.device = device
+        n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+        self.overlap = bool(overlap and self.M > 1 and world > 1)
+        if self.overlap:
+            max_ctas = min(max_ctas, n_sms - reserve_sms) if max_ctas else n_sms - reserve_sms
+        self.engine = e = Engine(K, Vs, views, seed=seed, device=device, doc_id_base=rank, doc_id_stride=world,
+                                 max_ctas=max_ctas, warps_per_cta=warps_per_cta)
+        e.set_stat_reducer(make_stat_reducer(group, stage_device) if world > 1 else None)
+        self.xch = CountExchange(EngineAdapter(e, device), group)
+        self.xch.reset()
+        e.init_assignments()                       # M:465-515 on the global document ids: draws what the unsharded run draws
+        self.xch.exchange()                        # local counts -> global counts
+        self.ovl = None
+        if self.overlap:
+            critical = int(np.argmax(e.ntok))
+            vg = {m: narrow_group for m in range(self.M) if m != critical} if narrow_group is not None else None
+            self._ovl_adapter = OverlapAdapter(e, device)
+            self.ovl = OverlappedSweep(self._ovl_adapter, group, view_groups=vg)
+        self.burninPeriod, self.optimizeInterval = 200, 50
+        self.ll_series = []
+
+    def sweep(self, iteration):
+        if self.ovl:
+            self.ovl.step(iteration)
+        else:
+            self.engine.sweep(iteration)
+            self.xch.exchange_sum()
+
+    def drain(self):
+        if self.ovl:
+            self._ovl_adapter.drain()
+
+    def global_loglik(self, quirk_len2=False):
+        """modelLogLikelihood (M:3322-3452) of the whole corpus: document parts summed over ranks + the topic-word part."""
+        self.drain()
+        doc, word = self.engine.loglik_parts(quirk_len2)
+        t = self.torch.from_numpy(doc.copy())
+        dev = self.torch.device("cuda", self.device) if self.dist.get_backend(self.group) == "nccl" else None
+        if dev is not None:
+            g = t.to(dev); self.dist.all_reduce(g, group=self.group); t = g.cpu()
+        else:
+            self.dist.all_reduce(t, group=self.group)
+        return t.numpy() + word
+
+    def estimate(self, numIterations, burninPeriod=200, optimizeInterval=50, ll_every=10):
+        e = self.engine
+        M = self.M
+        e.set_hyper(p_a=np.full((M, M), 0.2), p_b=np.ones((M, M)))                                    # M:1055-1058
+        for iteration in range(1, numIterations + 1):
+            if iteration < burninPeriod and M > 1:
+                e.set_hyper(p_a=np.full((M, M), min(iteration / 100.0 + 0.3, 1.1)))                  # M:1166-1169
+            elif iteration > burninPeriod and optimizeInterval != 0 and iteration % optimizeInterval == 0:
+                self.drain()
+                e.optimize_hyper(iteration)                                                          # M:1173-1210, global statistics
+            self.sweep(iteration)
+            if ll_every and iteration % ll_every == 0:
+                self.ll_series.append((iteration, self.global_loglik()))
+        self.drain()

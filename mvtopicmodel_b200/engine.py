@@ -114,6 +114,27 @@ class Engine:
     def optimize_hyper(self, iteration, which=15):
         self._ck(self.L.mvtm_optimize_hyper(self.h, int(iteration), int(which)))
 
+    def set_stat_reducer(self, fn):
+        """fn(op, ints, reals): op 0 = sum, 1 = max over the ranks, IN PLACE on the two numpy views (either may be None);
+        None removes the reducer.  Used by the multi-rank hyper-parameter step (mvtm_set_stat_reducer)."""
+        if fn is None:
+            self._reducer = None
+            self._ck(self.L.mvtm_set_stat_reducer(self.h, C.cast(None, _lib.STAT_REDUCER), None))
+            return
+
+        def trampoline(ctx, op, ints, n_ints, reals, n_reals):
+            try:
+                a = np.ctypeslib.as_array(ints, shape=(n_ints,)) if n_ints else None
+                b = np.ctypeslib.as_array(reals, shape=(n_reals,)) if n_reals else None
+                fn(int(op), a, b)
+                return 0
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._reducer = _lib.STAT_REDUCER(trampoline)      # keep the callback object alive
+        self._ck(self.L.mvtm_set_stat_reducer(self.h, self._reducer, None))
+
     def p_statistics(self):
         psum = np.empty((self.M, self.M), dtype=np.float64)
         docs = np.empty(self.M, dtype=np.int64)
@@ -176,6 +197,12 @@ class Engine:
         ll, n = C.c_double(), C.c_int64()
         self._ck(self.L.mvtm_heldout_loglik(self.h, int(m), _ptr(eo), _ptr(ew), C.byref(ll), C.byref(n)))
         return ll.value, n.value
+
+    def loglik_parts(self, quirk_len2=False):
+        """(document part over this handle's documents, topic-word part of the count tables), each M doubles."""
+        doc, word = np.empty(self.M, dtype=np.float64), np.empty(self.M, dtype=np.float64)
+        self._ck(self.L.mvtm_loglik_parts(self.h, _ptr(doc), _ptr(word), int(quirk_len2)))
+        return doc, word
 
     def doc_topic_hist(self, m):
         ml = C.c_int32()
