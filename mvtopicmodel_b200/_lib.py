@@ -67,6 +67,7 @@ SIGNATURES = {
     "mvtm_sum_exchange_finish_async": (_i32, [_vp, _i32, _i32, _vp, _i32]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),
+    "mvtm_activate_topics": (_i32, [_vp]),
     "mvtm_set_stat_reducer": (_i32, [_vp, STAT_REDUCER, _vp]),
     "mvtm_p_statistics": (_i32, [_vp, _vp, _vp]),
     "mvtm_get_hyper_full": (_i32, [_vp] + [_vp] * 11),

@@ -686,8 +686,19 @@ static int close_sweep(mvtm_handle *h, int update_global)
         if (h->v[m].n_items > 0) ring_record(h, m, ms);
     }
     h->stats.kernel_launches = h->open_launches;
-    if (update_global == 1) if (int rc = activate_sampled_topics(h)) return rc;
+    // multi-rank runs (a statistics reducer is installed) activate on the GLOBAL counts after the exchange: mvtm_activate_topics
+    if (update_global == 1 && !h->reducer) if (int rc = activate_sampled_topics(h)) return rc;
     return MVTM_OK;
+}
+
+extern "C" int mvtm_activate_topics(mvtm_handle *h)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (h->inactive.empty()) return MVTM_OK;
+    CK(h, cudaSetDevice(h->device));
+    if (int rc = wait_all_ready(h)) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return activate_sampled_topics(h);
 }
 
 static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool sync_stats)

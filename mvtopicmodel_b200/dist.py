@@ -230,10 +230,12 @@ class ShardedTrainer:
 
     def sweep(self, iteration):
         if self.ovl:
-            self.ovl.step(iteration)
+            self.engine.activate_topics()          # on the global counts of the previous sweep (waits for its exchanges; no-op
+            self.ovl.step(iteration)               #   unless optimizeDP left inactive topics)
         else:
             self.engine.sweep(iteration)
             self.xch.exchange_sum()
+            self.engine.activate_topics()          # U:263-270 on the global counts: every rank takes the same decision
 
     def drain(self):
         if self.ovl:

@@ -114,6 +114,9 @@ class Engine:
     def optimize_hyper(self, iteration, which=15):
         self._ck(self.L.mvtm_optimize_hyper(self.h, int(iteration), int(which)))
 
+    def activate_topics(self):
+        self._ck(self.L.mvtm_activate_topics(self.h))
+
     def set_stat_reducer(self, fn):
         """fn(op, ints, reals): op 0 = sum, 1 = max over the ranks, IN PLACE on the two numpy views (either may be None);
         None removes the reducer.  Used by the multi-rank hyper-parameter step (mvtm_set_stat_reducer)."""
