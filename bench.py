@@ -339,9 +339,13 @@ def main():
                              int((8 * ntok_local + 4 * sum(Vs) * eng.row_stride()) / 1e6),
                        "changed_frac": changed / max(1, ntok_local * args.steps), "invariant_violations": viol},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": traffic, "kernel": "k_sweep_view", "bytes_per_token": btok, "tokens_per_launch": ntok_local,
                          "avg_launch_ms": kern_ms_max / args.steps / M, "peak_source": peak_src},
-            "e2e": e2e, "gpu_launches": args.steps * M, "clocks": clocks}
+            "e2e": e2e, "clocks": clocks,
+            # my kernels inside the timed region: one k_sweep_view per view and step, plus the exchange's finishing passes
+            # (serial form: table and totals separately, overlapped form: one fused pass per view)
+            "gpu_launches": args.steps * M * (1 + (0 if not xch else (1 if ovl else 2)))}
     if xch:
         line["config"]["allreduce_bytes_per_sweep"] = ovl.bytes_per_exchange if ovl else xch.bytes_per_exchange
         line["config"]["exchange"] = (f"overlapped: view m's all-reduce under the following passes, sweep grid {n_sms - args.reserve_sms} CTAs, "
