@@ -5,10 +5,12 @@
  * checker for the CUDA engine (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl
  * reference legs).  Nothing under mvtopicmodel_b200/ may link, import or execute this file.
  *
- * PARITY STATUS: "parity unpinned" against the Java reference itself: the reference ships no tests,
- * no golden vectors and cannot run here (no JVM in this image).  The pins that
- * exist are the hand-derived known-answer vectors of SURVEY.md section 8(c) (FTree {1,2,3,4},
- * lower_bound, logGammaStirling, the histogram rule) which tests/test_oracle.py checks.
+ * PARITY STATUS: "parity unpinned" for the per-document sampler: the reference ships no tests, no
+ * golden vectors and its trainer cannot run here (no JVM in this image).
+ * Pinned BY EXECUTION of the reference's own jars (tools/jvm_mini.py, a bytecode interpreter; vectors in
+ * tests/golden/reference_vectors.json, checked by tests/test_reference_vectors.py): the F+tree
+ * (build / sample / update), lower_bound and MALLET's logGammaStirling -- bit for bit.  The rest
+ * rests on the hand-derived known answers of SURVEY.md section 8(c), which tests/test_oracle.py checks.
  *
  * Reference citations use these tags (all under /root/reference/src/main/java/org/madgik/):
  *   W  = MVTopicModel/FastQMVWVWorkerRunnable.java

@@ -47,14 +47,25 @@ def p_params(psum, docs_per_view):
     return pa, pmean
 
 
+def _jdiv(a, b):
+    """IEEE-754 division as the JVM performs it (x/0 = +-Infinity, 0/0 = NaN) -- Python raises instead."""
+    if b == 0.0:
+        if a == 0.0 or a != a:
+            return math.nan
+        return math.copysign(math.inf, a) * math.copysign(1.0, b)
+    return a / b
+
+
 def mallet_digamma(z):
+    if z != z:
+        return math.nan
     if z < 1e-6:
-        return -0.5772156649015329 - 1.0 / z
+        return -0.5772156649015329 - _jdiv(1.0, z)
     acc = 0.0
     while z < 9.5:
-        acc -= 1.0 / z
+        acc -= _jdiv(1.0, z)
         z += 1.0
-    return acc + math.log(z) - 1.0 / (2.0 * z)
+    return acc + (math.log(z) if z > 0 and z != math.inf else (math.inf if z == math.inf else math.nan)) - _jdiv(1.0, 2.0 * z)
 
 
 def learn_symmetric_concentration(count_hist, length_hist, num_dims, current):
@@ -64,7 +75,7 @@ def learn_symmetric_concentration(count_hist, length_hist, num_dims, current):
         param = current / num_dims
         dg, num = 0.0, 0.0
         for idx in range(1, largest + 1):
-            dg += 1.0 / (param + idx - 1)
+            dg += _jdiv(1.0, param + idx - 1)
             num += count_hist[idx] * dg
         dg, den = 0.0, 0.0
         cached = mallet_digamma(current)
@@ -73,9 +84,9 @@ def learn_symmetric_concentration(count_hist, length_hist, num_dims, current):
                 dg = mallet_digamma(current + length) - cached
             else:
                 for idx in range(0, length):
-                    dg += 1.0 / (current + idx)
+                    dg += _jdiv(1.0, current + idx)
             den += dg * length_hist[length]
-        current = param * num / den
+        current = _jdiv(param * num, den)
     return current
 
 

@@ -1,0 +1,58 @@
+"""Pins against outputs of THE REFERENCE'S OWN BINARIES (tests/golden/reference_vectors.json, produced by executing the bytecode
+of output/MVTopicModel-1.0-SNAPSHOT.jar and output/lib/mallet-2.0.8.jar with tools/jvm_mini.py -- there is no JVM in this image):
+the C oracle's F+tree and lower_bound, the Stirling log-gamma used by the log-likelihood, MALLET's digamma and
+learnSymmetricConcentration as restated in oracle/optim.py AND in the product's host code (libmvtm.so)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+
+
+def test_ftree_matches_reference_bytecode(oracle_mod):
+    """org.madgik.utils.FTree (FT:96-147): constructor, sample(u), update(t, v) -- tree arrays bit for bit, every draw identical."""
+    O = oracle_mod
+    for rec in GOLD["ftree"]:
+        K = rec["K"]
+        tree = O.ftree_build(rec["weights"])
+        assert np.array_equal(tree[1:], np.array(rec["tree"])[1:]), K          # slot 0 is unused by both
+        for u, want in rec["samples"]:
+            assert O.ftree_sample(tree, u) == want, (K, u)
+        for up in rec["updates"]:
+            O.ftree_update(tree, up["topic"], up["value"])
+            assert np.array_equal(tree[1:], np.array(up["tree"])[1:]), (K, up["topic"])
+            for u, want in up["samples"]:
+                assert O.ftree_sample(tree, u) == want, (K, u)
+
+
+def test_lower_bound_matches_reference_bytecode(oracle_mod):
+    """FastQMVWVWorkerRunnable.lower_bound (W:257-277; the prebuilt jar's older build takes int[]: same search)."""
+    for rec in GOLD["lower_bound"]:
+        assert oracle_mod.lower_bound([float(x) for x in rec["arr"]], rec["key"], rec["n"]) == rec["result"], rec
+
+
+def test_log_gamma_stirling_matches_mallet_bytecode(oracle_mod, engine_lib):
+    """cc.mallet.types.Dirichlet.logGammaStirling, the lgamma of modelLogLikelihood (M:3343 ...)."""
+    for z, want in GOLD["logGammaStirling"]:
+        got = oracle_mod.log_gamma_stirling(z)
+        assert got == pytest.approx(want, rel=1e-15, abs=1e-300), (z, got, want)
+
+
+def test_digamma_and_concentration_match_mallet_bytecode(engine_lib):
+    """cc.mallet.types.Dirichlet.digamma (the Bernoulli-free series of Q19) and learnSymmetricConcentration (optimizeBeta,
+    M:2327): the numpy restatement and the PRODUCT's host implementation against the jar's own results."""
+    from oracle import optim
+    for z, want in GOLD["digamma"]:
+        assert optim.mallet_digamma(z) == pytest.approx(want, rel=1e-14), z
+    f = engine_lib.mvtm_test_learn_symmetric_concentration
+    for rec in GOLD["learnSymmetricConcentration"]:
+        ch = np.asarray(rec["countHistogram"], dtype=np.int64); sh = np.asarray(rec["topicSizeHistogram"], dtype=np.int64)
+        want = rec["result"]
+        got_np = optim.learn_symmetric_concentration(ch.tolist(), sh.tolist(), rec["numDimensions"], rec["currentValue"])
+        got_lib = f(ch.ctypes.data_as(C.c_void_p), len(ch), sh.ctypes.data_as(C.c_void_p), len(sh), rec["numDimensions"], rec["currentValue"])
+        # half of the cases end in NaN -- the outcome optimizeBeta's `Double.isNaN(betaSum)` branch exists for (M:2340-2344)
+        assert got_np == pytest.approx(want, rel=1e-12, nan_ok=True), rec["numDimensions"]
+        assert got_lib == pytest.approx(want, rel=1e-12, nan_ok=True), rec["numDimensions"]
