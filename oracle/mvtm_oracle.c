@@ -5,12 +5,16 @@
  * checker for the CUDA engine (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl
  * reference legs).  Nothing under mvtopicmodel_b200/ may link, import or execute this file.
  *
- * PARITY STATUS: "parity unpinned" for the per-document sampler: the reference ships no tests, no
- * golden vectors and its trainer cannot run here (no JVM in this image).
- * Pinned BY EXECUTION of the reference's own jars (tools/jvm_mini.py, a bytecode interpreter; vectors in
- * tests/golden/reference_vectors.json, checked by tests/test_reference_vectors.py): the F+tree
- * (build / sample / update), lower_bound and MALLET's logGammaStirling -- bit for bit.  The rest
- * rests on the hand-derived known answers of SURVEY.md section 8(c), which tests/test_oracle.py checks.
+ * PARITY STATUS: pinned to outputs of the reference's own binaries.  The reference ships no tests or golden
+ * vectors and its trainer cannot be launched here (no JVM in this image), but
+ * tools/jvm_mini.py -- a JVM bytecode interpreter -- EXECUTES the reference's classes from the jars it ships:
+ *   - FastQMVWVWorkerRunnable.sampleTopicsForOneDoc (the sampler, W:301-597) on five corpora; this file's
+ *     reference-faithful mode reproduces its assignments token for token, sweep after sweep
+ *     (tests/golden/reference_sampler_vectors.json, tests/test_reference_vectors.py);
+ *   - FTree (build / sample / update), lower_bound, MALLET's logGammaStirling -- bit for bit
+ *     (tests/golden/reference_vectors.json).
+ * Not executed: the trainer's outer loop, modelLogLikelihood and the optimisers as a whole; those rest on
+ * the citations below and the hand-derived known answers of SURVEY.md section 8(c) (tests/test_oracle.py).
  *
  * Reference citations use these tags (all under /root/reference/src/main/java/org/madgik/):
  *   W  = MVTopicModel/FastQMVWVWorkerRunnable.java

@@ -1,0 +1,228 @@
+"""Golden vectors of the SAMPLER produced by the reference's own binary: FastQMVWVWorkerRunnable.sampleTopicsForOneDoc from
+output/MVTopicModel-1.0-SNAPSHOT.jar (a prebuilt, slightly older build of W:301-597 -- same statements, one shared queue, int[][]
+tokensPerTopic) is EXECUTED by tools/jvm_mini.py document after document, sweep after sweep, on small corpora.
+
+What is real and what is shimmed
+  executed from the jar : the whole per-document sampler (view-coupling matrix, local counts, dense topic index and its in-sweep
+                          maintenance incl. the dead insertion code Q1, other-view mass, new-topic mass, per-token masses, bucket
+                          choice, lower_bound, FTree.sample), FastQDelta, FTree (construction, sample, update)
+  shimmed (host Python) : the containers the sampler reads (ArrayList, MALLET Instance / FeatureSequence / LabelSequence) as thin
+                          views over the same arrays; ThreadLocalRandom.nextDouble and Randoms.nextBeta, which return the uniforms
+                          the ORACLE draws for the same (token position, document, iteration, view) -- Philox4x32-10, 24-bit, see
+                          oracle/mvtm_oracle.c orc_draw -- so that both consume identical randomness (the reference's own RNG is
+                          unseedable, Q9); Queue.add, which applies the delta at once the way FastQMVWVUpdaterRunnable does
+                          (U:197-260: counts, totals, the two tree leaves via the jar's FTree.update)
+
+Output: tests/golden/reference_sampler_vectors.json -- corpus, hyper-parameters, initial assignments, and the assignments after
+every sweep.  tests/test_reference_vectors.py replays them through the C oracle (reference-faithful mode) and demands equality
+token for token.  Needs /root/reference (build container only).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import jvm_mini  # noqa: E402
+from jvm_mini import JObject  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+REF = "/root/reference/output"
+W = "org/madgik/MVTopicModel/FastQMVWVWorkerRunnable"
+FT = "org/madgik/utils/FTree"
+PURPOSE_SAMPLE, PURPOSE_PDRAW = 0, 2
+
+
+def u24(x):
+    return float(int(x) >> 8) * (1.0 / 16777216.0)
+
+
+class RefSampler:
+    """One model state driven through the jar's sampler."""
+
+    def __init__(self, K, Vs, views, z0, seed, alpha, alphaSum, beta, gamma, p_a, p_b, inactive=()):
+        self.vm = vm = jvm_mini.MiniJVM([os.path.join(REF, "lib", "mallet-2.0.8.jar"), os.path.join(REF, "MVTopicModel-1.0-SNAPSHOT.jar")])
+        self.K, self.M, self.Vs, self.views, self.seed = K, len(Vs), Vs, views, seed
+        M = self.M
+        self.D = len(views[0][0]) - 1
+        self.z = [[int(t) for t in z0[m]] for m in range(M)]
+        # counts from the assignments (M:600-652)
+        self.nwk = [[[0] * K for _ in range(Vs[m])] for m in range(M)]
+        self.nk = [[0] * K for _ in range(M)]
+        for m in range(M):
+            for w, t in zip(views[m][1], self.z[m]):
+                if t >= 0 and 0 <= w < Vs[m]:
+                    self.nwk[m][int(w)][t] += 1
+                    self.nk[m][t] += 1
+        self.alpha = [list(map(float, a)) for a in alpha]
+        self.alphaSum, self.beta, self.gamma = list(map(float, alphaSum)), list(map(float, beta)), list(map(float, gamma))
+        self.betaSum = [self.beta[m] * Vs[m] for m in range(M)]
+        self.inactive = list(inactive)
+        # F+trees (M:2660-2696) built by the jar's FTree constructor
+        self.trees = []
+        for m in range(M):
+            row = []
+            for w in range(Vs[m]):
+                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(K)]
+                row.append(vm.new(FT, "([D)V", [leaves]))
+            self.trees.append(row)
+        # per-document containers: data.get(d).Assignments[m] = {instance -> FeatureSequence shim, topicSequence -> LabelSequence shim}
+        self.docs = []
+        for d in range(self.D):
+            ent = JObject("org/madgik/utils/MixTopicModelTopicAssignment")
+            arr = []
+            for m in range(M):
+                b, e = int(views[m][0][d]), int(views[m][0][d + 1])
+                if e == b and m > 0:
+                    arr.append(None)                       # the document lacks this view (MA:13-19)
+                    continue
+                ta = JObject("cc/mallet/topics/TopicAssignment")
+                zslice = self.z[m][b:e]                    # LabelSequence.getFeatures(): a LIVE array the sampler writes into
+                ta.fields["topicSequence"] = ("labels", m, b, zslice)
+                ta.fields["instance"] = ("instance", [int(x) for x in views[m][1][b:e]])
+                arr.append(ta)
+            ent.fields["Assignments"] = arr
+            self.docs.append(ent)
+        wk = JObject(W)
+        wk.fields.update(dict(data=("arraylist", self.docs), numModalities=M, numTopics=K, alpha=self.alpha, alphaSum=self.alphaSum,
+                              beta=self.beta, betaSum=self.betaSum, gamma=self.gamma, p_a=[list(map(float, r)) for r in p_a],
+                              p_b=[list(map(float, r)) for r in p_b], typeTopicCounts=self.nwk, tokensPerTopic=self.nk, trees=self.trees,
+                              random=("randoms",), queue=("queue",), inActiveTopicIndex=("inactive",), useTypeVectors=0,
+                              useTypeVectorsProb=0.0, typeTopicSimilarity=None, threadId=0))
+        self.worker = wk
+        self.iteration, self.doc = 0, 0
+        self.counters = {"new": 0, "doc": 0, "tree": 0, "tree_bucket": 0, "deltas": 0, "beta_draws": 0}
+        sh = vm.shims
+        sh["java/util/ArrayList.get:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: r[1][a[0]]
+        sh["cc/mallet/types/LabelSequence.getFeatures:()[I"] = lambda loc, r, a, pc: r[3]
+        sh["cc/mallet/types/Instance.getData:()Ljava/lang/Object;"] = lambda loc, r, a, pc: ("fs", r[1])
+        sh["cc/mallet/types/FeatureSequence.getLength:()I"] = lambda loc, r, a, pc: len(r[1])
+        sh["cc/mallet/types/FeatureSequence.getIndexAtPosition:(I)I"] = lambda loc, r, a, pc: r[1][a[0]]
+        sh["java/util/List.isEmpty:()Z"] = lambda loc, r, a, pc: int(len(self.inactive) == 0)
+        sh["java/util/List.get:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: self.inactive[a[0]]
+        sh["java/lang/Integer.intValue:()I"] = lambda loc, r, a, pc: r
+        sh["java/util/concurrent/ThreadLocalRandom.current:()Ljava/util/concurrent/ThreadLocalRandom;"] = lambda loc, r, a, pc: ("tlr",)
+        sh["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"] = self.next_double
+        sh["cc/mallet/util/Randoms.nextBeta:(DD)D"] = self.next_beta
+        def count_bucket(loc, r, a, pc):       # newMassCnt / topicDocMassCnt / wordFTreeMassCnt by call site (W:523, W:530, W:533)
+            self.counters[{1257: "new", 1326: "doc", 1350: "tree_bucket"}[pc]] += 1
+            return 0
+        sh["java/util/concurrent/atomic/AtomicInteger.getAndIncrement:()I"] = count_bucket
+        sh["java/util/Queue.add:(Ljava/lang/Object;)Z"] = self.apply_delta
+        for d in ("(Ljava/lang/String;)Ljava/lang/StringBuilder;", "(D)Ljava/lang/StringBuilder;", "(I)Ljava/lang/StringBuilder;"):
+            sh["java/lang/StringBuilder.append:" + d] = lambda loc, r, a, pc: r
+        sh["java/lang/StringBuilder.toString:()Ljava/lang/String;"] = lambda loc, r, a, pc: ""
+        sh["java/io/PrintStream.println:(Ljava/lang/String;)V"] = lambda loc, r, a, pc: None
+
+        def boom(loc, r, a, pc):
+            raise RuntimeError("the reference's sampler threw inside sampleTopicsForOneDoc")
+        sh["java/lang/Exception.printStackTrace:()V"] = boom
+
+    def leaf(self, m, w, t):          # U:242-260 / M:2678: gamma * alpha * ((n_wk + beta) / (n_k + betaSum))
+        return self.gamma[m] * self.alpha[m][t] * ((self.nwk[m][w][t] + self.beta[m]) / (self.nk[m][t] + self.betaSum[m]))
+
+    # --- randomness: exactly the oracle's draws (oracle/mvtm_oracle.c: orc_draw, draw_p) ---------------------------------
+    def philox(self, pos, view_or_pair, purpose):
+        ctr = [pos, self.doc, self.iteration, (view_or_pair << 8) | purpose]
+        return O.philox(ctr, [self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF])
+
+    def next_double(self, loc, recv, args, pc):
+        m, pos = loc[20], loc[22]          # the sampler's view and position loop variables (bytecode locals 20 and 22)
+        x = self.philox(pos, m, PURPOSE_SAMPLE)
+        if pc == 1223:                     # u = ThreadLocalRandom.nextDouble() of W:517
+            return u24(x[0])
+        if pc == 1357:                     # u2 of W:534 (the F+tree bucket)
+            self.counters["tree"] += 1
+            return u24(x[1])
+        raise RuntimeError(f"unexpected nextDouble call site {pc}")
+
+    def next_beta(self, loc, recv, args, pc):
+        m, j = loc[18], loc[19]            # W:327-337 loop variables
+        self.counters["beta_draws"] += 1
+        x = self.philox(0, m * self.M + j, PURPOSE_PDRAW)
+        return u24(x[0]) ** (1.0 / args[0])            # Beta(a, 1) by inversion, the oracle's default law (Q5)
+
+    # --- FastQMVWVUpdaterRunnable's treatment of one delta (U:197-260), applied at once ----------------------------------
+    def apply_delta(self, loc, recv, args, pc):
+        d = args[0].fields
+        m, w, old, new = d["Modality"], d["Type"], d["OldTopic"], d["NewTopic"]
+        row = self.nwk[m][w]
+        if old != -1:
+            row[old] -= 1; self.nk[m][old] -= 1
+        row[new] += 1; self.nk[m][new] += 1
+        if old != -1:
+            self.vm.call(FT, "update", "(ID)V", [self.trees[m][w], old, self.leaf(m, w, old)])
+        self.vm.call(FT, "update", "(ID)V", [self.trees[m][w], new, self.leaf(m, w, new)])
+        if new in self.inactive:                                                                 # U:263-270
+            self.inactive.remove(new); self.alpha[m][new] = self.alpha[m][self.K]
+        self.counters["deltas"] += 1
+        return 1
+
+    def sweep(self, iteration):
+        self.iteration = iteration
+        for d in range(self.D):
+            self.doc = d
+            self.vm.call(W, "sampleTopicsForOneDoc", "(I)V", [self.worker, d])
+        # gather the live per-document arrays back into CSR order
+        for d, ent in enumerate(self.docs):
+            for m, ta in enumerate(ent.fields["Assignments"]):
+                if ta is not None:
+                    _, _, b, zs = ta.fields["topicSequence"]
+                    self.z[m][b:b + len(zs)] = zs
+        return [list(z) for z in self.z]
+
+
+def make_case(name, K, Vs, means, D, seed, sweeps, p_a=0.0, inactive=(), alpha_new=0.1, rng_seed=0, sparse_view=None, unassigned=0):
+    from helpers import random_corpus
+    views = random_corpus(rng_seed, D, K, Vs, means, empty_frac=0.1)
+    M = len(Vs)
+    o = O.Oracle(K, Vs, views, seed=seed)
+    o.init_assignments()
+    z0 = [o.get_assignments(m).tolist() for m in range(M)]
+    alpha = np.full((M, K + 1), 0.1); alpha[:, K] = alpha_new
+    alphaSum = np.full(M, 0.1 * K)
+    beta, gamma = np.full(M, 0.01), np.ones(M)
+    pa, pb = np.full((M, M), p_a), np.ones((M, M))
+    if inactive:
+        # topics without tokens only: move their tokens to topic 0 first
+        for m in range(M):
+            z0[m] = [0 if t in inactive else t for t in z0[m]]
+    if sparse_view is not None:
+        beta[sparse_view] = 0.0001                      # the "too sparse" sentinel of optimizeBeta (M:2332-2336): W:335-336 zero p
+    if unassigned:
+        for m in range(M):                              # UNASSIGNED_TOPIC tokens (W:434: no decrement, delta with OldTopic = -1)
+            for i in range(0, len(z0[m]), unassigned):
+                z0[m][i] = -1
+    ref = RefSampler(K, Vs, views, z0, seed, alpha, alphaSum, beta, gamma, pa, pb, inactive)
+    out = {"name": name, "K": K, "V": Vs, "seed": seed, "views": [{"off": v[0].tolist(), "word": v[1].tolist()} for v in views],
+           "z0": z0, "alpha": alpha.tolist(), "alphaSum": alphaSum.tolist(), "beta": beta.tolist(), "betaSum": ref.betaSum, "gamma": gamma.tolist(),
+           "p_a": pa.tolist(), "p_b": pb.tolist(), "inactive": list(inactive), "z_after": []}
+    for it in range(1, sweeps + 1):
+        out["z_after"].append(ref.sweep(it))
+    out["counters"] = dict(ref.counters)
+    out["nk_final"] = [list(r) for r in ref.nk]
+    print(name, "tokens", [len(z) for z in z0], "sweeps", sweeps, ref.counters, "bytecode steps", ref.vm.steps, flush=True)
+    return out
+
+
+def main():
+    cases = [
+        make_case("single_view", K=8, Vs=[30], means=[7], D=40, seed=11, sweeps=3, rng_seed=1),
+        make_case("two_views_coupled", K=10, Vs=[40, 12], means=[8, 3], D=30, seed=12, sweeps=3, p_a=0.7, rng_seed=2),
+        make_case("three_views_inactive_topics", K=12, Vs=[30, 10, 8], means=[7, 3, 2], D=25, seed=13, sweeps=2, p_a=1.3,
+                  inactive=(4, 9), alpha_new=6.0, rng_seed=3),
+        make_case("sparse_sentinel_and_unassigned", K=9, Vs=[25, 10, 6], means=[6, 3, 2], D=25, seed=14, sweeps=2, p_a=0.9,
+                  sparse_view=1, unassigned=7, rng_seed=4),
+        make_case("k37_longer_docs", K=37, Vs=[120, 30], means=[25, 5], D=20, seed=15, sweeps=2, p_a=0.4, rng_seed=5),
+    ]
+    json.dump({"source": "output/MVTopicModel-1.0-SNAPSHOT.jar FastQMVWVWorkerRunnable.sampleTopicsForOneDoc executed by tools/jvm_mini.py",
+               "cases": cases}, open(os.path.join(HERE, "reference_sampler_vectors.json"), "w"))
+
+
+if __name__ == "__main__":
+    main()

@@ -56,3 +56,33 @@ def test_digamma_and_concentration_match_mallet_bytecode(engine_lib):
         # half of the cases end in NaN -- the outcome optimizeBeta's `Double.isNaN(betaSum)` branch exists for (M:2340-2344)
         assert got_np == pytest.approx(want, rel=1e-12, nan_ok=True), rec["numDimensions"]
         assert got_lib == pytest.approx(want, rel=1e-12, nan_ok=True), rec["numDimensions"]
+
+
+def test_sampler_matches_reference_bytecode(oracle_mod):
+    """THE SAMPLER against the reference's own binary: tests/golden/reference_sampler_vectors.json holds assignments produced by
+    executing FastQMVWVWorkerRunnable.sampleTopicsForOneDoc (W:301-597) from output/MVTopicModel-1.0-SNAPSHOT.jar, document by
+    document and sweep by sweep, with the uniforms the oracle draws for the same token (make_reference_sampler_vectors.py).  The C
+    oracle in reference-faithful mode (stale F+trees maintained per delta U:242-260, dead insertion code Q1, deltas applied at
+    once) must reproduce them TOKEN FOR TOKEN: single view; two coupled views (Beta-drawn p, other-view mass W:399-410); three
+    views with inactive topics (new-topic bucket W:413-418 / W:515, activation U:263-270)."""
+    O = oracle_mod
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
+    for case in gold["cases"]:
+        K, Vs = case["K"], case["V"]
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        o = O.Oracle(K, Vs, views, seed=case["seed"])
+        o.set_hyper(alpha=np.array(case["alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), p_a=np.array(case["p_a"]), p_b=np.array(case["p_b"]), inactive=case["inactive"])
+        o.set_assignments([np.array(z, dtype=np.int32) for z in case["z0"]])
+        o.rebuild_trees()
+        total = mism = 0
+        for it, want in enumerate(case["z_after"], start=1):
+            o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT)
+            for m in range(len(Vs)):
+                got = o.get_assignments(m)
+                w = np.array(want[m], dtype=np.int32)
+                total += len(w); mism += int((got != w).sum())
+                assert np.array_equal(got, w), (case["name"], "sweep", it, "view", m, "first mismatch at", int(np.argmax(got != w)))
+        for m in range(len(Vs)):
+            assert o.get_counts(m)[1].tolist() == case["nk_final"][m], case["name"]
+        assert total > 0 and mism == 0

@@ -103,6 +103,11 @@ class MiniJVM:
         self.zips = [zipfile.ZipFile(j) for j in jars]
         self.classes, self.statics, self.inited = {}, {}, set()
         self.steps = 0
+        # host shims for library classes: "class.method:descriptor" -> f(frame_locals, receiver, args, call_site_pc).  They see
+        # the calling frame's locals, so a shim can e.g. key a random draw on the loop variables of the method that asked for it
+        self.shims = {}
+        # debugging aid: {(len(code), pc): f(frame_locals, operand_stack)} called before the instruction at pc executes
+        self.probes = {}
 
     def load(self, name):
         if name not in self.classes:
@@ -181,8 +186,11 @@ class MiniJVM:
             c = cp[i]
             nat = cp[c[2]]
             return cf.cname(c[1]), cf.utf(nat[1]), cf.utf(nat[2])
+        ncode = len(code)
         while True:
             self.steps += 1
+            if self.probes and (ncode, pc) in self.probes:
+                self.probes[(ncode, pc)](loc, st)
             op = code[pc]
             if op == 0: pc += 1
             elif op == 1: st.append(None); pc += 1
@@ -277,7 +285,8 @@ class MiniJVM:
             elif op == 177: return None
             elif op == 178:
                 c, n, d = ref(u(">H", code, pc + 1)[0])
-                if c.startswith("java/") or n == "$assertionsDisabled": st.append(1 if n == "$assertionsDisabled" else None)
+                if n == "$assertionsDisabled": st.append(1)
+                elif c.startswith("java/"): st.append(JObject(c + "." + n))
                 else:
                     self.load(c); st.append(self.statics.get((c, n), 0.0 if d in "DF" else 0 if d in "IJSBCZ" else None))
                 pc += 3
@@ -294,7 +303,9 @@ class MiniJVM:
                 args = [st.pop() for _ in kinds][::-1]
                 recv = st.pop() if op != 184 else None
                 key = f"{c}.{n}:{d}"
-                if key in NATIVES:
+                if key in self.shims:
+                    r = self.shims[key](loc, recv, args, pc)
+                elif key in NATIVES:
                     r = NATIVES[key](*args)
                 elif c == "java/lang/Object" and n == "<init>":
                     r = None
@@ -325,6 +336,17 @@ class MiniJVM:
                 st.append([0.0] * n if t in (6, 7) else [0] * n); pc += 2
             elif op == 189:
                 n = st.pop(); st.append([None] * n); pc += 3
+            elif op == 197:
+                dims = code[pc + 3]
+                sizes = [st.pop() for _ in range(dims)][::-1]
+                desc = cf.cname(u(">H", code, pc + 1)[0])
+                leaf0 = 0.0 if desc.lstrip("[")[:1] in "DF" else (0 if desc.lstrip("[")[:1] in "IJSBCZ" else None)
+
+                def mk(level):
+                    if level == len(sizes) - 1:
+                        return [leaf0 if desc.count("[") == len(sizes) else None] * sizes[level]
+                    return [mk(level + 1) for _ in range(sizes[level])]
+                st.append(mk(0)); pc += 4
             elif op == 190:
                 a = st.pop()
                 if a is None: raise JavaThrow("java/lang/NullPointerException")
