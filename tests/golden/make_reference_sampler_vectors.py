@@ -123,6 +123,14 @@ class RefSampler:
             raise RuntimeError("the reference's sampler threw inside sampleTopicsForOneDoc")
         sh["java/lang/Exception.printStackTrace:()V"] = boom
 
+    def rebuild_trees(self):
+        """buildFTrees(false), M:2660-2696 (what estimate() does after every optimise step, M:1209): every leaf from the current
+        counts, 0 for topics in inActiveTopicIndex, through the jar's FTree.constructTree."""
+        for m in range(self.M):
+            for w in range(self.Vs[m]):
+                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(self.K)]
+                self.vm.call(FT, "constructTree", "([D)V", [self.trees[m][w], leaves])
+
     def leaf(self, m, w, t):          # U:242-260 / M:2678: gamma * alpha * ((n_wk + beta) / (n_k + betaSum))
         return self.gamma[m] * self.alpha[m][t] * ((self.nwk[m][w][t] + self.beta[m]) / (self.nk[m][t] + self.betaSum[m]))
 
@@ -177,6 +185,97 @@ class RefSampler:
         return [list(z) for z in self.z]
 
 
+MC = "org/madgik/MVTopicModel/FastQMVWVParallelTopicModel"
+
+
+def reference_loglik(ref):
+    """FastQMVWVParallelTopicModel.modelLogLikelihood (M:3322-3452) EXECUTED from the jar on the sampler's current state.  The
+    documents are presented the way MALLET holds them: a LabelSequence's backing array has capacity max(length, 2)
+    (FeatureSequence(Alphabet, int) allocates max(capacity, 2) ints), which is what quirk Q18 is about."""
+    vm, M, K = ref.vm, ref.M, ref.K
+    docs = []
+    for d in range(ref.D):
+        ent = JObject("org/madgik/utils/MixTopicModelTopicAssignment")
+        arr = []
+        for m in range(M):
+            b, e = int(ref.views[m][0][d]), int(ref.views[m][0][d + 1])
+            if e == b and m > 0:
+                arr.append(None)
+                continue
+            ta = JObject("cc/mallet/topics/TopicAssignment")
+            feats = list(ref.z[m][b:e])
+            ta.fields["topicSequence"] = ("labels", m, b, feats + [0] * (max(2, len(feats)) - len(feats)))
+            arr.append(ta)
+        ent.fields["Assignments"] = arr
+        docs.append(ent)
+    model = JObject(MC)
+    model.fields.update(dict(numModalities=M, numTopics=K, data=("arraylist", docs), typeTopicCounts=ref.nwk, tokensPerTopic=ref.nk,
+                             alpha=ref.alpha, alphaSum=ref.alphaSum, beta=ref.beta, betaSum=ref.betaSum, gamma=ref.gamma,
+                             numTypes=list(ref.Vs)))
+    sh = vm.shims
+    sh["java/util/ArrayList.size:()I"] = lambda loc, r, a, pc: len(r[1])
+    sh["java/lang/Byte.valueOf:(B)Ljava/lang/Byte;"] = lambda loc, r, a, pc: a[0]
+    sh["java/lang/Byte.byteValue:()B"] = lambda loc, r, a, pc: r
+    sh["java/lang/StringBuilder.append:(Ljava/lang/Object;)Ljava/lang/StringBuilder;"] = lambda loc, r, a, pc: r
+    sh["org/apache/log4j/Logger.info:(Ljava/lang/Object;)V"] = lambda loc, r, a, pc: None
+
+    def warn(loc, r, a, pc):
+        raise RuntimeError("modelLogLikelihood logged a warning (NaN / infinite term)")
+    sh["org/apache/log4j/Logger.warn:(Ljava/lang/Object;)V"] = warn
+    vm.statics[(MC, "logger")] = JObject("logger")
+    old = vm.strict_fields
+    vm.strict_fields = True
+    try:
+        return list(vm.call(MC, "modelLogLikelihood", "()[D", [model]))
+    finally:
+        vm.strict_fields = old
+
+
+def reference_conditionals(ref, iteration, max_tokens=400):
+    """north_star check (b) against the reference itself: one sweep of the jar's sampler with the GLOBAL counts frozen (deltas
+    dropped, the inferencer's nut = 0 mode, W:587) while the per-token masses it computes are read out of its frame at the moment
+    it draws u (W:517): dense index S, cumulative document masses (W:496-513), new-topic mass C (W:515) and the leaves of the
+    word's F+tree (the B bucket).  Net conditional P(t) = (A_t + leaf_t [+ C on the first inactive topic]) / total.  A token is
+    recorded only when S equals the set of topics the document currently holds (so the dead insertion code Q1 has had no
+    effect on it) together with the document's assignments at that moment, from which any implementation can rebuild n_d."""
+    vm, K, M = ref.vm, ref.K, ref.M
+    recs = []
+    ref.rebuild_trees()          # fresh trees: during a sweep only two leaves per delta are refreshed (Q3), the check is on frozen, consistent state
+    saved_apply = vm.shims["java/util/Queue.add:(Ljava/lang/Object;)Z"]
+    vm.shims["java/util/Queue.add:(Ljava/lang/Object;)Z"] = lambda loc, r, a, pc: 1          # counts stay frozen
+    saved_nd = vm.shims["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"]
+
+    def nd(loc, recv, args, pc):
+        r = saved_nd(loc, recv, args, pc)
+        if pc == 1223 and len(recs) < max_tokens:
+            m, pos, nz = loc[20], loc[22], loc[19]
+            S, cum, C = loc[6][:nz], loc[7][:nz], loc[25]
+            counts = loc[13]
+            held = sorted(t for t in range(K) if any(counts[i][t] != 0 for i in range(M)))
+            if list(S) == held:
+                leaves = loc[11].fields["tree"][K:2 * K]
+                mass = [float(x) for x in leaves]
+                prev = 0.0
+                for t, c in zip(S, cum):
+                    mass[t] += c - prev; prev = c
+                total = sum(mass) + C
+                probs = [x / total for x in mass]
+                if C > 0:
+                    probs[ref.inactive[0]] += C / total
+                ent = ref.docs[ref.doc].fields["Assignments"]
+                zdoc = [None if ta is None else list(ta.fields["topicSequence"][3]) for ta in ent]
+                recs.append({"doc": ref.doc, "view": m, "pos": pos, "p_row": [float(x) for x in loc[17][m]], "z_doc": zdoc,
+                             "probs": probs, "new_share": C / total})
+        return r
+    vm.shims["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"] = nd
+    try:
+        ref.sweep(iteration)
+    finally:
+        vm.shims["java/util/Queue.add:(Ljava/lang/Object;)Z"] = saved_apply
+        vm.shims["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"] = saved_nd
+    return recs
+
+
 def make_case(name, K, Vs, means, D, seed, sweeps, p_a=0.0, inactive=(), alpha_new=0.1, rng_seed=0, sparse_view=None, unassigned=0):
     from helpers import random_corpus
     views = random_corpus(rng_seed, D, K, Vs, means, empty_frac=0.1)
@@ -202,11 +301,18 @@ def make_case(name, K, Vs, means, D, seed, sweeps, p_a=0.0, inactive=(), alpha_n
     out = {"name": name, "K": K, "V": Vs, "seed": seed, "views": [{"off": v[0].tolist(), "word": v[1].tolist()} for v in views],
            "z0": z0, "alpha": alpha.tolist(), "alphaSum": alphaSum.tolist(), "beta": beta.tolist(), "betaSum": ref.betaSum, "gamma": gamma.tolist(),
            "p_a": pa.tolist(), "p_b": pb.tolist(), "inactive": list(inactive), "z_after": []}
+    out["loglik_after"] = []
     for it in range(1, sweeps + 1):
         out["z_after"].append(ref.sweep(it))
+        out["loglik_after"].append(reference_loglik(ref))          # modelLogLikelihood from the jar on the state just reached
+    # frozen-count conditionals of the state just reached (the assignments keep moving, the tables do not)
+    out["frozen_counts_z"] = [list(z) for z in ref.z]
+    out["frozen_alpha"] = [list(a) for a in ref.alpha]
+    out["frozen_inactive"] = list(ref.inactive)
+    out["conditionals"] = reference_conditionals(ref, sweeps + 1)
     out["counters"] = dict(ref.counters)
     out["nk_final"] = [list(r) for r in ref.nk]
-    print(name, "tokens", [len(z) for z in z0], "sweeps", sweeps, ref.counters, "bytecode steps", ref.vm.steps, flush=True)
+    print(name, "tokens", [len(z) for z in z0], "sweeps", sweeps, "conditionals", len(out["conditionals"]), ref.counters, "bytecode steps", ref.vm.steps, flush=True)
     return out
 
 

@@ -1143,3 +1143,63 @@ def test_sharded_trainer_two_ranks_one_gpu(engine_lib, oracle_mod):
     assert [a + b for a, b in zip(r0[7], r1[7])] == [len(v[1]) for v in full]
     assert [int(np.sum(x)) for x in r0[6]] == [len(v[1]) for v in full]
     assert abs(np.sum(r0[3][0]) - 1.0) < 1e-9                             # optimizeDP ran: alpha is a distribution over K+1 slots
+
+
+# ---- the engine against vectors produced by the reference's own binary (tests/golden/reference_sampler_vectors.json) ----------
+def _reference_cases():
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
+    for case in gold["cases"]:
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        yield case, case["K"], case["V"], views
+
+
+def test_engine_conditionals_match_reference_bytecode(engine_lib):
+    """north_star check (b) against THE REFERENCE: the per-token conditional distributions the reference's sampler bytecode
+    (FastQMVWVWorkerRunnable.sampleTopicsForOneDoc from the shipped jar, executed by tools/jvm_mini.py) computed on frozen counts
+    -- its dense index, document masses, new-topic mass and F+tree leaves -- vs mvtm_cond_probs on the same state: 1e-5 relative
+    on every topic (fp32 scan on the device), incl. coupled views, inactive topics and the sparse-view sentinel."""
+    from mvtopicmodel_b200 import Engine
+    n = 0
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        e = Engine(K, Vs, views, seed=case["seed"])
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        frozen_z = [np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]]
+        for m in range(M):
+            e.set_assignments(m, frozen_z[m])
+        frozen = [e.get_counts(m) for m in range(M)]
+        for rec in case["conditionals"][::2]:
+            zs = [z.copy() for z in frozen_z]
+            for m, zd in enumerate(rec["z_doc"]):
+                if zd is not None:
+                    b = int(views[m][0][rec["doc"]])
+                    zs[m][b:b + len(zd)] = zd
+            for m in range(M):
+                e.set_assignments(m, zs[m])
+                e.set_counts(m, *frozen[m])                      # the document moved, the global tables did not
+            got = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"])
+            want = np.array(rec["probs"])
+            big = want > 1e-9
+            assert np.max(np.abs(got[:K][big] - want[big]) / want[big]) < REL_TOL_COND, (case["name"], rec["doc"], rec["view"], rec["pos"])
+            assert np.all(np.abs(got[:K][~big] - want[~big]) < 1e-12)
+            assert got[K] == pytest.approx(rec["new_share"], rel=REL_TOL_COND, abs=1e-12)
+            n += 1
+    assert n > 300
+
+
+def test_engine_loglik_matches_reference_bytecode(engine_lib):
+    """mvtm_loglik (quirk_len2 = 1, the reference's own behaviour Q18) vs FastQMVWVParallelTopicModel.modelLogLikelihood executed
+    from the shipped jar on the states its sampler reached: 1e-10 relative."""
+    from mvtopicmodel_b200 import Engine
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+        e = Engine(K, Vs, views, seed=case["seed"], present=present)
+        # the last live sweep's state: hyper-parameters as the reference held them then (activation may have changed alpha)
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        for m in range(M):
+            e.set_assignments(m, np.array(case["z_after"][-1][m], dtype=np.int32))
+        assert np.allclose(e.loglik(True), case["loglik_after"][-1], rtol=1e-10, atol=0), case["name"]

@@ -64,13 +64,17 @@ def test_sampler_matches_reference_bytecode(oracle_mod):
     document and sweep by sweep, with the uniforms the oracle draws for the same token (make_reference_sampler_vectors.py).  The C
     oracle in reference-faithful mode (stale F+trees maintained per delta U:242-260, dead insertion code Q1, deltas applied at
     once) must reproduce them TOKEN FOR TOKEN: single view; two coupled views (Beta-drawn p, other-view mass W:399-410); three
-    views with inactive topics (new-topic bucket W:413-418 / W:515, activation U:263-270)."""
+    views with inactive topics (new-topic bucket W:413-418 / W:515, activation U:263-270).  After every sweep the oracle's
+    log-likelihood must equal the value the jar's modelLogLikelihood bytecode returns for that state."""
     O = oracle_mod
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
     for case in gold["cases"]:
         K, Vs = case["K"], case["V"]
         views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
-        o = O.Oracle(K, Vs, views, seed=case["seed"])
+        # the reference keeps an Assignments[0] object for every document and one for view m > 0 only where the document has
+        # the view (M:437-455); the log-likelihood's phantom-token quirk Q18 looks at exactly that
+        present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+        o = O.Oracle(K, Vs, views, seed=case["seed"], present=present)
         o.set_hyper(alpha=np.array(case["alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
                     betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), p_a=np.array(case["p_a"]), p_b=np.array(case["p_b"]), inactive=case["inactive"])
         o.set_assignments([np.array(z, dtype=np.int32) for z in case["z0"]])
@@ -83,6 +87,53 @@ def test_sampler_matches_reference_bytecode(oracle_mod):
                 w = np.array(want[m], dtype=np.int32)
                 total += len(w); mism += int((got != w).sum())
                 assert np.array_equal(got, w), (case["name"], "sweep", it, "view", m, "first mismatch at", int(np.argmax(got != w)))
+            # modelLogLikelihood (M:3322-3452) executed from the jar on the same state, incl. the phantom tokens of Q18
+            assert np.allclose(o.loglik(True), case["loglik_after"][it - 1], rtol=1e-13, atol=0), (case["name"], it)
         for m in range(len(Vs)):
             assert o.get_counts(m)[1].tolist() == case["nk_final"][m], case["name"]
         assert total > 0 and mism == 0
+
+
+def _conditional_cases():
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
+    for case in gold["cases"]:
+        K, Vs = case["K"], case["V"]
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        yield case, K, Vs, views
+
+
+def _state_with_doc(case, views, rec):
+    """The frozen-count state's assignments with document rec['doc'] as the reference held it when it reached the token."""
+    zs = [np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]]
+    for m, zd in enumerate(rec["z_doc"]):
+        if zd is not None:
+            b = int(views[m][0][rec["doc"]])
+            zs[m][b:b + len(zd)] = zd
+    return zs
+
+
+def test_conditionals_match_reference_bytecode(oracle_mod):
+    """north_star check (b) for the ORACLE: per-token conditional distributions on frozen counts as the reference's sampler
+    bytecode computed them (its S / cumulative masses / C / F+tree leaves read out of the running frame) vs the oracle's
+    three-bucket masses: 1e-9 relative / 1e-15 absolute."""
+    O = oracle_mod
+    n = 0
+    for case, K, Vs, views in _conditional_cases():
+        M = len(Vs)
+        o = O.Oracle(K, Vs, views, seed=case["seed"])
+        o.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        o.set_assignments([np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]])
+        frozen = [o.get_counts(m) for m in range(M)]
+        for rec in case["conditionals"][::3]:
+            o.set_assignments(_state_with_doc(case, views, rec))
+            for m in range(M):
+                o.set_counts(m, *frozen[m])
+            o.rebuild_trees()
+            p = np.eye(M); p[rec["view"]] = rec["p_row"]
+            got = o.cond_probs(rec["view"], rec["doc"], rec["pos"], p=p)
+            # (the reference's document masses are recovered as differences of its cumulative array: absolute error ~1e-16)
+            assert np.allclose(got[:K], rec["probs"], rtol=1e-9, atol=1e-15), (case["name"], rec["doc"], rec["view"], rec["pos"])
+            assert got[K] == pytest.approx(rec["new_share"], rel=1e-9, abs=1e-15)
+            n += 1
+    assert n > 200

@@ -108,6 +108,7 @@ class MiniJVM:
         self.shims = {}
         # debugging aid: {(len(code), pc): f(frame_locals, operand_stack)} called before the instruction at pc executes
         self.probes = {}
+        self.strict_fields = False      # True: reading a field nobody has written raises instead of yielding the JVM default
 
     def load(self, name):
         if name not in self.classes:
@@ -294,6 +295,8 @@ class MiniJVM:
                 c, n, d = ref(u(">H", code, pc + 1)[0]); self.statics[(c, n)] = st.pop(); pc += 3
             elif op == 180:
                 c, n, d = ref(u(">H", code, pc + 1)[0]); o = st.pop()
+                if self.strict_fields and n not in o.fields:
+                    raise KeyError(f"field {c}.{n}:{d} was never set")
                 st.append(o.fields.get(n, 0.0 if d in "DF" else 0 if d in "IJSBCZ" else None)); pc += 3
             elif op == 181:
                 c, n, d = ref(u(">H", code, pc + 1)[0]); v = st.pop(); o = st.pop(); o.fields[n] = v; pc += 3
