@@ -231,6 +231,74 @@ def reference_loglik(ref):
         vm.strict_fields = old
 
 
+def _model_object(ref, docs=None):
+    """A FastQMVWVParallelTopicModel object over the sampler's state (fields set directly, no constructor)."""
+    vm, M, K = ref.vm, ref.M, ref.K
+    model = JObject(MC)
+    model.fields.update(dict(numModalities=M, numTopics=K, data=("arraylist", docs if docs is not None else ref.docs),
+                             typeTopicCounts=ref.nwk, tokensPerTopic=ref.nk, alpha=ref.alpha, alphaSum=ref.alphaSum, beta=ref.beta,
+                             betaSum=ref.betaSum, gamma=ref.gamma, numTypes=list(ref.Vs), totalTokens=[len(z) for z in ref.z],
+                             maxTypeCount=[int(max(sum(row) for row in ref.nwk[m])) for m in range(M)], formatter=("nf",),
+                             docLengthCounts=None, topicDocCounts=None, histogramSize=[0] * M,
+                             totalDocsPerModality=[sum(1 for e in ref.docs if e.fields["Assignments"][m] is not None) for m in range(M)]))
+    sh = vm.shims
+    sh["java/util/ArrayList.size:()I"] = lambda loc, r, a, pc: len(r[1])
+    sh["java/lang/Byte.valueOf:(B)Ljava/lang/Byte;"] = lambda loc, r, a, pc: a[0]
+    sh["java/lang/Byte.byteValue:()B"] = lambda loc, r, a, pc: r
+    sh["java/lang/StringBuilder.append:(Ljava/lang/Object;)Ljava/lang/StringBuilder;"] = lambda loc, r, a, pc: r
+    sh["org/apache/log4j/Logger.info:(Ljava/lang/Object;)V"] = lambda loc, r, a, pc: None
+    sh["org/apache/log4j/Logger.warn:(Ljava/lang/Object;)V"] = lambda loc, r, a, pc: None
+    sh["java/text/NumberFormat.format:(D)Ljava/lang/String;"] = lambda loc, r, a, pc: ""
+    sh["java/text/NumberFormat.format:(Ljava/lang/Object;)Ljava/lang/String;"] = lambda loc, r, a, pc: ""
+    sh[MC + ".appendMetadata:(Ljava/lang/String;)V"] = lambda loc, r, a, pc: None
+    sh["cc/mallet/types/FeatureSequence.getFeatures:()[I"] = lambda loc, r, a, pc: (r[3] if r[0] == "labels" else r[1])
+    sh["cc/mallet/types/FeatureSequence.size:()I"] = lambda loc, r, a, pc: len(r[1])
+
+    class _It:
+        def __init__(self, lst):
+            self.l, self.i = lst, 0
+    sh["java/util/ArrayList.iterator:()Ljava/util/Iterator;"] = lambda loc, r, a, pc: _It(r[1])
+    sh["java/util/Iterator.hasNext:()Z"] = lambda loc, r, a, pc: int(r.i < len(r.l))
+
+    def _next(loc, r, a, pc):
+        v = r.l[r.i]; r.i += 1
+        return v
+    sh["java/util/Iterator.next:()Ljava/lang/Object;"] = _next
+    vm.statics[(MC, "logger")] = JObject("logger")
+    return model
+
+
+def reference_counts_and_histograms(ref):
+    """initializeHistograms (M:849-897) + buildInitialTypeTopicCounts (M:600-652) EXECUTED from the jar over the current
+    assignments, on COPIES of the tables: type-topic counts, topic totals, topicDocCounts[m][t][c] and docLengthCounts."""
+    import copy
+    model = _model_object(ref)
+    model.fields["typeTopicCounts"] = copy.deepcopy(ref.nwk)
+    model.fields["tokensPerTopic"] = copy.deepcopy(ref.nk)
+    # the per-document arrays must show the CURRENT assignments (the sampler's live slices already do)
+    ref.vm.strict_fields = True
+    try:
+        ref.vm.call(MC, "initializeHistograms", "()V", [model])
+        ref.vm.call(MC, "buildInitialTypeTopicCounts", "()V", [model])
+    finally:
+        ref.vm.strict_fields = False
+    return {"typeTopicCounts": model.fields["typeTopicCounts"], "tokensPerTopic": model.fields["tokensPerTopic"],
+            "topicDocCounts": model.fields["topicDocCounts"], "docLengthCounts": model.fields["docLengthCounts"]}
+
+
+def reference_optimize_beta(ref):
+    """optimizeBeta (M:2288-2367) EXECUTED from the jar (it calls MALLET's learnSymmetricConcentration from the MALLET jar) on
+    copies of beta / betaSum: returns the values it would install."""
+    model = _model_object(ref)
+    model.fields["beta"], model.fields["betaSum"] = list(ref.beta), list(ref.betaSum)
+    ref.vm.strict_fields = True
+    try:
+        ref.vm.call(MC, "optimizeBeta", "()V", [model])
+    finally:
+        ref.vm.strict_fields = False
+    return {"beta": model.fields["beta"], "betaSum": model.fields["betaSum"]}
+
+
 def reference_conditionals(ref, iteration, max_tokens=400):
     """north_star check (b) against the reference itself: one sweep of the jar's sampler with the GLOBAL counts frozen (deltas
     dropped, the inferencer's nut = 0 mode, W:587) while the per-token masses it computes are read out of its frame at the moment
@@ -309,6 +377,8 @@ def make_case(name, K, Vs, means, D, seed, sweeps, p_a=0.0, inactive=(), alpha_n
     out["frozen_counts_z"] = [list(z) for z in ref.z]
     out["frozen_alpha"] = [list(a) for a in ref.alpha]
     out["frozen_inactive"] = list(ref.inactive)
+    out["counts_and_histograms"] = reference_counts_and_histograms(ref)
+    out["optimize_beta"] = reference_optimize_beta(ref)
     out["conditionals"] = reference_conditionals(ref, sweeps + 1)
     out["counters"] = dict(ref.counters)
     out["nk_final"] = [list(r) for r in ref.nk]

@@ -1203,3 +1203,28 @@ def test_engine_loglik_matches_reference_bytecode(engine_lib):
         for m in range(M):
             e.set_assignments(m, np.array(case["z_after"][-1][m], dtype=np.int32))
         assert np.allclose(e.loglik(True), case["loglik_after"][-1], rtol=1e-10, atol=0), case["name"]
+
+
+def test_engine_counts_histograms_and_beta_step_match_reference_bytecode(engine_lib):
+    """Count tables, topicDocCounts (every bin, incl. bin 0 as buildInitialTypeTopicCounts writes it, M:647-649) and the
+    optimizeBeta step of mvtm_optimize_hyper vs the reference's own bytecode (buildInitialTypeTopicCounts, initializeHistograms,
+    optimizeBeta executed from the shipped jars): integers bit for bit, beta / betaSum to 1e-9 incl. the sentinel / NaN branches."""
+    from mvtopicmodel_b200 import Engine
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+        e = Engine(K, Vs, views, seed=case["seed"], present=present)
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        ref = case["counts_and_histograms"]
+        for m in range(M):
+            e.set_assignments(m, np.array(case["frozen_counts_z"][m], dtype=np.int32))
+            nwk, nk = e.get_counts(m)
+            assert np.array_equal(nwk, np.array(ref["typeTopicCounts"][m])) and np.array_equal(nk, np.array(ref["tokensPerTopic"][m]))
+            want, got = np.array(ref["topicDocCounts"][m]), e.doc_topic_hist(m)
+            w = min(want.shape[1], got.shape[1])
+            assert np.array_equal(got[:, :w], want[:, :w]) and not want[:, w:].any() and not got[:, w:].any(), (case["name"], m)
+        e.optimize_hyper(50, 8)                                         # MVTM_OPT_BETA
+        hf = e.get_hyper_full()
+        assert np.allclose(hf["beta"], case["optimize_beta"]["beta"], rtol=1e-9, atol=0), case["name"]
+        assert np.allclose(hf["betaSum"], case["optimize_beta"]["betaSum"], rtol=1e-9, atol=0), case["name"]

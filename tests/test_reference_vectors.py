@@ -137,3 +137,27 @@ def test_conditionals_match_reference_bytecode(oracle_mod):
             assert got[K] == pytest.approx(rec["new_share"], rel=1e-9, abs=1e-15)
             n += 1
     assert n > 200
+
+
+def test_counts_histograms_and_optimize_beta_match_reference_bytecode(oracle_mod):
+    """buildInitialTypeTopicCounts + initializeHistograms (M:600-652, M:849-897) and optimizeBeta (M:2288-2367, through MALLET's
+    learnSymmetricConcentration) executed from the jars on the states the reference's sampler reached, vs the oracle: count
+    tables and topicDocCounts (bins c >= 1: bin 0 is never read, M:2461) bit for bit; beta / betaSum incl. the 'too sparse'
+    sentinel and NaN branches to 1e-12."""
+    from oracle import optim
+    O = oracle_mod
+    for case, K, Vs, views in _conditional_cases():
+        M = len(Vs)
+        o = O.Oracle(K, Vs, views, seed=case["seed"])
+        o.set_assignments([np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]])
+        ref = case["counts_and_histograms"]
+        for m in range(M):
+            nwk, nk = o.get_counts(m)
+            assert np.array_equal(nwk, np.array(ref["typeTopicCounts"][m])) and np.array_equal(nk, np.array(ref["tokensPerTopic"][m]))
+            want = np.array(ref["topicDocCounts"][m])
+            got = o.get_hist(m)
+            w = min(want.shape[1], got.shape[1])
+            assert np.array_equal(got[:, 1:w], want[:, 1:w]) and not want[:, w:].any() and not got[:, w:].any(), (case["name"], m)
+            b, bs = optim.optimize_beta(nwk, nk, Vs[m], case["beta"][m], case["betaSum"][m])
+            assert b == pytest.approx(case["optimize_beta"]["beta"][m], rel=1e-12), (case["name"], m)
+            assert bs == pytest.approx(case["optimize_beta"]["betaSum"][m], rel=1e-12), (case["name"], m)

@@ -179,6 +179,17 @@ class MiniJVM:
         return o
 
     def run(self, cf, code, loc):
+        try:
+            return self._run(cf, code, loc)
+        except JavaThrow:
+            raise
+        except Exception as e:          # annotate host-side failures with the bytecode location (innermost frame only)
+            if not getattr(e, "_jvm_where", None):
+                e._jvm_where = (cf.this, self._pc)
+                e.args = (f"{e.args[0] if e.args else ''} [at {cf.this} pc {self._pc}]",) + tuple(e.args[1:])
+            raise
+
+    def _run(self, cf, code, loc):
         loc = list(loc) + [None] * 64
         st, pc, u = [], 0, struct.unpack_from
         cp = cf.cp
@@ -190,6 +201,7 @@ class MiniJVM:
         ncode = len(code)
         while True:
             self.steps += 1
+            self._pc = pc
             if self.probes and (ncode, pc) in self.probes:
                 self.probes[(ncode, pc)](loc, st)
             op = code[pc]
