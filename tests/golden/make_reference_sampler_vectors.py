@@ -10,8 +10,11 @@ What is real and what is shimmed
                           views over the same arrays; ThreadLocalRandom.nextDouble and Randoms.nextBeta, which return the uniforms
                           the ORACLE draws for the same (token position, document, iteration, view) -- Philox4x32-10, 24-bit, see
                           oracle/mvtm_oracle.c orc_draw -- so that both consume identical randomness (the reference's own RNG is
-                          unseedable, Q9); Queue.add, which applies the delta at once the way FastQMVWVUpdaterRunnable does
-                          (U:197-260: counts, totals, the two tree leaves via the jar's FTree.update)
+                          unseedable, Q9); the queue between the two runnables: Queue.add hands the delta (plus the end-of-sweep
+                          sentinel) straight to FastQMVWVUpdaterRunnable.run -- ALSO executed from the jar (U:164-297: counts,
+                          totals, topicDocCounts histogram, the two F+tree leaves, activation of inactive topics) -- so every
+                          delta is applied at once; the initial tables and histograms come from the jar's
+                          initializeHistograms + buildInitialTypeTopicCounts (M:849-897, M:600-652)
 
 Output: tests/golden/reference_sampler_vectors.json -- corpus, hyper-parameters, initial assignments, and the assignments after
 every sweep.  tests/test_reference_vectors.py replays them through the C oracle (reference-faithful mode) and demands equality
@@ -35,6 +38,8 @@ from oracle import oracle as O  # noqa: E402
 REF = "/root/reference/output"
 W = "org/madgik/MVTopicModel/FastQMVWVWorkerRunnable"
 FT = "org/madgik/utils/FTree"
+UP = "org/madgik/MVTopicModel/FastQMVWVUpdaterRunnable"
+MC = "org/madgik/MVTopicModel/FastQMVWVParallelTopicModel"
 PURPOSE_SAMPLE, PURPOSE_PDRAW = 0, 2
 
 
@@ -51,26 +56,12 @@ class RefSampler:
         M = self.M
         self.D = len(views[0][0]) - 1
         self.z = [[int(t) for t in z0[m]] for m in range(M)]
-        # counts from the assignments (M:600-652)
-        self.nwk = [[[0] * K for _ in range(Vs[m])] for m in range(M)]
+        self.nwk = [[[0] * K for _ in range(Vs[m])] for m in range(M)]       # filled by the jar's buildInitialTypeTopicCounts below
         self.nk = [[0] * K for _ in range(M)]
-        for m in range(M):
-            for w, t in zip(views[m][1], self.z[m]):
-                if t >= 0 and 0 <= w < Vs[m]:
-                    self.nwk[m][int(w)][t] += 1
-                    self.nk[m][t] += 1
         self.alpha = [list(map(float, a)) for a in alpha]
         self.alphaSum, self.beta, self.gamma = list(map(float, alphaSum)), list(map(float, beta)), list(map(float, gamma))
         self.betaSum = [self.beta[m] * Vs[m] for m in range(M)]
         self.inactive = list(inactive)
-        # F+trees (M:2660-2696) built by the jar's FTree constructor
-        self.trees = []
-        for m in range(M):
-            row = []
-            for w in range(Vs[m]):
-                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(K)]
-                row.append(vm.new(FT, "([D)V", [leaves]))
-            self.trees.append(row)
         # per-document containers: data.get(d).Assignments[m] = {instance -> FeatureSequence shim, topicSequence -> LabelSequence shim}
         self.docs = []
         for d in range(self.D):
@@ -88,13 +79,6 @@ class RefSampler:
                 arr.append(ta)
             ent.fields["Assignments"] = arr
             self.docs.append(ent)
-        wk = JObject(W)
-        wk.fields.update(dict(data=("arraylist", self.docs), numModalities=M, numTopics=K, alpha=self.alpha, alphaSum=self.alphaSum,
-                              beta=self.beta, betaSum=self.betaSum, gamma=self.gamma, p_a=[list(map(float, r)) for r in p_a],
-                              p_b=[list(map(float, r)) for r in p_b], typeTopicCounts=self.nwk, tokensPerTopic=self.nk, trees=self.trees,
-                              random=("randoms",), queue=("queue",), inActiveTopicIndex=("inactive",), useTypeVectors=0,
-                              useTypeVectorsProb=0.0, typeTopicSimilarity=None, threadId=0))
-        self.worker = wk
         self.iteration, self.doc = 0, 0
         self.counters = {"new": 0, "doc": 0, "tree": 0, "tree_bucket": 0, "deltas": 0, "beta_draws": 0}
         sh = vm.shims
@@ -104,7 +88,34 @@ class RefSampler:
         sh["cc/mallet/types/FeatureSequence.getLength:()I"] = lambda loc, r, a, pc: len(r[1])
         sh["cc/mallet/types/FeatureSequence.getIndexAtPosition:(I)I"] = lambda loc, r, a, pc: r[1][a[0]]
         sh["java/util/List.isEmpty:()Z"] = lambda loc, r, a, pc: int(len(self.inactive) == 0)
-        sh["java/util/List.get:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: self.inactive[a[0]]
+        sh["java/util/List.get:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: (("queue",) if r[0] == "queues" else self.inactive[a[0]])
+        sh["java/util/List.size:()I"] = lambda loc, r, a, pc: (1 if r[0] == "queues" else len(self.inactive))
+        unbox = lambda v: v.fields["value"] if isinstance(v, JObject) else v
+        sh["java/util/List.contains:(Ljava/lang/Object;)Z"] = lambda loc, r, a, pc: int(unbox(a[0]) in self.inactive)
+
+        def list_remove(loc, r, a, pc):
+            v = unbox(a[0])
+            if v in self.inactive:
+                self.inactive.remove(v); return 1
+            return 0
+        sh["java/util/List.remove:(Ljava/lang/Object;)Z"] = list_remove
+        sh["java/lang/Integer.valueOf:(I)Ljava/lang/Integer;"] = lambda loc, r, a, pc: a[0]
+
+        def integer_init(loc, r, a, pc):
+            r.fields["value"] = a[0]
+        sh["java/lang/Integer.<init>:(I)V"] = integer_init
+        sh["java/util/Queue.poll:()Ljava/lang/Object;"] = lambda loc, r, a, pc: (self.pending.pop(0) if self.pending else None)
+
+        def set_add(loc, r, a, pc):
+            r.fields.setdefault("items", set()).add(a[0]); return 1
+        sh["java/util/Set.add:(Ljava/lang/Object;)Z"] = set_add
+        sh["java/util/Set.size:()I"] = lambda loc, r, a, pc: len(r.fields.get("items", ()))
+        sh["java/lang/Thread.currentThread:()Ljava/lang/Thread;"] = lambda loc, r, a, pc: ("thread",)
+
+        sh["java/lang/Thread.sleep:(J)V"] = lambda loc, r, a, pc: None      # U:276-280: the 20 ms nap after every pass over the queues
+        sh["java/util/concurrent/CyclicBarrier.await:()I"] = lambda loc, r, a, pc: 0
+        sh["org/apache/log4j/Logger.info:(Ljava/lang/Object;)V"] = lambda loc, r, a, pc: None
+        vm.statics[(UP, "logger")] = JObject("logger")
         sh["java/lang/Integer.intValue:()I"] = lambda loc, r, a, pc: r
         sh["java/util/concurrent/ThreadLocalRandom.current:()Ljava/util/concurrent/ThreadLocalRandom;"] = lambda loc, r, a, pc: ("tlr",)
         sh["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"] = self.next_double
@@ -122,6 +133,36 @@ class RefSampler:
         def boom(loc, r, a, pc):
             raise RuntimeError("the reference's sampler threw inside sampleTopicsForOneDoc")
         sh["java/lang/Exception.printStackTrace:()V"] = boom
+
+        # counts, totals, topicDocCounts and docLengthCounts by the jar's own initialisation code (M:849-897, M:600-652)
+        model = _model_object(self)
+        vm.call(MC, "initializeHistograms", "()V", [model])
+        vm.call(MC, "buildInitialTypeTopicCounts", "()V", [model])
+        self.hist, self.doc_len_counts = model.fields["topicDocCounts"], model.fields["docLengthCounts"]
+        # F+trees (M:2660-2696) built by the jar's FTree constructor
+        self.trees = []
+        for m in range(M):
+            row = []
+            for w in range(Vs[m]):
+                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(K)]
+                row.append(vm.new(FT, "([D)V", [leaves]))
+            self.trees.append(row)
+        # the updater (U:78-147 fields set directly): one queue, drained by running its run() after every enqueue
+        self.pending = []
+        up = JObject(UP)
+        up.fields.update(dict(typeTopicCounts=self.nwk, tokensPerTopic=self.nk, trees=self.trees, queues=("queues",), alpha=self.alpha,
+                              alphaSum=self.alphaSum, beta=self.beta, betaSum=self.betaSum, gamma=self.gamma, numTopics=K,
+                              numModalities=M, numTypes=list(Vs), topicDocCounts=self.hist, docLengthCounts=self.doc_len_counts,
+                              inActiveTopicIndex=("inactive",), optimizeParams=0, isFinished=1, useCycleProposals=0,
+                              cyclicBarrier=("barrier",)))
+        self.updater = up
+        wk = JObject(W)
+        wk.fields.update(dict(data=("arraylist", self.docs), numModalities=M, numTopics=K, alpha=self.alpha, alphaSum=self.alphaSum,
+                              beta=self.beta, betaSum=self.betaSum, gamma=self.gamma, p_a=[list(map(float, r)) for r in p_a],
+                              p_b=[list(map(float, r)) for r in p_b], typeTopicCounts=self.nwk, tokensPerTopic=self.nk, trees=self.trees,
+                              random=("randoms",), queue=("queue",), inActiveTopicIndex=("inactive",), useTypeVectors=0,
+                              useTypeVectorsProb=0.0, typeTopicSimilarity=None, threadId=0))
+        self.worker = wk
 
     def rebuild_trees(self):
         """buildFTrees(false), M:2660-2696 (what estimate() does after every optimise step, M:1209): every leaf from the current
@@ -155,19 +196,14 @@ class RefSampler:
         x = self.philox(0, m * self.M + j, PURPOSE_PDRAW)
         return u24(x[0]) ** (1.0 / args[0])            # Beta(a, 1) by inversion, the oracle's default law (Q5)
 
-    # --- FastQMVWVUpdaterRunnable's treatment of one delta (U:197-260), applied at once ----------------------------------
+    # --- the queue: every delta goes straight through the jar's FastQMVWVUpdaterRunnable.run (U:164-297) ---------------------
     def apply_delta(self, loc, recv, args, pc):
-        d = args[0].fields
-        m, w, old, new = d["Modality"], d["Type"], d["OldTopic"], d["NewTopic"]
-        row = self.nwk[m][w]
-        if old != -1:
-            row[old] -= 1; self.nk[m][old] -= 1
-        row[new] += 1; self.nk[m][new] += 1
-        if old != -1:
-            self.vm.call(FT, "update", "(ID)V", [self.trees[m][w], old, self.leaf(m, w, old)])
-        self.vm.call(FT, "update", "(ID)V", [self.trees[m][w], new, self.leaf(m, w, new)])
-        if new in self.inactive:                                                                 # U:263-270
-            self.inactive.remove(new); self.alpha[m][new] = self.alpha[m][self.K]
+        sentinel = JObject("org/madgik/utils/FastQDelta")                 # W:215-222: FastQDelta(-1, -1, -1, -1, ...) ends a worker's stream
+        sentinel.fields.update(dict(NewTopic=-1, OldTopic=-1, Type=-1, Modality=-1, DocOldTopicCnt=-1, DocNewTopicCnt=-1))
+        self.pending.extend([args[0], sentinel])
+        self.updater.fields["isFinished"] = 1
+        self.vm.call(UP, "run", "()V", [self.updater])
+        assert not self.pending
         self.counters["deltas"] += 1
         return 1
 
@@ -183,9 +219,6 @@ class RefSampler:
                     _, _, b, zs = ta.fields["topicSequence"]
                     self.z[m][b:b + len(zs)] = zs
         return [list(z) for z in self.z]
-
-
-MC = "org/madgik/MVTopicModel/FastQMVWVParallelTopicModel"
 
 
 def reference_loglik(ref):
@@ -381,6 +414,7 @@ def make_case(name, K, Vs, means, D, seed, sweeps, p_a=0.0, inactive=(), alpha_n
     out["optimize_beta"] = reference_optimize_beta(ref)
     out["conditionals"] = reference_conditionals(ref, sweeps + 1)
     out["counters"] = dict(ref.counters)
+    out["hist_maintained"] = [[list(r) for r in h] for h in ref.hist]      # topicDocCounts as the updater left it (U:220-232)
     out["nk_final"] = [list(r) for r in ref.nk]
     print(name, "tokens", [len(z) for z in z0], "sweeps", sweeps, "conditionals", len(out["conditionals"]), ref.counters, "bytecode steps", ref.vm.steps, flush=True)
     return out

@@ -64,7 +64,8 @@ def test_sampler_matches_reference_bytecode(oracle_mod):
     document and sweep by sweep, with the uniforms the oracle draws for the same token (make_reference_sampler_vectors.py).  The C
     oracle in reference-faithful mode (stale F+trees maintained per delta U:242-260, dead insertion code Q1, deltas applied at
     once) must reproduce them TOKEN FOR TOKEN: single view; two coupled views (Beta-drawn p, other-view mass W:399-410); three
-    views with inactive topics (new-topic bucket W:413-418 / W:515, activation U:263-270).  After every sweep the oracle's
+    views with inactive topics (new-topic bucket W:413-418 / W:515, activation U:263-270).  The deltas were applied by the
+    jar's FastQMVWVUpdaterRunnable.run, whose doc-topic histogram must equal the oracle's at the end.  After every sweep the oracle's
     log-likelihood must equal the value the jar's modelLogLikelihood bytecode returns for that state."""
     O = oracle_mod
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
@@ -91,6 +92,10 @@ def test_sampler_matches_reference_bytecode(oracle_mod):
             assert np.allclose(o.loglik(True), case["loglik_after"][it - 1], rtol=1e-13, atol=0), (case["name"], it)
         for m in range(len(Vs)):
             assert o.get_counts(m)[1].tolist() == case["nk_final"][m], case["name"]
+            # topicDocCounts as the jar's UPDATER left it after all those deltas (U:220-232) vs the oracle's maintained copy
+            want, got = np.array(case["hist_maintained"][m]), o.get_hist(m)
+            w = min(want.shape[1], got.shape[1])
+            assert np.array_equal(got[:, 1:w], want[:, 1:w]) and not want[:, w:].any() and not got[:, w:].any(), (case["name"], m)
         assert total > 0 and mism == 0
 
 
