@@ -14,7 +14,8 @@ What is real and what is shimmed
                           sentinel) straight to FastQMVWVUpdaterRunnable.run -- ALSO executed from the jar (U:164-297: counts,
                           totals, topicDocCounts histogram, the two F+tree leaves, activation of inactive topics) -- so every
                           delta is applied at once; the initial tables and histograms come from the jar's
-                          initializeHistograms + buildInitialTypeTopicCounts (M:849-897, M:600-652)
+                          initializeHistograms + buildInitialTypeTopicCounts (M:849-897, M:600-652), the F+trees from its
+                          recalcTrees (this build's name for buildFTrees, M:2660-2696)
 
 Output: tests/golden/reference_sampler_vectors.json -- corpus, hyper-parameters, initial assignments, and the assignments after
 every sweep.  tests/test_reference_vectors.py replays them through the C oracle (reference-faithful mode) and demands equality
@@ -139,14 +140,13 @@ class RefSampler:
         vm.call(MC, "initializeHistograms", "()V", [model])
         vm.call(MC, "buildInitialTypeTopicCounts", "()V", [model])
         self.hist, self.doc_len_counts = model.fields["topicDocCounts"], model.fields["docLengthCounts"]
-        # F+trees (M:2660-2696) built by the jar's FTree constructor
-        self.trees = []
-        for m in range(M):
-            row = []
-            for w in range(Vs[m]):
-                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(K)]
-                row.append(vm.new(FT, "([D)V", [leaves]))
-            self.trees.append(row)
+        # F+trees by the jar's recalcTrees(true) (this build's name for buildFTrees, M:2660-2696): leaves
+        # gamma*alpha*(n_wk+beta)/(n_k+betaSum), 0 for inactive topics, one `new FTree(temp)` per word type
+        self.trees = [[None] * Vs[m] for m in range(M)]
+        model.fields["trees"], model.fields["inActiveTopicIndex"] = self.trees, ("inactive",)
+        model.fields["docSmoothingOnlyMass"] = [0.0] * M
+        self.model = model
+        vm.call(MC, "recalcTrees", "(Z)V", [model, 1])
         # the updater (U:78-147 fields set directly): one queue, drained by running its run() after every enqueue
         self.pending = []
         up = JObject(UP)
@@ -165,15 +165,8 @@ class RefSampler:
         self.worker = wk
 
     def rebuild_trees(self):
-        """buildFTrees(false), M:2660-2696 (what estimate() does after every optimise step, M:1209): every leaf from the current
-        counts, 0 for topics in inActiveTopicIndex, through the jar's FTree.constructTree."""
-        for m in range(self.M):
-            for w in range(self.Vs[m]):
-                leaves = [0.0 if t in self.inactive else self.leaf(m, w, t) for t in range(self.K)]
-                self.vm.call(FT, "constructTree", "([D)V", [self.trees[m][w], leaves])
-
-    def leaf(self, m, w, t):          # U:242-260 / M:2678: gamma * alpha * ((n_wk + beta) / (n_k + betaSum))
-        return self.gamma[m] * self.alpha[m][t] * ((self.nwk[m][w][t] + self.beta[m]) / (self.nk[m][t] + self.betaSum[m]))
+        """recalcTrees(false) executed from the jar: what estimate() does after every optimise step (M:1209)."""
+        self.vm.call(MC, "recalcTrees", "(Z)V", [self.model, 0])
 
     # --- randomness: exactly the oracle's draws (oracle/mvtm_oracle.c: orc_draw, draw_p) ---------------------------------
     def philox(self, pos, view_or_pair, purpose):
