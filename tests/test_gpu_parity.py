@@ -1228,3 +1228,63 @@ def test_engine_counts_histograms_and_beta_step_match_reference_bytecode(engine_
         hf = e.get_hyper_full()
         assert np.allclose(hf["beta"], case["optimize_beta"]["beta"], rtol=1e-9, atol=0), case["name"]
         assert np.allclose(hf["betaSum"], case["optimize_beta"]["betaSum"], rtol=1e-9, atol=0), case["name"]
+
+
+def test_engine_trajectory_matches_reference_bytecode(engine_lib, oracle_mod):
+    """north_star check (c) against THE REFERENCE: the log-likelihood trajectory of the reference's own sampler + updater bytecode
+    (tests/golden/reference_trajectory.json: 30 sweeps over a 400-document two-view corpus, burn-in ramp of p_a, LL by the jar's
+    modelLogLikelihood every 5 sweeps) vs the engine from the same initial assignments with its own randomness and its
+    asynchronous sweeps.
+
+    One run on 11 K tokens is noisy -- the reference's own seed-to-seed spread here is +-0.9 % (text view) and +-2.6 % (the
+    1.5 K-token side view), measured with the reference-faithful oracle, which reproduces the jar's run token for token
+    (tests/test_reference_vectors.py) and is therefore the reference with other random numbers.  So the comparison is between
+    ENSEMBLES: the jar's trajectory plus five reference-faithful runs vs six engine runs; the means must agree within 1 % (text
+    view; 2 % on the tiny side view) at every checkpoint, and every engine run must stay within the band the reference runs
+    span, widened by 1 %."""
+    import json
+    from mvtopicmodel_b200 import Engine
+    O = oracle_mod
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_trajectory.json")))
+    K, Vs = g["K"], g["V"]
+    views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in g["views"]]
+    M = len(Vs)
+    present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+    marks = {it: np.array(ll) for it, ll in g["loglik"]}
+    checkpoints = [it for it in sorted(marks) if it > 0]
+    z0 = [np.array(z, dtype=np.int32) for z in g["z0"]]
+    ref_runs = [np.array([marks[it] for it in checkpoints])]                 # the jar's own run
+    for seed in range(1, 6):
+        o = O.Oracle(K, Vs, views, seed=seed, present=present)
+        o.set_assignments(z0); o.rebuild_trees()
+        traj = []
+        for it in range(1, checkpoints[-1] + 1):
+            o.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+            o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT)
+            if it in marks:
+                traj.append(o.loglik(True))
+        ref_runs.append(np.array(traj))
+    eng_runs = []
+    for seed in (77, 1, 2, 3, 4, 5):
+        e = Engine(K, Vs, views, seed=seed, present=present, max_ctas=2, warps_per_cta=2)     # a few documents in flight
+        for m in range(M):
+            e.set_assignments(m, z0[m])
+        assert np.allclose(e.loglik(True), marks[0], rtol=1e-10)          # same state, same formula (incl. Q18)
+        traj = []
+        for it in range(1, checkpoints[-1] + 1):
+            e.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+            e.sweep(it)
+            if it in marks:
+                traj.append(e.loglik(True))
+        assert e.check_invariants() == 0
+        eng_runs.append(np.array(traj))
+    ref_runs, eng_runs = np.array(ref_runs), np.array(eng_runs)           # [run, checkpoint, view]
+    ref_mean, eng_mean = ref_runs.mean(0), eng_runs.mean(0)
+    rel = np.abs(eng_mean - ref_mean) / np.abs(ref_mean)
+    print("checkpoints", checkpoints, "\n mean engine", eng_mean.round(0).tolist(), "\n mean reference", ref_mean.round(0).tolist(), "\n rel", rel.round(4).tolist())
+    # text view (9.8 K tokens): 1 %.  The side view has 1.5 K tokens and a run-to-run spread of +-2.6 % in the reference itself, so
+    # the standard error of a six-run mean is ~1 % there: it is held to 2 % (observed: 0.1-1.4 %)
+    assert np.all(rel[:, 0] < REL_TOL_LL) and np.all(rel[:, 1:] < 2 * REL_TOL_LL), rel
+    lo, hi = ref_runs.min(0), ref_runs.max(0)
+    widen = np.array([REL_TOL_LL] + [2 * REL_TOL_LL] * (M - 1))
+    assert np.all(eng_runs >= lo - widen * np.abs(lo)) and np.all(eng_runs <= hi + widen * np.abs(hi))

@@ -166,3 +166,32 @@ def test_counts_histograms_and_optimize_beta_match_reference_bytecode(oracle_mod
             b, bs = optim.optimize_beta(nwk, nk, Vs[m], case["beta"][m], case["betaSum"][m])
             assert b == pytest.approx(case["optimize_beta"]["beta"][m], rel=1e-12), (case["name"], m)
             assert bs == pytest.approx(case["optimize_beta"]["betaSum"][m], rel=1e-12), (case["name"], m)
+
+
+def _trajectory():
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_trajectory.json")
+    g = json.load(open(path))
+    views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in g["views"]]
+    return g, g["K"], g["V"], views
+
+
+def test_oracle_reproduces_reference_trajectory(oracle_mod):
+    """30 sweeps (~360 K token draws) of the reference's own sampler + updater bytecode over a 400-document two-view corpus with
+    the burn-in ramp of p_a (tests/golden/make_reference_trajectory.py): the oracle, fed the same uniforms, ends with the SAME
+    assignments and the same log-likelihood at every checkpoint."""
+    O = oracle_mod
+    g, K, Vs, views = _trajectory()
+    M = len(Vs)
+    present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+    o = O.Oracle(K, Vs, views, seed=g["seed"], present=present)
+    o.set_assignments([np.array(z, dtype=np.int32) for z in g["z0"]])
+    o.rebuild_trees()
+    marks = {it: ll for it, ll in g["loglik"]}
+    assert np.allclose(o.loglik(True), marks[0], rtol=1e-12)
+    for it in range(1, max(marks) + 1):
+        o.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+        o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT)
+        if it in marks:
+            assert np.allclose(o.loglik(True), marks[it], rtol=1e-12), it
+    for m in range(M):
+        assert np.array_equal(o.get_assignments(m), np.array(g["z_final"][m], dtype=np.int32))
