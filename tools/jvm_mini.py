@@ -369,6 +369,8 @@ class MiniJVM:
             elif op == 191:
                 o = st.pop(); raise JavaThrow(o.cls if isinstance(o, JObject) else str(o))
             elif op == 192: pc += 3
+            elif op == 193:            # instanceof: host objects are trusted to be what the bytecode expects; null is an instance of nothing
+                o = st.pop(); st.append(0 if o is None else 1); pc += 3
             elif op in (198, 199):
                 a = st.pop(); t = (a is None) if op == 198 else (a is not None)
                 pc = pc + u(">h", code, pc + 1)[0] if t else pc + 3
