@@ -105,11 +105,15 @@ def cpu_reference_run(workload, sample_docs, steps, warmup, threads):
     o.init_assignments()
     o.rebuild_trees()
     ntok = sum(o.ntok)
+    # the reference's own algorithm: F+trees maintained per delta by the updater threads (stale otherwise, Q3) and the dead
+    # dense-index insertion (Q1) -- the configuration tests/test_reference_vectors.py shows to reproduce the reference's
+    # sampler bytecode token for token
+    flags = O.F_STALE_TREES | O.F_Q1_COMPAT
     for it in range(1, warmup + 1):
-        o.sweep_mt(it, threads)
+        o.sweep_mt(it, threads, flags)
     t0 = time.perf_counter()
     for it in range(warmup + 1, warmup + steps + 1):
-        o.sweep_mt(it, threads)
+        o.sweep_mt(it, threads, flags)
     dt = time.perf_counter() - t0
     assert o.check_invariants() == 0
     return ntok * steps / dt, dt / steps * 1e3, ntok, K
@@ -153,7 +157,7 @@ def main():
                 "data": "synthetic", "config": {"workload": wl_desc, "sample": f"{args.cpu_sample_docs} docs / {ntok} tokens per step"},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": f"first {args.cpu_sample_docs} docs ({ntok} tokens) of {args.workload}, {steps} sweeps; "
-                                           f"{nst} sampler + {nut} updater threads (M:1036-1037); C restatement of the Java scheme, no JVM in this image"},
+                                           f"{nst} sampler + {nut} updater threads (M:1036-1037); C restatement of the Java scheme (token-for-token equal to the reference's sampler bytecode in its sequential form), no JVM in this image"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
