@@ -42,6 +42,8 @@
 #define ORC_F_STALE_TREES   2u   /* Q3: B bucket from the incrementally maintained trees (U:242-260)     */
 #define ORC_F_DEFERRED      4u   /* apply all deltas at the end of the sweep instead of immediately      */
 #define ORC_F_BETA_MALLET   8u   /* Q5: MALLET Randoms.nextBeta law instead of true Beta(a,1)=u^(1/a)    */
+#define ORC_F_CHECK_RULE 256u     /* reference-faithful mode + Q1: also run the engine's flag rule for the dense index and count
+                                     the tokens at which it disagrees with the reference's own list S (must stay 0)          */
 #define ORC_F_ENGINE_MIRROR 16u  /* view-major order, dense single-scan sampler in the engine's order     */
 #define ORC_F_DOC_ORDER     32u  /* (engine mirror) plain document order, no length sort                 */
 #define ORC_F_FROZEN        64u  /* global counts frozen: the inferencer's nut = 0 mode, I:211-256 */
@@ -71,6 +73,10 @@ typedef struct {
     int32_t *inactive;               /* ascending topic ids */
     uint64_t seed;
     int engine_G;                    /* lanes per document-view of the engine's scan (mvtm_scan_layout) */
+    int64_t cnt_rule_bad;            /* ORC_F_CHECK_RULE: tokens at which the flag rule disagreed with the reference's S */
+    uint8_t *rflag;                  /* engine mirror with Q1: D x K flags "topic is NOT in the dense index of this document for
+                                        the rest of the sweep" (left it, or was gained while absent: W:441-468 removes, W:563-584
+                                        never inserts); kept across the view passes of one sweep */
     int64_t doc_base, doc_stride;    /* global id of local document d = doc_base + d*doc_stride (keys the RNG) */
     int64_t cnt_new, cnt_doc, cnt_tree, cnt_changed;   /* W:33-35 bucket counters */
     char err[256];
@@ -210,7 +216,7 @@ void orc_destroy(orc_t *o)
         free(o->n_k[m]); free(o->type_total[m]); free(o->tree[m]); free(o->hist[m]); free(o->doclen_cnt[m]);
         free(o->alpha[m]);
     }
-    free(o->inactive); free(o);
+    free(o->inactive); free(o->rflag); free(o);
 }
 int orc_add_view(orc_t *o, int m, const int64_t *doc_off, const int32_t *word, const uint8_t *present)
 {   /* MA:13-19 / M:410-463 restated as a doc-aligned CSR per view; absent view == empty range */
@@ -491,6 +497,8 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
     int nz = 0;                                                          /* W:376-391 */
     for (int t = 0; t < K; t++)
         for (int i = 0; i < M; i++) if (s->nd[i * K + t] != 0) { s->S[nz++] = t; break; }
+    uint8_t *rule = NULL;                                                /* the engine's "not in S" flags, checked against S */
+    if ((flags & ORC_F_CHECK_RULE) && (flags & ORC_F_Q1_COMPAT)) rule = (uint8_t *)calloc((size_t)K, 1);
 
     for (int m = 0; m < M; m++) {                                        /* W:393 */
         memset(s->O, 0, (size_t)K * 8);
@@ -517,6 +525,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
                 s->nd[m * K + old_t]--;
                 int deleted = 1;
                 for (int j = 0; j < M && deleted; j++) deleted = (s->nd[j * K + old_t] == 0);
+                if (deleted && rule) rule[old_t] = 1;
                 if (deleted) {
                     int di = 0;
                     while (di < nz && s->S[di] != old_t) di++;
@@ -525,6 +534,18 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
                         nz--;
                     }
                 }
+            }
+            if (rule) {                                                  /* S must equal {held and not flagged} at every token */
+                int bad = 0, di = 0;
+                for (int t = 0; t < K; t++) {
+                    int held = 0;
+                    for (int j = 0; j < M; j++) held |= (s->nd[j * K + t] != 0);
+                    int in_rule = held && !rule[t];
+                    int in_ref = (di < nz && s->S[di] == t);
+                    if (in_ref) di++;
+                    bad |= (in_rule != in_ref);
+                }
+                o->cnt_rule_bad += bad;
             }
             double acc = 0;                                              /* W:496-513 */
             for (int di = 0; di < nz; di++) {
@@ -550,6 +571,11 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
             }
             if (new_t == -1) new_t = K - 1;                              /* W:549-553 */
             o->z[m][b + pos] = new_t;                                    /* W:557 */
+            if (rule) {
+                int held = 0;
+                for (int j = 0; j < M; j++) held |= (s->nd[j * K + new_t] != 0);
+                if (!held) rule[new_t] = 1;
+            }
             s->nd[m * K + new_t]++;                                      /* W:560 */
             if (!(flags & ORC_F_Q1_COMPAT)) {
                 /* intended semantics of W:563-584: insert when the topic was absent from every view */
@@ -572,6 +598,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
             }
         }
     }
+    free(rule);
 }
 
 typedef struct { orc_t *o; orc_scratch *s; unsigned flags; } emit_ctx;
@@ -604,6 +631,7 @@ static int engine_slot_size(int K)
 /* unnormalised engine weights for token (d, m, pos) given local counts nd (own token already removed),
  * other-view state and the frozen topic totals nk_frozen.  out has K entries. */
 static unsigned g_engine_weight_flags = 0;   /* set by the sweep for the duration of a mirror pass (single-threaded) */
+static const uint8_t *g_not_in_S = NULL;     /* K flags of the document being sampled (Q1), or NULL */
 static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, const int len[ORC_MAXM],
                            double p[ORC_MAXM][ORC_MAXM], const int32_t *nk_frozen, double *out)
 {
@@ -613,6 +641,7 @@ static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, cons
     for (int t = 0; t < K; t++) {
         int inS = 0;
         for (int i = 0; i < M; i++) if (nd[i * K + t] != 0) { inS = 1; break; }
+        if (g_not_in_S && g_not_in_S[t]) inS = 0;      /* Q1: held, but not in the dense index: neither n_d nor O enters (W:501-513 walks S) */
         double O = 0;
         if (inS && M > 1) {
             for (int i = 0; i < M; i++)
@@ -623,7 +652,7 @@ static void engine_weights(const orc_t *o, int m, int w, const int32_t *nd, cons
         double ga = (o->n_inactive && is_inactive(o, t)) ? 0.0 : o->gamma[m] * o->alpha[m][t];
         if (g_engine_weight_flags & ORC_F_BARE_TREES) ga = 1.0;
         double phi = (row[t] + o->beta[m]) / (nk_frozen[t] + o->betaSum[m]);
-        out[t] = phi * (p[m][m] * nd[m * K + t] + O + ga);
+        out[t] = phi * ((inS ? p[m][m] * nd[m * K + t] : 0.0) + O + ga);
     }
 }
 
@@ -669,16 +698,30 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
     Cdoc *= coefm;
     double C = o->n_inactive == 0 ? 0 : Cdoc / K;
     int64_t b = o->doc_off[m][d];
+    uint8_t *rf = ((flags & ORC_F_Q1_COMPAT) && o->rflag) ? o->rflag + (size_t)d * K : NULL;
+    g_not_in_S = rf;
     for (int pos = 0; pos < len[m]; pos++) {
         int w = o->word[m][b + pos];
         if (w >= o->V[m] || w < 0) continue;
         int old_t = o->z[m][b + pos];
-        if (old_t != ORC_UNASSIGNED) s->nd[m * K + old_t]--;
+        if (old_t != ORC_UNASSIGNED) {
+            s->nd[m * K + old_t]--;
+            if (rf) {                                   /* W:441-468: no view holds it any more -> it leaves the index for good */
+                int held = 0;
+                for (int i = 0; i < M; i++) held |= (s->nd[i * K + old_t] != 0);
+                if (!held) rf[old_t] = 1;
+            }
+        }
         engine_weights(o, m, w, s->nd, len, p, nk_frozen, s->cum);
         uint32_t x[4];
         orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
         int new_t = orc_engine_select_g(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1, o->engine_G);
         o->z[m][b + pos] = new_t;
+        if (rf) {                                       /* W:563-584 is dead code: a topic gained while absent is never inserted */
+            int held = 0;
+            for (int i = 0; i < M; i++) held |= (s->nd[i * K + new_t] != 0);
+            if (!held) rf[new_t] = 1;
+        }
         s->nd[m * K + new_t]++;
         if (new_t != old_t && !(flags & ORC_F_FROZEN)) {   /* n_wk live, n_k deferred to the end of the view pass (engine semantics) */
             int32_t *row = o->n_wk[m] + (size_t)w * K;
@@ -722,6 +765,8 @@ static void activate_sampled_topics(orc_t *o)
     }
 }
 
+long long orc_rule_violations(const orc_t *o) { return (long long)o->cnt_rule_bad; }
+
 int orc_sweep(orc_t *o, int iteration, unsigned flags)
 {
     orc_scratch *s = scratch_new(o);
@@ -729,6 +774,10 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
     if (flags & ORC_F_ENGINE_MIRROR) {
         int K = o->K;
         g_engine_weight_flags = flags;
+        if (flags & ORC_F_Q1_COMPAT) {                   /* the dense index is rebuilt per document every sweep (W:376-391) */
+            if (!o->rflag) o->rflag = (uint8_t *)malloc((size_t)(o->D > 0 ? o->D : 1) * K);
+            memset(o->rflag, 0, (size_t)(o->D > 0 ? o->D : 1) * K);
+        }
         int32_t *nk_frozen = (int32_t *)malloc((size_t)K * 4);
         int32_t *dnk = (int32_t *)malloc((size_t)K * 4);
         int64_t *order = (int64_t *)malloc((size_t)(o->D > 0 ? o->D : 1) * 8);
@@ -738,6 +787,7 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
             if (!(flags & ORC_F_DOC_ORDER)) qsort_r(order, (size_t)o->D, 8, cmp_len_desc, o->doc_off[m]);
             memset(dnk, 0, (size_t)K * 4);
             for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, flags, s, nk_frozen, dnk, cnt);
+            g_not_in_S = NULL;
             if (!(flags & ORC_F_FROZEN)) {       /* the engine flushes its n_k deltas at the end of the view pass */
                 memcpy(nk_frozen, o->n_k[m], (size_t)K * 4);
                 recount_nk_hist(o, m);           /* local doc-topic histogram (and a local n_k, replaced below)  */
@@ -762,7 +812,13 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
 /* ------------------------------------------------------------------------------------------------ */
 /* conditional distribution of one token on frozen counts                                            */
 /* ------------------------------------------------------------------------------------------------ */
+int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, double *out);
 int orc_cond_probs(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, double *out)
+{ return orc_cond_probs_q1(o, m, d, pos, p_in, engine_form, NULL, out); }
+
+/* not_in_S (K flags, may be NULL): topics the document holds that the reference's dense index lacks at this token (quirk Q1:
+ * gained earlier in the sweep); the token's own removal (W:434-471) is applied here on top of it. */
+int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, double *out)
 {   /* reference form: masses of the three buckets of W:495-538 with freshly built trees (M:2660-2691);
      * engine form: the dense net distribution.  Both from the sweep-start state of the document (Q1/Q3
      * do not matter there).  out[0..K) normalised probabilities, out[K] = share of the new-topic bucket. */
@@ -788,13 +844,16 @@ int orc_cond_probs(orc_t *o, int m, int64_t d, int pos, const double *p_in, int 
     double C = o->n_inactive == 0 ? 0 : Cdoc * coefm / K;
     double total = C;
     if (engine_form) {
+        g_not_in_S = not_in_S;
         engine_weights(o, m, w, s->nd, len, p, o->n_k[m], out);
+        g_not_in_S = NULL;
         for (int t = 0; t < K; t++) total += out[t];
     } else {
         const int32_t *row = o->n_wk[m] + (size_t)w * K;
         for (int t = 0; t < K; t++) {
             int inS = 0;
             for (int i = 0; i < M; i++) if (s->nd[i * K + t] != 0) { inS = 1; break; }
+            if (not_in_S && not_in_S[t]) inS = 0;
             double A = 0;
             if (inS) {
                 double O = 0;

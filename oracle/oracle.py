@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmvtm_oracle.so")
 
 F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER, F_FROZEN, F_BARE_TREES = 1, 2, 4, 8, 16, 32, 64, 128
+F_CHECK_RULE = 256
 
 
 def build(force=False):
@@ -62,6 +63,8 @@ def lib():
             "orc_sweep": (i32, [p, i32, u32]),
             "orc_sweep_mt": (i32, [p, i32, i32, u32]),
             "orc_cond_probs": (i32, [p, i32, i64, i32, p, i32, p]),
+            "orc_rule_violations": (C.c_longlong, [p]),
+            "orc_cond_probs_q1": (i32, [p, i32, i64, i32, p, i32, p, p]),
             "orc_engine_select": (i32, [p, i32, dbl, dbl, i32]),
             "orc_loglik": (i32, [p, p, i32]),
             "orc_check_invariants": (i64, [p]),
@@ -231,13 +234,20 @@ class Oracle:
         if rc:
             raise RuntimeError(f"orc_sweep_mt rc={rc}")
 
-    def cond_probs(self, m, doc, pos, p=None, engine_form=False):
+    def cond_probs(self, m, doc, pos, p=None, engine_form=False, not_in_S=None):
+        """not_in_S: topics the document holds that the reference's dense index lacks at this token (quirk Q1)."""
         out = np.zeros(self.K + 1, dtype=np.float64)
         pm = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
-        rc = lib().orc_cond_probs(self.h, int(m), int(doc), int(pos), _ptr(pm), int(engine_form), _ptr(out))
+        ex = None
+        if not_in_S is not None:
+            ex = np.zeros(self.K, dtype=np.uint8); ex[list(not_in_S)] = 1
+        rc = lib().orc_cond_probs_q1(self.h, int(m), int(doc), int(pos), _ptr(pm), int(engine_form), _ptr(ex), _ptr(out))
         if rc:
             raise ValueError(f"orc_cond_probs rc={rc}")
         return out
+
+    def rule_violations(self):
+        return int(lib().orc_rule_violations(self.h))
 
     def loglik(self, quirk_len2=False):
         out = np.zeros(self.M, dtype=np.float64)

@@ -325,13 +325,14 @@ def reference_optimize_beta(ref):
     return {"beta": model.fields["beta"], "betaSum": model.fields["betaSum"]}
 
 
-def reference_conditionals(ref, iteration, max_tokens=400):
+def reference_conditionals(ref, iteration, max_tokens=600):
     """north_star check (b) against the reference itself: one sweep of the jar's sampler with the GLOBAL counts frozen (deltas
     dropped, the inferencer's nut = 0 mode, W:587) while the per-token masses it computes are read out of its frame at the moment
     it draws u (W:517): dense index S, cumulative document masses (W:496-513), new-topic mass C (W:515) and the leaves of the
     word's F+tree (the B bucket).  Net conditional P(t) = (A_t + leaf_t [+ C on the first inactive topic]) / total.  A token is
     recorded only when S equals the set of topics the document currently holds (so the dead insertion code Q1 has had no
-    effect on it) together with the document's assignments at that moment, from which any implementation can rebuild n_d."""
+    effect on it) together with the document's assignments at that moment, from which any implementation can rebuild n_d.  Tokens
+    on which Q1 HAS had an effect are recorded too, with the list of held topics the index lacks (`not_in_S`)."""
     vm, K, M = ref.vm, ref.K, ref.M
     recs = []
     ref.rebuild_trees()          # fresh trees: during a sweep only two leaves per delta are refreshed (Q3), the check is on frozen, consistent state
@@ -346,7 +347,10 @@ def reference_conditionals(ref, iteration, max_tokens=400):
             S, cum, C = loc[6][:nz], loc[7][:nz], loc[25]
             counts = loc[13]
             held = sorted(t for t in range(K) if any(counts[i][t] != 0 for i in range(M)))
-            if list(S) == held:
+            q1 = list(S) != held
+            if q1 and not set(S) <= set(held):
+                raise RuntimeError("the reference's dense index holds a topic no view holds")
+            if (not q1) or len([r for r in recs if r.get("not_in_S")]) < max_tokens // 2:
                 leaves = loc[11].fields["tree"][K:2 * K]
                 mass = [float(x) for x in leaves]
                 prev = 0.0
@@ -358,8 +362,11 @@ def reference_conditionals(ref, iteration, max_tokens=400):
                     probs[ref.inactive[0]] += C / total
                 ent = ref.docs[ref.doc].fields["Assignments"]
                 zdoc = [None if ta is None else list(ta.fields["topicSequence"][3]) for ta in ent]
-                recs.append({"doc": ref.doc, "view": m, "pos": pos, "p_row": [float(x) for x in loc[17][m]], "z_doc": zdoc,
-                             "probs": probs, "new_share": C / total})
+                rec = {"doc": ref.doc, "view": m, "pos": pos, "p_row": [float(x) for x in loc[17][m]], "z_doc": zdoc,
+                       "probs": probs, "new_share": C / total}
+                if q1:      # quirk Q1 at work: topics the document holds that the reference's dense index lacks (gained this sweep)
+                    rec["not_in_S"] = [t for t in held if t not in set(S)]
+                recs.append(rec)
         return r
     vm.shims["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"] = nd
     try:

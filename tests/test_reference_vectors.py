@@ -120,9 +120,11 @@ def _state_with_doc(case, views, rec):
 def test_conditionals_match_reference_bytecode(oracle_mod):
     """north_star check (b) for the ORACLE: per-token conditional distributions on frozen counts as the reference's sampler
     bytecode computed them (its S / cumulative masses / C / F+tree leaves read out of the running frame) vs the oracle's
-    three-bucket masses: 1e-9 relative / 1e-15 absolute."""
+    three-bucket masses and its engine-form dense distribution: 1e-9 relative / 1e-15 absolute.  Tokens on which quirk Q1 has
+    had an effect (topics gained earlier in the sweep are missing from the reference's dense index) are included: the vectors
+    name those topics (`not_in_S`) and both forms must drop their document terms exactly as the reference does."""
     O = oracle_mod
-    n = 0
+    n = n_q1 = 0
     for case, K, Vs, views in _conditional_cases():
         M = len(Vs)
         o = O.Oracle(K, Vs, views, seed=case["seed"])
@@ -130,18 +132,20 @@ def test_conditionals_match_reference_bytecode(oracle_mod):
                     betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
         o.set_assignments([np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]])
         frozen = [o.get_counts(m) for m in range(M)]
-        for rec in case["conditionals"][::3]:
+        for rec in case["conditionals"][::3] + [r for r in case["conditionals"] if r.get("not_in_S")][::2]:
             o.set_assignments(_state_with_doc(case, views, rec))
             for m in range(M):
                 o.set_counts(m, *frozen[m])
             o.rebuild_trees()
             p = np.eye(M); p[rec["view"]] = rec["p_row"]
-            got = o.cond_probs(rec["view"], rec["doc"], rec["pos"], p=p)
-            # (the reference's document masses are recovered as differences of its cumulative array: absolute error ~1e-16)
-            assert np.allclose(got[:K], rec["probs"], rtol=1e-9, atol=1e-15), (case["name"], rec["doc"], rec["view"], rec["pos"])
-            assert got[K] == pytest.approx(rec["new_share"], rel=1e-9, abs=1e-15)
+            for engine_form in (False, True):       # the three-bucket masses and the engine's dense net distribution
+                got = o.cond_probs(rec["view"], rec["doc"], rec["pos"], p=p, engine_form=engine_form, not_in_S=rec.get("not_in_S"))
+                # (the reference's document masses are recovered as differences of its cumulative array: absolute error ~1e-16)
+                assert np.allclose(got[:K], rec["probs"], rtol=1e-9, atol=1e-15), (case["name"], rec["doc"], rec["view"], rec["pos"], engine_form)
+                assert got[K] == pytest.approx(rec["new_share"], rel=1e-9, abs=1e-15)
             n += 1
-    assert n > 200
+            n_q1 += bool(rec.get("not_in_S"))
+    assert n > 200 and n_q1 > 100      # incl. tokens on which quirk Q1 (dead insertion code) changes the distribution
 
 
 def test_counts_histograms_and_optimize_beta_match_reference_bytecode(oracle_mod):
@@ -195,3 +199,21 @@ def test_oracle_reproduces_reference_trajectory(oracle_mod):
             assert np.allclose(o.loglik(True), marks[it], rtol=1e-12), it
     for m in range(M):
         assert np.array_equal(o.get_assignments(m), np.array(g["z_final"][m], dtype=np.int32))
+
+
+def test_flag_rule_equals_reference_dense_index(oracle_mod):
+    """The engine's Q1 mode does not keep the reference's sorted list S; it keeps one flag per topic: "left the index (no view held
+    it any more) or was gained while absent" -- and takes S = {held and not flagged}.  Inside the reference-faithful oracle (which
+    reproduces the reference's sampler bytecode token for token) that rule is run next to the real list at every token of
+    several sweeps: they must never disagree."""
+    from helpers import random_corpus
+    O = oracle_mod
+    for K, Vs, means, D in [(12, [30, 10, 8], [7, 3, 2], 200), (37, [120, 30], [25, 5], 150), (50, [300], [6], 300)]:
+        views = random_corpus(K, D, K, Vs, means)
+        o = O.Oracle(K, Vs, views, seed=3)
+        o.init_assignments(); o.rebuild_trees()
+        for it in range(1, 7):
+            if len(Vs) > 1:
+                o.set_hyper(p_a=np.full((len(Vs), len(Vs)), 0.8))
+            o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT | O.F_CHECK_RULE)
+        assert o.rule_violations() == 0
