@@ -1170,7 +1170,9 @@ def test_engine_conditionals_match_reference_bytecode(engine_lib):
         for m in range(M):
             e.set_assignments(m, frozen_z[m])
         frozen = [e.get_counts(m) for m in range(M)]
-        for rec in case["conditionals"][::2]:
+        # tokens on which quirk Q1 has had no effect (the vectors also hold Q1-affected tokens, marked by `not_in_S`: on those the
+        # engine's documented index "topics the document holds" differs from the reference's by design)
+        for rec in [r for r in case["conditionals"] if not r.get("not_in_S")][::2]:
             zs = [z.copy() for z in frozen_z]
             for m, zd in enumerate(rec["z_doc"]):
                 if zd is not None:
