@@ -16,10 +16,35 @@ F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_OR
 F_CHECK_RULE = 256
 
 
+_STAMP = _SO + ".cpuflags"
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    return set(ln.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def _built_for_this_cpu():
+    """The Makefile compiles with -march=native (BASELINE.md's CPU arm), and the built file travels with the repo snapshot: if the
+    host it lands on lacks an ISA extension of the host it was built on, rebuild there instead of dying on an illegal instruction."""
+    if not os.path.exists(_STAMP):
+        return True
+    with open(_STAMP) as f:
+        return set(f.read().split()) <= _cpu_flags()
+
+
 def build(force=False):
     src = os.path.join(_HERE, "mvtm_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src) or not _built_for_this_cpu():
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        with open(_STAMP, "w") as f:
+            f.write(" ".join(sorted(_cpu_flags())))
     return _SO
 
 
@@ -29,7 +54,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
+        if not os.path.exists(_SO) or not _built_for_this_cpu():
             build()
         L = C.CDLL(_SO)
         p, i32, i64, u64, dbl, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_uint
