@@ -233,6 +233,16 @@ int mvtm_get_hyper_full(mvtm_handle *h, double *alpha, double *alpha_sum, double
 int mvtm_test_sampler(uint64_t seed, int32_t which, double a, double b, int32_t n, double *out);
 double mvtm_test_learn_symmetric_concentration(const int64_t *count_hist, int32_t n_count, const int64_t *length_hist,
                                                int32_t n_length, int32_t num_dimensions, double current);
+/* optimizeDP (which & MVTM_OPT_DP, M:2440-2591) then optimizeGamma (which & MVTM_OPT_GAMMA, M:2369-2438) on plain host arrays with
+ * SCRIPTED draws -- the same code mvtm_optimize_hyper runs, without a device, so that the arguments of every sampler call and the
+ * resulting alpha / gamma can be compared with the reference's bytecode fed the same draws (tests/test_optim_host.py).
+ * hist[m]: K x stride[m] bins of topicDocCounts; lencnt[m]: n_len[m] bins of docLengthCounts; alpha: M x (K+1);
+ * scal = { gammaRoot, rootTablesCnt } (in/out); script: one value per draw in call order (Gamma(a,1), Beta, Bernoulli, Antoniak);
+ * arg_log: 3 doubles (kind 1..4, a, b) per consumed draw; *n_used: draws consumed.  MVTM_ERR_ARG when the script is too short. */
+int mvtm_test_hyper_core(int32_t M, int32_t K, uint32_t which, const int64_t *const *hist, const int32_t *stride,
+                         const int64_t *const *lencnt, const int32_t *n_len, double *alpha, double *alpha_sum, double *gamma,
+                         double *gamma_view, double *tables_cnt, double *scal, int32_t *inactive, int32_t *n_inactive,
+                         const double *script, int64_t script_len, double *arg_log, int64_t *n_used);
 
 /* Build information: "sm_100a", kernel variants compiled in. */
 const char *mvtm_build_info(void);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mvtm_get_hyper_full": (_i32, [_vp] + [_vp] * 11),
     "mvtm_test_sampler": (_i32, [C.c_uint64, _i32, C.c_double, C.c_double, _i32, _vp]),
     "mvtm_test_learn_symmetric_concentration": (C.c_double, [_vp, _i32, _vp, _i32, _i32, C.c_double]),
+    "mvtm_test_hyper_core": (_i32, [_i32, _i32, C.c_uint32] + [_vp] * 13 + [C.c_int64, _vp, _vp]),
     "mvtm_build_info": (C.c_char_p, []),
 }
 

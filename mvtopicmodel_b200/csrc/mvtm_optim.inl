@@ -13,6 +13,16 @@ namespace {
 
 struct OptRng {
     uint64_t seed; uint32_t iteration; uint64_t n;
+    // test hook (mvtm_test_hyper_core): when `script` is set, every sampler call returns the next scripted value instead of drawing,
+    // and records (kind, a, b) -- kind 1 Gamma(a,1), 2 Beta(a,b), 3 Bernoulli(a), 4 Antoniak(a, n=b) -- so that the argument of
+    // every draw of optimizeDP / optimizeGamma can be compared with what the reference's bytecode passes to its samplers
+    const double *script = nullptr; long long script_len = 0, script_pos = 0; double *arg_log = nullptr; bool overrun = false;
+    double take(double kind, double a, double b)
+    {
+        if (script_pos >= script_len) { overrun = true; script_pos++; return 1.0; }
+        if (arg_log) { arg_log[3 * script_pos] = kind; arg_log[3 * script_pos + 1] = a; arg_log[3 * script_pos + 2] = b; }
+        return script[script_pos++];
+    }
     static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
     {
         for (int r = 0; r < 10; r++) {
@@ -40,6 +50,7 @@ struct OptRng {
 static double rand_gamma(OptRng &g, double shape)
 {   // Gamma(shape, 1).  shape <= 0 -> 0 like KR:298-300
     if (!(shape > 0.0)) return 0.0;
+    if (g.script) return g.take(1, shape, 0);
     if (shape < 1.0) return rand_gamma(g, shape + 1.0) * std::pow(g.next_open(), 1.0 / shape);
     const double d = shape - 1.0 / 3.0, c = 1.0 / std::sqrt(9.0 * d);
     for (;;) {
@@ -53,13 +64,15 @@ static double rand_gamma(OptRng &g, double shape)
 }
 static double rand_beta(OptRng &g, double a, double b)
 {   // KR:267-271: first component of a 2-dimensional Dirichlet drawn as normalised Gammas
+    if (g.script) return g.take(2, a, b);
     const double x = rand_gamma(g, a), y = rand_gamma(g, b);
     return x / (x + y);
 }
-static int rand_bernoulli(OptRng &g, double p) { return g.next() < p ? 1 : 0; }   // KR:789-795
+static int rand_bernoulli(OptRng &g, double p) { return g.script ? (int)g.take(3, p, 0) : (g.next() < p ? 1 : 0); }   // KR:789-795
 static int rand_antoniak(OptRng &g, double alpha, int n)
 {   // number of tables of a CRP(alpha) after n customers (Antoniak 1974), KS:1089-1110
     if (n > 20000) throw std::range_error("MAXSTIRLING");           // KS:1023: the reference's table ends here
+    if (g.script) return (int)g.take(4, alpha, n);
     int m = 0;
     for (int i = 0; i < n; i++) m += rand_bernoulli(g, alpha / (alpha + i));
     return m < 1 ? 1 : m;
@@ -267,17 +280,29 @@ static int optimize_p(mvtm_handle *h)
     return MVTM_OK;
 }
 
-static int optimize_dp(mvtm_handle *h, OptRng &g)
+// The values optimizeDP / optimizeGamma read and write (M:2369-2591), detached from the handle: the engine points this at its own
+// fields, the CPU test hook at plain arrays -- one body of code for both.
+struct HyperState {
+    int M, K;
+    double *alpha;                       // M x (K+1)
+    double *alphaSum, *gamma, *gammaView, *tablesCnt;   // [M]
+    double *gammaRoot, *rootTablesCnt;
+    std::vector<int> *inactive;
+};
+
+// hist_of(m, hist, stride): topicDocCounts of view m as K rows of `stride` bins (bin c = documents holding the topic c times)
+template <class HistFn>
+static int optimize_dp_core(HyperState &S, HistFn &&hist_of, OptRng &g)
 {   // M:2440-2591
-    const int M = h->M, K = h->K;
+    const int M = S.M, K = S.K;
     std::vector<std::vector<double>> mk((size_t)M, std::vector<double>((size_t)K + 1, 0.0));
     std::vector<double> mk_root((size_t)K + 1, 0.0);
     std::vector<char> active((size_t)K, 0);
     std::vector<long long> hist; int stride = 0;
     for (int m = 0; m < M; m++) {
-        if (int rc = doc_topic_hist_host(h, m, hist, stride)) return rc;
+        if (int rc = hist_of(m, hist, stride)) return rc;
         for (int t = 0; t < K; t++) {
-            const double ga = h->gamma[m] * h->alpha[(size_t)m * (K + 1) + t];
+            const double ga = S.gamma[m] * S.alpha[(size_t)m * (K + 1) + t];
             for (int i = 1; i < stride; i++) {
                 const long long cnt = hist[(size_t)t * stride + i];
                 if (cnt <= 0) continue;
@@ -294,69 +319,91 @@ static int optimize_dp(mvtm_handle *h, OptRng &g)
         for (int m = 0; m < M; m++) {
             if (mk[m][t] > 1) {
                 int tbl;
-                try { tbl = rand_antoniak(g, h->gammaRoot, (int)std::ceil(mk[m][t])); } catch (...) { tbl = 1; }
+                try { tbl = rand_antoniak(g, *S.gammaRoot, (int)std::ceil(mk[m][t])); } catch (...) { tbl = 1; }
                 mk_root[t] += tbl;
             } else if (mk[m][t] == 1) mk_root[t] += 1;
         }
-    mk_root[(size_t)K] = h->gammaRoot;                                                          // M:2520
-    h->rootTablesCnt = std::accumulate(mk_root.begin(), mk_root.end(), 0.0);
+    mk_root[(size_t)K] = *S.gammaRoot;                                                          // M:2520
+    *S.rootTablesCnt = std::accumulate(mk_root.begin(), mk_root.end(), 0.0);
     std::vector<double> v((size_t)K + 1, 0.0), tt;
     for (int s = 0; s < 10; s++) { sample_dirichlet(g, mk_root, tt); for (int k = 0; k <= K; k++) v[k] += tt[k] / 10.0; }
-    h->inactive.clear();
-    for (int t = 0; t < K; t++) if (!active[(size_t)t]) h->inactive.push_back(t);
+    S.inactive->clear();
+    for (int t = 0; t < K; t++) if (!active[(size_t)t]) S.inactive->push_back(t);
     for (int m = 0; m < M; m++) {
-        for (int t = 0; t < K; t++) mk[m][t] += v[t] * h->gammaRoot;                            // M:2553
-        mk[m][(size_t)K] = h->gammaView[m] + v[(size_t)K] * h->gammaRoot;                       // M:2557
-        h->tablesCnt[m] = std::accumulate(mk[m].begin(), mk[m].end(), 0.0);
-        double *al = &h->alpha[(size_t)m * (K + 1)];
+        for (int t = 0; t < K; t++) mk[m][t] += v[t] * *S.gammaRoot;                            // M:2553
+        mk[m][(size_t)K] = S.gammaView[m] + v[(size_t)K] * *S.gammaRoot;                        // M:2557
+        S.tablesCnt[m] = std::accumulate(mk[m].begin(), mk[m].end(), 0.0);
+        double *al = &S.alpha[(size_t)m * (K + 1)];
         std::fill(al, al + K + 1, 0.0);
         double asum = 0.0;
         for (int s = 0; s < 10; s++) { sample_dirichlet(g, mk[m], tt); for (int k = 0; k <= K; k++) { al[k] += tt[k] / 10.0; asum += tt[k] / 10.0; } }
-        h->alphaSum[m] = asum;
+        S.alphaSum[m] = asum;
     }
     return MVTM_OK;
 }
 
-static int optimize_gamma(mvtm_handle *h, OptRng &g)
+// lencnt_of(m, lencnt): docLengthCounts of view m (M:626), bin j = documents of length j (all ranks)
+template <class LenFn>
+static int optimize_gamma_core(HyperState &S, LenFn &&lencnt_of, OptRng &g)
 {   // M:2369-2438 (Escobar & West 1995 / Teh et al. 2006 auxiliary-variable updates)
-    const int K = h->K;
+    const int K = S.K;
     const double aalpha = 5, balpha = 0.1, agamma = 5, bgamma = 0.1;
     const int R = 10;
     for (int r = 0; r < R; r++) {
-        const double eta = rand_beta(g, h->gammaRoot + 1, h->rootTablesCnt);
+        const double eta = rand_beta(g, *S.gammaRoot + 1, *S.rootTablesCnt);
         const double bloge = bgamma - std::log(eta);
-        const double pie = 1.0 / (1.0 + (h->rootTablesCnt * bloge / (agamma + K - 1)));
+        const double pie = 1.0 / (1.0 + (*S.rootTablesCnt * bloge / (agamma + K - 1)));
         const int u = rand_bernoulli(g, pie);
-        h->gammaRoot = rand_gamma(g, agamma + K - 1 + u) * (1.0 / bloge);
+        *S.gammaRoot = rand_gamma(g, agamma + K - 1 + u) * (1.0 / bloge);
     }
-    for (int m = 0; m < h->M; m++) {
+    std::vector<long long> lencnt;
+    for (int m = 0; m < S.M; m++) {
+        if (int rc = lencnt_of(m, lencnt)) return rc;
+        for (int r = 0; r < R; r++) {
+            const double prev = S.gamma[m];
+            const double eta = rand_beta(g, S.gammaView[m] + 1, S.tablesCnt[m]);
+            const double bloge = bgamma - std::log(eta);
+            const double pie = 1.0 / (1.0 + (S.tablesCnt[m] * bloge / (agamma + K - 1)));
+            const int u = rand_bernoulli(g, pie);
+            S.gammaView[m] = rand_gamma(g, agamma + K - 1 + u) * (1.0 / bloge);
+            double qs = 0.0, qw = 0.0;
+            for (size_t j = 1; j < lencnt.size(); j++)            // j = 0: Bernoulli(0) = 0 and log Beta(.,0) = log 1 = 0
+                for (long long i = 0; i < lencnt[j]; i++) {
+                    qs += rand_bernoulli(g, (double)j / ((double)j + S.gamma[m]));
+                    qw += std::log(rand_beta(g, S.gamma[m] + 1, (double)j));
+                }
+            S.gamma[m] = rand_gamma(g, aalpha + S.tablesCnt[m] - qs) * (1.0 / (balpha - qw));
+            if (S.gamma[m] == 0 || !std::isfinite(S.gamma[m])) S.gamma[m] = prev;              // M:2425-2428
+        }
+    }
+    return MVTM_OK;
+}
+
+static HyperState hyper_state_of(mvtm_handle *h)
+{
+    return HyperState{ h->M, h->K, h->alpha.data(), h->alphaSum, h->gamma, h->gammaView, h->tablesCnt, &h->gammaRoot, &h->rootTablesCnt, &h->inactive };
+}
+
+static int optimize_dp(mvtm_handle *h, OptRng &g)
+{
+    HyperState S = hyper_state_of(h);
+    return optimize_dp_core(S, [h](int m, std::vector<long long> &hist, int &stride) { return doc_topic_hist_host(h, m, hist, stride); }, g);
+}
+
+static int optimize_gamma(mvtm_handle *h, OptRng &g)
+{
+    HyperState S = hyper_state_of(h);
+    return optimize_gamma_core(S, [h](int m, std::vector<long long> &lencnt) -> int {
         ViewDev &v = h->v[m];
         int gml = 0;
         if (int rc = global_max_len(h, m, gml)) return rc;
-        std::vector<long long> lencnt((size_t)gml + 1, 0);                                // docLengthCounts, M:626 (all ranks)
+        lencnt.assign((size_t)gml + 1, 0);                                                // docLengthCounts, M:626 (all ranks)
         for (long long d = 0; d < h->D; d++) {
             const long long len = v.h_doc_off[(size_t)d + 1] - v.h_doc_off[(size_t)d];
             if (len > 0 || v.h_present[(size_t)d]) lencnt[(size_t)len]++;
         }
-        if (int rc = reduce_stats(h, 0, lencnt.data(), (long long)lencnt.size(), nullptr, 0)) return rc;
-        for (int r = 0; r < R; r++) {
-            const double prev = h->gamma[m];
-            const double eta = rand_beta(g, h->gammaView[m] + 1, h->tablesCnt[m]);
-            const double bloge = bgamma - std::log(eta);
-            const double pie = 1.0 / (1.0 + (h->tablesCnt[m] * bloge / (agamma + K - 1)));
-            const int u = rand_bernoulli(g, pie);
-            h->gammaView[m] = rand_gamma(g, agamma + K - 1 + u) * (1.0 / bloge);
-            double qs = 0.0, qw = 0.0;
-            for (size_t j = 1; j < lencnt.size(); j++)            // j = 0: Bernoulli(0) = 0 and log Beta(.,0) = log 1 = 0
-                for (long long i = 0; i < lencnt[j]; i++) {
-                    qs += rand_bernoulli(g, (double)j / ((double)j + h->gamma[m]));
-                    qw += std::log(rand_beta(g, h->gamma[m] + 1, (double)j));
-                }
-            h->gamma[m] = rand_gamma(g, aalpha + h->tablesCnt[m] - qs) * (1.0 / (balpha - qw));
-            if (h->gamma[m] == 0 || !std::isfinite(h->gamma[m])) h->gamma[m] = prev;           // M:2425-2428
-        }
-    }
-    return MVTM_OK;
+        return reduce_stats(h, 0, lencnt.data(), (long long)lencnt.size(), nullptr, 0);
+    }, g);
 }
 
 static int optimize_beta(mvtm_handle *h)
@@ -452,6 +499,33 @@ extern "C" int mvtm_test_sampler(uint64_t seed, int32_t which, double a, double 
         }
     }
     return MVTM_OK;
+}
+// optimizeDP (which & MVTM_OPT_DP) then optimizeGamma (which & MVTM_OPT_GAMMA) on plain host arrays with SCRIPTED draws: the same
+// core the engine runs, no device.  hist[m] is K x stride[m] (topicDocCounts), lencnt[m] has n_len[m] bins (docLengthCounts).
+// scal = { gammaRoot, rootTablesCnt } in/out.  arg_log receives 3 doubles per consumed draw; *n_used the number consumed.
+// Returns MVTM_ERR_ARG when the script is too short.
+extern "C" int mvtm_test_hyper_core(int32_t M, int32_t K, uint32_t which, const int64_t *const *hist, const int32_t *stride,
+                                    const int64_t *const *lencnt, const int32_t *n_len, double *alpha, double *alpha_sum, double *gamma,
+                                    double *gamma_view, double *tables_cnt, double *scal, int32_t *inactive, int32_t *n_inactive,
+                                    const double *script, int64_t script_len, double *arg_log, int64_t *n_used)
+{
+    if (M < 1 || K < 1 || !alpha || !alpha_sum || !gamma || !gamma_view || !tables_cnt || !scal || !script) return MVTM_ERR_ARG;
+    OptRng g{ 0, 0u, 0 };
+    g.script = script; g.script_len = script_len; g.arg_log = arg_log;
+    std::vector<int> inact;
+    HyperState S{ M, K, alpha, alpha_sum, gamma, gamma_view, tables_cnt, &scal[0], &scal[1], &inact };
+    if (which & MVTM_OPT_DP) {
+        if (!hist || !stride) return MVTM_ERR_ARG;
+        optimize_dp_core(S, [&](int m, std::vector<long long> &h, int &st) { st = stride[m]; h.assign(hist[m], hist[m] + (size_t)K * st); return 0; }, g);
+        if (inactive) for (size_t i = 0; i < inact.size(); i++) inactive[i] = inact[i];
+        if (n_inactive) *n_inactive = (int32_t)inact.size();
+    }
+    if (which & MVTM_OPT_GAMMA) {
+        if (!lencnt || !n_len) return MVTM_ERR_ARG;
+        optimize_gamma_core(S, [&](int m, std::vector<long long> &l) { l.assign(lencnt[m], lencnt[m] + n_len[m]); return 0; }, g);
+    }
+    if (n_used) *n_used = g.script_pos;
+    return g.overrun ? MVTM_ERR_ARG : MVTM_OK;
 }
 extern "C" double mvtm_test_learn_symmetric_concentration(const int64_t *count_hist, int32_t n_count, const int64_t *length_hist, int32_t n_length,
                                                           int32_t num_dimensions, double current)
