@@ -1243,7 +1243,7 @@ def test_engine_trajectory_matches_reference_bytecode(engine_lib, oracle_mod):
     (tests/test_reference_vectors.py) and is therefore the reference with other random numbers.  So the comparison is between
     ENSEMBLES: the jar's trajectory plus five reference-faithful runs vs six engine runs; the means must agree within 1 % (text
     view; 3 % = three standard errors on the tiny side view) at every checkpoint, and on the text view every engine run must
-    stay within the band the reference runs span, widened by 1 %."""
+    stay within 1 % + four reference standard deviations of the reference mean."""
     import json
     from mvtopicmodel_b200 import Engine
     O = oracle_mod
@@ -1288,6 +1288,8 @@ def test_engine_trajectory_matches_reference_bytecode(engine_lib, oracle_mod):
     # spread of +-2.6 % in the reference itself, so the standard error of a six-run mean is ~1 % there: it is held to 3 standard
     # errors (observed: 0.1-1.4 %)
     assert np.all(rel[:, 0] < REL_TOL_LL) and np.all(rel[:, 1:] < 3 * REL_TOL_LL), rel
-    # no single engine run leaves the band the reference runs span on the text view (widened by 1 %)
-    lo, hi = ref_runs.min(0)[:, 0], ref_runs.max(0)[:, 0]
-    assert np.all(eng_runs[:, :, 0] >= lo - REL_TOL_LL * np.abs(lo)) and np.all(eng_runs[:, :, 0] <= hi + REL_TOL_LL * np.abs(hi))
+    # no single engine run strays from the reference mean on the text view by more than 1 % plus four run-to-run standard
+    # deviations of the reference itself (pooled over the checkpoints: ~0.35 %; the known engine runs stay within 0.9 %)
+    sd_rel = np.sqrt(np.mean((ref_runs[:, :, 0].std(0, ddof=1) / np.abs(ref_mean[:, 0])) ** 2))
+    dev = np.abs(eng_runs[:, :, 0] - ref_mean[:, 0]) / np.abs(ref_mean[:, 0])
+    assert dev.max() < REL_TOL_LL + 4 * sd_rel, (dev.max(), sd_rel)
