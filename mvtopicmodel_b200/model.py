@@ -185,6 +185,27 @@ class FastQMVWVParallelTopicModel:
     def getTopicAssignments(self, m):
         return self.engine.get_assignments(m)
 
+    def docLengthCounts(self, m):
+        """Histogram of document lengths of view m (M:107, filled at M:626): bin j = documents of length j that have the view."""
+        off = self.views[m][0]
+        lens = (off[1:] - off[:-1])[np.asarray(self.present[m], dtype=bool) | ((off[1:] - off[:-1]) > 0)]
+        return np.bincount(lens)
+
+    def getTopicProbabilities(self, instance, modality=None):
+        """M:2134-2171.  getTopicProbabilities(instanceID) -> one smoothed topic distribution per view of that training document
+        (a view the document lacks raises, as the reference's null Assignments entry does);
+        getTopicProbabilities(topics, modality) -> the distribution of one topic sequence (e.g. from the inferencer)."""
+        if modality is not None:
+            return state_io.topic_probabilities(instance, self.numTopics, self.gamma[modality], self.alpha[modality])
+        d, out = int(instance), []
+        for m in range(self.numModalities):
+            off = self.views[m][0]
+            if not (self.present[m][d] or off[d + 1] > off[d]):
+                raise ValueError(f"document {d} has no view {m}")
+            z = self.engine.get_assignments(m)[off[d]:off[d + 1]]
+            out.append(state_io.topic_probabilities(z, self.numTopics, self.gamma[m], self.alpha[m]))
+        return out
+
     def getInferencer(self):
         """M:3457-3463"""
         return FastQMVWVTopicInferencer(self)

@@ -212,3 +212,13 @@ def read_state(inp, views, present=None):
     if advance():
         raise ValueError("state file ended before the corpus did")
     return zs, header
+
+
+def topic_probabilities(topics, num_topics, gamma_m, alpha_m):
+    """getTopicProbabilities(LabelSequence topics, byte modality), M:2148-2171: counts of the document's current assignments plus
+    gamma[m] * alpha[m][t], normalised over the K topics (unassigned tokens, -1, are skipped: they hold no topic)."""
+    import numpy as np
+    t = np.asarray(topics, dtype=np.int64)
+    d = np.bincount(t[t >= 0], minlength=num_topics).astype(np.float64)[:num_topics]
+    d += float(gamma_m) * np.asarray(alpha_m, dtype=np.float64)[:num_topics]
+    return d / d.sum()

@@ -182,3 +182,22 @@ def test_simple_tokenizer_matches_mallet_bytecode():
         n += len(toks)
         h.update(("\x1f".join(toks) + "\x1e").encode("utf-8"))
     assert n == g["tokens"] and h.hexdigest() == g["sha256_of_token_stream"]
+
+
+def test_topic_probabilities_and_doc_length_counts():
+    """getTopicProbabilities (M:2148-2171) and docLengthCounts (M:107/626) of the mirror; no device needed for these readers."""
+    from mvtopicmodel_b200 import state_io
+    from mvtopicmodel_b200.model import FastQMVWVParallelTopicModel
+    K = 4
+    alpha = np.array([0.1, 0.2, 0.3, 0.4, 0.05])                       # K+1 slots: the new-topic slot takes no part (M:2160-2163)
+    p = state_io.topic_probabilities([2, 2, 0, -1, 2], K, 1.5, alpha)
+    want = np.array([1 + 0.15, 0.30, 3 + 0.45, 0.60]); want /= want.sum()
+    assert np.allclose(p, want, rtol=1e-15) and abs(p.sum() - 1) < 1e-15
+    assert np.allclose(state_io.topic_probabilities([], K, 2.0, alpha), alpha[:K] / alpha[:K].sum())
+    mdl = FastQMVWVParallelTopicModel(K, 2)
+    mdl.views = [(np.array([0, 3, 3, 5, 9]), None), (np.array([0, 0, 2, 2, 3]), None)]
+    mdl.present = [np.array([1, 1, 1, 1], dtype=np.uint8), np.array([0, 1, 0, 1], dtype=np.uint8)]
+    assert mdl.docLengthCounts(0).tolist() == [1, 0, 1, 1, 1]           # lengths 3, 0, 2, 4: the empty document counts in bin 0
+    assert mdl.docLengthCounts(1).tolist() == [0, 1, 1]                 # only the documents that have the view
+    q = mdl.getTopicProbabilities(np.array([1, 1, 3]), 1)
+    assert np.allclose(q, state_io.topic_probabilities([1, 1, 3], K, mdl.gamma[1], mdl.alpha[1]))
