@@ -201,3 +201,20 @@ def test_topic_probabilities_and_doc_length_counts():
     assert mdl.docLengthCounts(1).tolist() == [0, 1, 1]                 # only the documents that have the view
     q = mdl.getTopicProbabilities(np.array([1, 1, 3]), 1)
     assert np.allclose(q, state_io.topic_probabilities([1, 1, 3], K, mdl.gamma[1], mdl.alpha[1]))
+
+
+def test_sorted_words_match_reference_bytecode():
+    """state_io.sorted_words / top_words vs getSortedWords (M:1792-1809) executed from the reference's jar, ties ordered by MALLET's
+    own IDSorter.compareTo bytecode (tests/golden/make_reference_sorted_words_vectors.py)."""
+    import json
+    from mvtopicmodel_b200 import state_io
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sorted_words.json")))
+    n_ties = 0
+    for case in g["cases"]:
+        nwk = np.array(case["typeTopicCounts"])
+        for k in range(case["K"]):
+            want = [tuple(x) for x in case["sorted"][k]]
+            assert state_io.sorted_words(nwk, k) == want
+            n_ties += sum(1 for a, b in zip(want, want[1:]) if a[1] == b[1])
+        assert state_io.top_words(nwk, 5) == [[str(t) for t, _ in s[:5]] for s in case["sorted"]]
+    assert n_ties > 100                                  # the tie rule (larger type id first) is really exercised
