@@ -58,6 +58,50 @@ def main():
         res = vm.call(MC, "getSortedWords", "(I)Ljava/util/ArrayList;", [model, 1])
         srt = [[[o.fields["id"], int(o.fields["p"])] for o in ts.fields["items"]] for ts in res.fields["items"]]
         out["cases"].append({"V": V, "K": K, "typeTopicCounts": nwk.tolist(), "sorted": srt})
+    # displayTopWords(numWords, numLabels, usingNewLines) (M:1851-1888) from the same jar: real string building, numbers through the
+    # mirror's NumberFormat restatement, words as their type ids.  The jar predates the source in ONE character: its one-line mode
+    # separates words by " " where the source (and the mirror) writes "; " -- recorded as is.
+    sys.path.insert(0, ROOT)
+    from mvtopicmodel_b200 import state_io
+
+    def sb_init(loc, r, a, pc):
+        r.fields["s"] = ""
+
+    def sb_append(loc, r, a, pc):
+        v = a[0]
+        r.fields["s"] += v if isinstance(v, str) else str(v)
+        return r
+    sh["java/lang/StringBuilder.<init>:()V"] = sb_init
+    for d in ("(I)", "(Ljava/lang/String;)", "(Ljava/lang/Object;)"):
+        sh["java/lang/StringBuilder.append:" + d + "Ljava/lang/StringBuilder;"] = sb_append
+    sh["java/lang/StringBuilder.toString:()Ljava/lang/String;"] = lambda loc, r, a, pc: r.fields["s"]
+    sh["java/text/NumberFormat.format:(D)Ljava/lang/String;"] = lambda loc, r, a, pc: state_io.java_number_format(a[0])
+    sh["cc/mallet/types/Alphabet.lookupObject:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: str(a[0])
+    sh["java/util/ArrayList.get:(I)Ljava/lang/Object;"] = lambda loc, r, a, pc: r.fields["items"][a[0]]
+    sh["java/lang/Byte.valueOf:(B)Ljava/lang/Byte;"] = lambda loc, r, a, pc: a[0]
+    sh["java/lang/Byte.byteValue:()B"] = lambda loc, r, a, pc: r
+
+    class _It:
+        def __init__(self, lst):
+            self.l, self.i = lst, 0
+    sh["java/util/TreeSet.iterator:()Ljava/util/Iterator;"] = lambda loc, r, a, pc: _It(r.fields["items"])
+    sh["java/util/Iterator.hasNext:()Z"] = lambda loc, r, a, pc: int(r.i < len(r.l))
+
+    def _next(loc, r, a, pc):
+        v = r.l[r.i]; r.i += 1
+        return v
+    sh["java/util/Iterator.next:()Ljava/lang/Object;"] = _next
+    out["displayTopWords"] = []
+    V, K = 30, 4
+    nwk = [(rng.integers(0, 6, size=(V, K)) * (rng.random((V, K)) < 0.5)).astype(int) for _ in range(2)]
+    alpha = rng.dirichlet(np.full(K + 1, 0.8), size=2)
+    model = JObject(MC)
+    model.fields.update(dict(numTopics=K, numModalities=2, numTypes=[V, V], typeTopicCounts=[t.tolist() for t in nwk],
+                             alpha=alpha.tolist(), formatter=("nf",), alphabet=[("alphabet", 0), ("alphabet", 1)]))
+    for num_words, new_lines in [(1, 0), (4, 0), (4, 1), (100, 1)]:
+        text = vm.call(MC, "displayTopWords", "(IIZ)Ljava/lang/String;", [model, num_words, 0, new_lines])
+        out["displayTopWords"].append({"numWords": num_words, "usingNewLines": bool(new_lines), "text": text})
+    out["displayTopWords_state"] = {"typeTopicCounts": [t.tolist() for t in nwk], "alpha": alpha.tolist()}
     json.dump(out, open(os.path.join(HERE, "reference_sorted_words.json"), "w"))
     print("reference_sorted_words.json:", [(c["V"], c["K"], [len(s) for s in c["sorted"]]) for c in out["cases"]], "bytecode steps", vm.steps)
 

@@ -218,3 +218,20 @@ def test_sorted_words_match_reference_bytecode():
             n_ties += sum(1 for a, b in zip(want, want[1:]) if a[1] == b[1])
         assert state_io.top_words(nwk, 5) == [[str(t) for t, _ in s[:5]] for s in case["sorted"]]
     assert n_ties > 100                                  # the tie rule (larger type id first) is really exercised
+
+
+def test_display_top_words_matches_reference_bytecode():
+    """display_top_words vs displayTopWords (M:1851-1888) executed from the reference's jar: numWords - 1 words per topic and view
+    (the loop starts at word = 1), view after view on one line, counts through NumberFormat.  The shipped jar is older than the
+    source in one character: its one-line mode separates words by " ", the source and the mirror by "; "."""
+    import json
+    from mvtopicmodel_b200 import state_io
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sorted_words.json")))
+    st = g["displayTopWords_state"]
+    nwk, alpha = [np.array(t) for t in st["typeTopicCounts"]], np.array(st["alpha"])
+    assert len(g["displayTopWords"]) >= 4
+    for rec in g["displayTopWords"]:
+        got = state_io.display_top_words(nwk, alpha, [str, str], rec["numWords"], using_new_lines=rec["usingNewLines"])
+        if not rec["usingNewLines"]:
+            got = got.replace("; ", " ")
+        assert got == rec["text"], rec["numWords"]
