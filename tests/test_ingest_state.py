@@ -235,3 +235,27 @@ def test_display_top_words_matches_reference_bytecode():
         if not rec["usingNewLines"]:
             got = got.replace("; ", " ")
         assert got == rec["text"], rec["numWords"]
+
+
+def test_text_writers_match_reference_bytecode():
+    """write_state / write_type_topic_counts / write_topic_word_weights vs printState (M:3276-3320), printTypeTopicCounts
+    (M:2076-2102) and printTopicWordWeights (M:2113-2129) executed from the reference's jar over a two-view state (sources, a type
+    with a blank, zero counts): identical text.  tests/golden/make_reference_text_output_vectors.py."""
+    import json
+    from mvtopicmodel_b200 import state_io
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_text_outputs.json")))
+    views = [(np.array(v["off"]), np.array(v["word"])) for v in g["views"]]
+    zs = [np.array(z) for z in g["z"]]
+    lookups = [(lambda i, voc=voc: voc[int(i)]) for voc in g["vocab"]]
+    nwk = [np.array(t) for t in g["typeTopicCounts"]]
+    buf = io.StringIO()
+    state_io.write_state(buf, views, zs, None, lookups, g["gamma"], np.array(g["alpha"]), g["beta"], sources=g["sources"])
+    assert buf.getvalue() == g["printState"]
+    back, header = state_io.read_state(io.StringIO(g["printState"]), views)          # and the reader takes the reference's text
+    assert all(np.array_equal(a, b) for a, b in zip(back, zs)) and header["beta0"] == g["beta"][0]
+    buf = io.StringIO()
+    state_io.write_type_topic_counts(buf, nwk, lookups)
+    assert buf.getvalue() == g["printTypeTopicCounts"]
+    buf = io.StringIO()
+    state_io.write_topic_word_weights(buf, nwk, g["beta"], lookups)
+    assert buf.getvalue() == g["printTopicWordWeights"]
