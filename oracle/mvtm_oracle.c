@@ -486,7 +486,7 @@ static void sample_doc_reference(orc_t *o, int64_t d, int iteration, unsigned fl
 {
     int M = o->M, K = o->K;
     double p[ORC_MAXM][ORC_MAXM];
-    int len[ORC_MAXM];
+    int len[ORC_MAXM] = { 0 };
     draw_p(o, d, iteration, flags, p);
     memset(s->nd, 0, (size_t)M * K * 4);
     for (int m = 0; m < M; m++) {                                       /* W:339-360 */

@@ -19,12 +19,17 @@ F_CHECK_RULE = 256
 _STAMP = _SO + ".cpuflags"
 
 
+_ISA_PREFIXES = ("sse", "ssse", "avx", "fma", "bmi", "adx", "aes", "pclmul", "popcnt", "lzcnt", "abm", "movbe", "f16c", "sha", "vaes",
+                 "vpclmul", "gfni", "amx", "rdrnd", "rdseed", "clflushopt", "clwb", "movdir", "serialize", "waitpkg", "xsave", "fsgsbase")
+
+
 def _cpu_flags():
+    """the instruction-set flags of /proc/cpuinfo (only those -march=native can turn into instructions)"""
     try:
         with open("/proc/cpuinfo") as f:
             for ln in f:
                 if ln.startswith("flags"):
-                    return set(ln.split(":", 1)[1].split())
+                    return {w for w in ln.split(":", 1)[1].split() if w.startswith(_ISA_PREFIXES)}
     except OSError:
         pass
     return set()
@@ -42,7 +47,12 @@ def _built_for_this_cpu():
 def build(force=False):
     src = os.path.join(_HERE, "mvtm_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src) or not _built_for_this_cpu():
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        except (OSError, subprocess.CalledProcessError):
+            if force or not os.path.exists(_SO):
+                raise
+            return _SO                       # no compiler on this host: keep the file that travelled here
         with open(_STAMP, "w") as f:
             f.write(" ".join(sorted(_cpu_flags())))
     return _SO
