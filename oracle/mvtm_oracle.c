@@ -684,7 +684,7 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
 {
     int M = o->M, K = o->K;
     double p[ORC_MAXM][ORC_MAXM];
-    int len[ORC_MAXM];
+    int len[ORC_MAXM] = { 0 };
     draw_p(o, d, iteration, flags, p);
     memset(s->nd, 0, (size_t)M * K * 4);
     for (int i = 0; i < M; i++) {
