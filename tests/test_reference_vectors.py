@@ -217,3 +217,21 @@ def test_flag_rule_equals_reference_dense_index(oracle_mod):
                 o.set_hyper(p_a=np.full((len(Vs), len(Vs)), 0.8))
             o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT | O.F_CHECK_RULE)
         assert o.rule_violations() == 0
+
+
+def test_mallet_next_beta_law_matches_mallet_bytecode(oracle_mod):
+    """The per-document view-coupling draw (W:333) in the reference is MALLET's Randoms.nextBeta.  Its law -- incl. quirk Q5: for
+    alpha > 1, beta = 1 the first normal proposal is always accepted, a truncated N(1, 0.25/(alpha-1)) instead of Beta(alpha, 1) --
+    as drawn by the MALLET jar's own bytecode (tests/golden/make_reference_beta_vectors.py) vs the oracle's restatement
+    orc_next_beta_mallet (flag ORC_F_BETA_MALLET): two-sample Kolmogorov-Smirnov at alpha = 0.001."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_beta_vectors.json")))
+    assert len(g["cases"]) >= 8
+    for k, case in enumerate(g["cases"]):
+        ref = np.sort(np.array(case["samples"]))
+        got = np.sort(np.array([oracle_mod.next_beta_mallet(1000003 * k + s, case["a"], case["b"]) for s in range(6000)]))
+        grid = np.concatenate([ref, got])
+        d = np.abs(np.searchsorted(ref, grid, side="right") / len(ref) - np.searchsorted(got, grid, side="right") / len(got)).max()
+        assert d < 1.95 * np.sqrt((len(ref) + len(got)) / (len(ref) * len(got))), (case["a"], case["b"], d)
+        if case["a"] > 1 and case["b"] == 1:
+            assert case["uniforms_per_draw"] == 1.0                    # Q5: never a second round of the rejection loop
+            assert ref.mean() < case["a"] / (case["a"] + 1) - 0.01     # ... and not the Beta(a, 1) law
