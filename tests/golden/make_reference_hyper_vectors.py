@@ -5,6 +5,7 @@ the source of uniforms: java.util.Random.nextDouble and Cokus.randDouble are ser
   RandomSamplers.randGamma(shape, scale)   KR:294-360   the calls of optimizeGamma (M:2394, M:2410, M:2424)
   RandomSamplers.randBeta(a, b)            KR:267-271   (M:2388, M:2404, M:2420)
   RandomSamplers.randBernoulli(p)          KR:789-795   (M:2393, M:2409, M:2418)
+  Randoms.nextGamma(alpha, 1)  (MALLET)    the Gamma draws of sampleDirichlet (M:2616), from output/lib/mallet-2.0.8.jar
   Samplers.randAntoniak(alpha, n)          KS:1089-1110 (M:2471, M:2500): the FIRST call for a given n on a fresh class inverts the
                                            exact Stirling-number law; every later call reads a cache row the earlier calls
                                            multiplied and prefix-summed in place (quirk Q7) -- both are recorded.
@@ -65,6 +66,14 @@ def main():
         xs = [v.call(KS, "randAntoniak", "(DI)I", [alpha, n]) for _ in range(400)]
         out["randAntoniak_repeated"].append({"alpha": alpha, "n": n, "draws": xs,
                                              "exact_mean": float(sum(alpha / (alpha + i) for i in range(n)))})
+    # MALLET's Randoms.nextGamma(alpha, 1) -- the Gamma draws of sampleDirichlet (M:2616) -- from the MALLET jar
+    mv = jvm_mini.MiniJVM([os.path.join(REF, "lib", "mallet-2.0.8.jar")])
+    MR = "cc/mallet/util/Randoms"
+    mv.shims[MR + ".nextUniform:()D"] = lambda loc, r, a, pc: float(rng.random())
+    mv.shims[MR + ".nextGaussian:()D"] = lambda loc, r, a, pc: float(rng.standard_normal())
+    mobj = jvm_mini.JObject(MR)
+    out["mallet_nextGamma"] = [{"shape": a, "samples": [r7(mv.call(MR, "nextGamma", "(DD)D", [mobj, a, 1.0])) for _ in range(N)]}
+                               for a in (0.05, 0.5, 1.0, 2.5, 40.0, 900.0)]
     json.dump(out, open(os.path.join(HERE, "reference_hyper_vectors.json"), "w"))
     print("reference_hyper_vectors.json written;", {k: len(v) for k, v in out.items() if isinstance(v, list)})
     for r in out["randAntoniak_repeated"]:

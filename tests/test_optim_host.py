@@ -104,6 +104,15 @@ def test_gamma_sampler_matches_reference_bytecode_law(engine_lib):
         assert ref.mean() == pytest.approx(rec["shape"] * rec["scale"], rel=0.15)
 
 
+def test_gamma_sampler_matches_mallet_bytecode_law(engine_lib):
+    """Randoms.nextGamma(alpha, 1) of the MALLET jar -- what sampleDirichlet draws (M:2616) -- against rand_gamma of the engine."""
+    recs = _hyper_vectors()["mallet_nextGamma"]
+    assert len(recs) >= 6
+    for k, rec in enumerate(recs):
+        d, bound = _ks_two_sample(np.array(rec["samples"]), draws(engine_lib, 400 + k, 1, rec["shape"], 0, 30_000))
+        assert d < bound, (rec["shape"], d, bound)
+
+
 def test_beta_sampler_matches_reference_bytecode_law(engine_lib):
     for k, rec in enumerate(_hyper_vectors()["randBeta"]):
         ref = np.array(rec["samples"])
