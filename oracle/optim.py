@@ -3,8 +3,11 @@
 Follows org.madgik.MVTopicModel.FastQMVWVParallelTopicModel (M): optimizeP M:2698-2819, optimizeBeta M:2288-2367,
 the Antoniak law behind optimizeDP (org.knowceans.util.Samplers.stirling / randAntoniak, KS:1052-1110) and MALLET 2.0.8's
 Dirichlet.digamma / learnSymmetricConcentration as recovered in SURVEY.md section 8(c) (binary-only dependency).
-Parity status: unpinned (the reference has no tests); these are independent restatements used to check the engine's
-host code in mvtopicmodel_b200/csrc/mvtm_optim.inl.
+PARITY STATUS: pinned to outputs of the reference's own binaries, executed by tools/jvm_mini.py (the reference has no tests of its
+own): optimizeBeta and MALLET's digamma / learnSymmetricConcentration (tests/test_reference_vectors.py), optimizeP's per-pair sums,
+pMean and p_a on corpora where the older jar and the source agree (tests/test_optim_host.py; the TreeMap collision rule Q11 rests
+on the source citation), the Antoniak law against a first call of Samplers.randAntoniak.  These restatements are what the engine's
+device statistics and host code in mvtopicmodel_b200/csrc/mvtm_optim.inl are checked against.
 """
 import math
 

@@ -218,3 +218,32 @@ def test_optimize_dp_and_gamma_match_reference_bytecode_on_scripted_draws(engine
         np.testing.assert_allclose(st2["gamma"], ref["gamma"], rtol=1e-12)
         rc, _, _, _ = _run_hyper_core(engine_lib, case, _lib.OPT_DP, script[:n_dp - 1])
         assert rc == 1
+
+
+def test_optimize_p_restatement_matches_reference_bytecode():
+    """oracle/optim.py p_statistics + p_params (what k_p_stats and the engine's optimize_p are held to on the GPU, 1e-12) vs
+    optimizeP executed from the reference's jar (tests/golden/make_reference_optimize_p_vectors.py): per-pair sums of
+    pDistr_Mean on every case; pMean and p_a = min(-1/ln pMean, 100) incl. the pMean = 1 -> 5000 -> 100 branch where every document
+    has every view (the older jar divides by totalDocsPerModality[m] instead of the min over the pair, M:2793)."""
+    import json
+    import os
+    from oracle import optim
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_optimize_p.json")))
+    assert len(g["cases"]) >= 4
+    saw_cap = False
+    for c in g["cases"]:
+        views = [(np.array(v["off"]), np.array(v["word"])) for v in c["views"]]
+        zs = [np.array(z) for z in c["z"]]
+        ps = optim.p_statistics(views, zs, c["K"])
+        docs = np.array(c["totalDocsPerModality"], dtype=np.float64)
+        iu = np.triu_indices(c["M"], 1)
+        np.testing.assert_allclose(ps[iu], (np.array(c["pMean"]) * docs[:, None])[iu], rtol=1e-12)
+        assert np.array_equal(ps, ps.T)
+        if c["all_views_present"]:
+            pa, pm = optim.p_params(ps, c["totalDocsPerModality"])
+            off = ~np.eye(c["M"], dtype=bool)
+            np.testing.assert_allclose(pm, np.array(c["pMean"]), rtol=1e-12)
+            np.testing.assert_allclose(pa[off], np.array(c["p_a"])[off], rtol=1e-12)
+            assert np.all(np.array(c["p_b"])[off] == 1.0)
+            saw_cap |= bool(np.any(pa[off] == 100.0))
+    assert saw_cap
