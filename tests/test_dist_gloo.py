@@ -191,3 +191,79 @@ def test_shard_views_partition():
                 tot[m] += len(sv[m][1])
                 assert sv[m][0][-1] == len(sv[m][1])
         assert tot == [len(full[0][1]), len(full[1][1])]
+
+
+def _hyper_worker(rank, world, port, q):
+    """Multi-rank hyper-parameter step on the CPU: each rank holds the statistics of ITS documents (topicDocCounts with its own
+    stride, docLengthCounts with its own length); the product's reducer (dist.make_stat_reducer, what mvtm_set_stat_reducer
+    installs) makes them global -- max for the strides, sum for the bins -- and the product's hyper core
+    (mvtm_test_hyper_core) then computes, on every rank, exactly what the reference's bytecode computed on the whole corpus."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        import json
+        from mvtopicmodel_b200 import _lib
+        from mvtopicmodel_b200.dist import make_stat_reducer
+        lib = _lib.lib()
+        reduce_ = make_stat_reducer()
+        case = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_hyper_step_vectors.json")))["cases"][1]
+        M, K = case["M"], case["K"]
+        rng = np.random.default_rng(99)                      # same stream on both ranks: a consistent split of every bin
+        hist, lencnt = [], []
+        for m in range(M):
+            h = np.array(case["topicDocCounts"][m], dtype=np.int64)
+            part = rng.binomial(h, 0.5)
+            mine = part if rank == 0 else h - part
+            # local stride = up to the last non-empty bin of THIS rank, as doc_topic_hist_host sees it before the reduction
+            nz = np.nonzero(mine.sum(axis=0))[0]
+            ls = np.array([int(nz[-1]) + 1 if len(nz) else 1], dtype=np.int64)
+            gs = ls.copy(); reduce_(1, gs, None)               # global max
+            loc = np.zeros((K, int(gs[0])), dtype=np.int64); loc[:, :int(ls[0])] = mine[:, :int(ls[0])]
+            flat = loc.reshape(-1); reduce_(0, flat, None)      # global sum
+            g = flat.reshape(K, int(gs[0]))
+            assert np.array_equal(g, h[:, :int(gs[0])]) and not h[:, int(gs[0]):].any()
+            hist.append(np.ascontiguousarray(g))
+            l = np.array(case["docLengthCounts"][m], dtype=np.int64)
+            lp = rng.binomial(l, 0.5)
+            lm = lp if rank == 0 else l - lp
+            reduce_(0, lm, None)
+            assert np.array_equal(lm, l)
+            lencnt.append(lm)
+        stride = np.array([h.shape[1] for h in hist], dtype=np.int32)
+        n_len = np.array([len(l) for l in lencnt], dtype=np.int32)
+        hp = (C.c_void_p * M)(*[h.ctypes.data for h in hist]); lp_ = (C.c_void_p * M)(*[l.ctypes.data for l in lencnt])
+        alpha = np.array(case["in"]["alpha"]); asum = alpha.sum(axis=1).copy(); gamma = np.array(case["in"]["gamma"])
+        gview = np.array(case["in"]["gammaView"]); tables = np.zeros(M); scal = np.array([case["in"]["gammaRoot"], 0.0])
+        vals = np.ascontiguousarray([s[3] for s in case["script"]], dtype=np.float64)
+        inact, n_inact, used = np.zeros(K, dtype=np.int32), C.c_int32(-1), C.c_int64(0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = lib.mvtm_test_hyper_core(M, K, _lib.OPT_DP | _lib.OPT_GAMMA, hp, p(stride), lp_, p(n_len), p(alpha), p(asum), p(gamma), p(gview),
+                                      p(tables), p(scal), p(inact), C.byref(n_inact), p(vals), len(vals), None, C.byref(used))
+        assert rc == 0 and used.value == len(vals)
+        assert np.allclose(alpha, np.array(case["after_optimizeDP"]["alpha"]), rtol=1e-12, atol=1e-300)
+        assert np.allclose(gamma, case["after_optimizeGamma"]["gamma"], rtol=1e-12)
+        assert scal[0] == pytest.approx(case["after_optimizeGamma"]["gammaRoot"], rel=1e-12)
+        assert inact[:n_inact.value].tolist() == case["after_optimizeDP"]["inactive"]
+        # real-valued statistics go through the same callback (optimizeP's pair sums)
+        r = np.array([1.5 + rank, 2.0]); reduce_(0, None, r)
+        assert r.tolist() == [4.0, 4.0]
+        q.put((rank, "ok"))
+    except Exception:   # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_hyper_statistics_reducer_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_hyper_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
