@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- Gibbs token-updates/s of the B200 engine on BASELINE.json configs[1] (lda_100k).
+"""bench.py -- Gibbs token-updates/s of the B200 engine on the BASELINE.json target shape.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--docs D]
 
-A "step" is one full Gibbs sweep (mvtm_sweep) over the rank's shard.  N > 1 is launched by torchrun, one rank per
-GPU; every rank holds a 100 K-document shard (weak scaling), n_wk is replicated and the per-sweep count deltas
-are all-reduced with NCCL inside the timed region.  Rank 0 prints ONE JSON line.
+Default workload: acm_2v (BASELINE configs[2]: two views, K = 1000) at 1 000 000 documents IN TOTAL -- north_star's target
+("a 1M-document, 2-view, 1000-topic synthetic corpus").  The corpus is the union of 8 blocks of D/8 documents; rank r of N
+holds blocks r, r+N, ... so every N in {1, 2, 4, 8} samples the SAME corpus (strong scaling).  A "step" is one full Gibbs
+sweep (every view) over the whole corpus.  N > 1 is launched by torchrun, one rank per GPU; n_wk is replicated and the
+per-sweep count deltas are all-reduced with NCCL inside the timed region (overlapped with the other view's pass).  Rank 0
+prints ONE JSON line.  Other workloads (lda_100k, pubmed_3v, stress_4v, uniform_k1000) via --workload; --docs = total documents.
 
---impl reference times the reference's CPU scheme (oracle/: multithreaded restatement of the Java
-worker/updater/queue design; the Java code itself cannot run, there is no JVM in this image) on the host cores.
+--impl reference times the reference's CPU scheme (oracle/: multithreaded restatement of the Java worker/updater/queue
+design; the Java code itself cannot run, there is no JVM in this image) on the host cores, on a bounded sample.
 """
 import argparse
 import json
@@ -25,19 +28,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gibbs_token_updates_per_sec"
 UNIT = "tokens/s"
+N_BLOCKS = 8
+DEFAULT_DOCS = {"acm_2v": 1_000_000, "lda_100k": 100_000, "pubmed_3v": 1_000_000, "stress_4v": 2_000_000, "uniform_k1000": 200_000}
+CFG_IDX = {"lda_100k": 1, "acm_2v": 2, "pubmed_3v": 3, "stress_4v": 4}
+
+
+def b_tok_view(K, m, mean_lens):
+    """Algorithmic bytes per token update of view m, SURVEY.md 8(d) / BASELINE.md section 3: 4K (n_wk row) + 4 (word) + 8 (z r/w)
+    + 16 (two count RMWs) + 8K/N_m (n_k and alpha rows per doc-view) + 4*sum_{i != m} N_i/N_m (other views' z re-read)."""
+    n = mean_lens[m]
+    other = sum(mean_lens[i] for i in range(len(mean_lens)) if i != m)
+    return 4 * K + 28 + 8.0 * K / n + 4.0 * other / n
 
 
 def b_tok(K, mean_lens, tokens):
-    """Algorithmic bytes per token update, SURVEY.md 8(d) / BASELINE.md section 3: per view 4K (row) + 4 (word) + 8 (z r/w)
-    + 16 (two count RMWs) + 8K/N_m (n_k and alpha rows per doc-view) + 4*sum_{i != m} N_i/N_m (other views' z re-read),
-    token-weighted over the views."""
-    tot, acc = float(sum(tokens)), 0.0
-    for m, (n, t) in enumerate(zip(mean_lens, tokens)):
-        if t == 0:
-            continue
-        other = sum(mean_lens[i] for i in range(len(mean_lens)) if i != m)
-        acc += t * (4 * K + 28 + 8.0 * K / n + 4.0 * other / n)
-    return acc / tot
+    tot = float(sum(tokens))
+    return sum(t * b_tok_view(K, m, mean_lens) for m, t in enumerate(tokens) if t) / tot
 
 
 def measured_peak():
@@ -95,12 +101,43 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---- corpus: 8 blocks, generated in parallel before CUDA is touched ---------------------------------------------------------
+def _gen_block(args):
+    workload, block, docs = args
+    from mvtopicmodel_b200 import corpus
+    if workload == "uniform_k1000":
+        # the genuinely HBM-bound case: uniform words over V = 400 K at K = 1000 (1.6 GB table, no cache reuse)
+        return corpus.generate_uniform(docs, 1000, 400_000, 100, seed=7 + block)
+    return corpus.generate(workload, shard=block, docs=docs)
+
+
+def build_corpus(workload, total_docs, rank, world):
+    """This rank's share of the corpus: blocks rank, rank+world, ... of N_BLOCKS, concatenated (doc-aligned across views)."""
+    per = total_docs // N_BLOCKS
+    blocks = list(range(rank, N_BLOCKS, world)) if world <= N_BLOCKS else [rank % N_BLOCKS]
+    jobs = [(workload, b, per) for b in blocks]
+    if len(jobs) == 1:
+        res = [_gen_block(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+            res = pool.map(_gen_block, jobs)
+    K, Vs = res[0][0], res[0][1]
+    views = []
+    for m in range(len(Vs)):
+        offs, words, base = [np.zeros(1, dtype=np.int64)], [], 0
+        for r in res:
+            off, w = r[2][m]
+            offs.append(off[1:] + base); words.append(w); base += int(off[-1])
+        views.append((np.concatenate(offs), np.concatenate(words)))
+    return K, Vs, views
+
+
 def cpu_reference_run(workload, sample_docs, steps, warmup, threads):
     """The reference's multithreaded CPU scheme (oracle restatement) on a bounded sample of the workload."""
-    from mvtopicmodel_b200 import corpus
     from oracle import oracle as O
     O.build()
-    K, Vs, views = corpus.generate(workload, docs=sample_docs)
+    K, Vs, views = _gen_block((workload, 0, sample_docs))
     o = O.Oracle(K, Vs, views, seed=2026)
     o.init_assignments()
     o.rebuild_trees()
@@ -119,14 +156,27 @@ def cpu_reference_run(workload, sample_docs, steps, warmup, threads):
     return ntok * steps / dt, dt / steps * 1e3, ntok, K
 
 
+def load_traffic(workload, docs_per_gpu):
+    """ncu evidence for the dominant kernel of this workload (profiles/ncu_traffic.json: one entry per captured workload)."""
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        allw = json.load(open(tp))
+    except Exception:
+        return None
+    ent = allw.get(workload) if isinstance(allw, dict) else None
+    if not isinstance(ent, dict):
+        return None
+    return ent
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--workload", default="lda_100k")
-    ap.add_argument("--docs", type=int, default=None, help="documents per rank (default: the workload's D)")
+    ap.add_argument("--workload", default="acm_2v")
+    ap.add_argument("--docs", type=int, default=None, help="documents IN TOTAL over all ranks (default: 1 M for acm_2v)")
     ap.add_argument("--cpu-sample-docs", type=int, default=25000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -139,11 +189,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from mvtopicmodel_b200 import corpus
-    cfg = corpus.CONFIGS[args.workload]
-    cfg_idx = {"lda_100k": 1, "acm_2v": 2, "pubmed_3v": 3, "stress_4v": 4}.get(args.workload, -1)
-    docs_cfg = args.docs if args.docs else cfg["D"]
-    wl_desc = (f"{args.workload}: BASELINE configs[{cfg_idx}] synthetic shape, {docs_cfg} docs/GPU, {len(cfg['views'])} view(s), "
-               f"V={[v[0] for v in cfg['views']]}, K={cfg['K']}, ~{int(docs_cfg * sum(v[1] * v[3] for v in cfg['views']) / 1e6)}M tokens/GPU")
+    total_docs = args.docs if args.docs else DEFAULT_DOCS.get(args.workload, 100_000)
+    total_docs = max(N_BLOCKS, total_docs // N_BLOCKS * N_BLOCKS)
+    if args.workload == "uniform_k1000":
+        shape = "uniform words, V=400000, K=1000, 100 tokens/doc (HBM-bound control: no cache reuse)"
+    else:
+        cfg = corpus.CONFIGS[args.workload]
+        shape = (f"BASELINE configs[{CFG_IDX.get(args.workload, -1)}] synthetic shape, {len(cfg['views'])} view(s), "
+                 f"V={[v[0] for v in cfg['views']]}, K={cfg['K']}")
+    wl_desc = f"{args.workload}: {shape}; {total_docs} docs in total, sharded over the ranks"
     threads = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -153,7 +207,7 @@ def main():
         val, ms, ntok, K = cpu_reference_run(args.workload, args.cpu_sample_docs, steps, warmup, threads)
         nst, nut = 3 * threads // 4, threads // 4
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f64",
                 "data": "synthetic", "config": {"workload": wl_desc, "sample": f"{args.cpu_sample_docs} docs / {ntok} tokens per step"},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                  "sample": f"first {args.cpu_sample_docs} docs ({ntok} tokens) of {args.workload}, {steps} sweeps; "
@@ -162,8 +216,12 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # corpus first: the block generators fork, which must happen before CUDA is initialised
+    K, Vs, views = build_corpus(args.workload, total_docs, rank, world)
+    M = len(views)
+    D_local = len(views[0][0]) - 1
     # a single view has nothing to hide its exchange under (its next pass needs the result at once): serial there
-    overlap = world > 1 and len(cfg["views"]) > 1 and not args.no_overlap
+    overlap = world > 1 and M > 1 and not args.no_overlap
     import torch
     from mvtopicmodel_b200 import Engine
     from mvtopicmodel_b200.dist import CountExchange, EngineAdapter, OverlapAdapter, OverlappedSweep
@@ -172,9 +230,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    K, Vs, views = corpus.generate(args.workload, shard=rank, docs=args.docs)
-    M = len(views)
-    D_local = len(views[0][0]) - 1
     n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     eng = Engine(K, Vs, views, seed=2026, device=local_rank, doc_id_base=rank, doc_id_stride=world,
                  max_ctas=(n_sms - args.reserve_sms) if overlap else 0)
@@ -217,7 +272,7 @@ def main():
             ovl_adapter.drain()         # the last views' exchange belongs to the timed region
 
     it = 0
-    for _ in range(4):          # set-up: the engine's ring-depth autotune settles over its first four sweeps (not warm-up, not timed)
+    for _ in range(6):          # set-up: the engine's ring-depth autotune takes three samples per depth (not warm-up, not timed)
         it += 1
         step(it)
     for _ in range(args.warmup):
@@ -229,28 +284,29 @@ def main():
         time.sleep(0.3)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, changed = 0.0, 0
+    view_ms, changed = np.zeros(M), 0
     ev0.record()
     for _ in range(args.steps):
         it += 1
         step(it)
         st = eng.stats()
-        kern_ms += sum(st["ms_view"])
+        view_ms += np.array(st["ms_view"])
         changed += st["changed"]
     drain()
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    ring = eng.stats()["ring_locked"]
     clocks = sampler.stop() if rank == 0 else None
     if dist:
-        t = torch.tensor([ms_total, kern_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_total] + list(view_ms), device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, kern_ms_max = float(t[0]), float(t[1])
+        ms_total, view_ms_max = float(t[0]), t[1:].cpu().numpy()
         n = torch.tensor([ntok_local], device="cuda", dtype=torch.int64)
         dist.all_reduce(n)
         ntok_global = int(n[0])
     else:
-        ntok_global, kern_ms_max = ntok_local, kern_ms
+        ntok_global, view_ms_max = ntok_local, view_ms
     if world == 1:
         viol = eng.check_invariants()
     else:
@@ -297,7 +353,6 @@ def main():
             it += 1
             e2e_step(it)
         barrier()
-        t0 = time.perf_counter()
         ev0.record()
         for _ in range(e2e_steps):
             it += 1
@@ -325,27 +380,38 @@ def main():
 
     peak, peak_src = measured_peak()
     mean_lens = [eng.ntok[m] / max(1, int(((views[m][0][1:] - views[m][0][:-1]) > 0).sum())) for m in range(M)]
-    btok = b_tok(K, mean_lens, eng.ntok)
-    kern_s = kern_ms_max * 1e-3
-    achieved = btok * ntok_local * args.steps / kern_s / 1e9 if kern_s > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp) and args.workload == "lda_100k" and args.docs is None:      # the capture is of this workload's kernel
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    btok_all = b_tok(K, mean_lens, eng.ntok)
+    # the dominant kernel: the view pass with the most device time (k_sweep_view of that view; one launch per step)
+    dom = int(np.argmax(view_ms_max))
+    btok_dom = b_tok_view(K, dom, mean_lens)
+    launch_ms = float(view_ms_max[dom]) / args.steps
+    achieved = btok_dom * eng.ntok[dom] / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    ent = load_traffic(args.workload, D_local)
+    traffic = l2_hit = dram_frac = None
+    bound = "unknown (no ncu capture of this workload under profiles/)"
+    if ent:
+        # the capture's DRAM bytes are per launch at ITS document count: scale per token to this launch
+        per_tok = ent["dram_bytes_per_launch"] / ent["tokens_per_launch"]
+        traffic = per_tok * eng.ntok[dom]
+        l2_hit = ent.get("l2_hit_rate_pct")
+        dram_frac = traffic / (launch_ms * 1e-3) / 1e9 / peak if launch_ms > 0 else None
+        bound = ent.get("bound", "hbm" if dram_frac and dram_frac > 0.6 else "l2+issue")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32+f32", "data": "synthetic",
-            "config": {"workload": wl_desc, "docs_per_gpu": D_local, "tokens_per_gpu": ntok_local, "K": K, "views": M,
+            "config": {"workload": wl_desc, "docs_total": total_docs, "docs_per_gpu": D_local, "tokens_per_gpu": ntok_local,
+                       "tokens_total": ntok_global, "K": K, "views": M, "ring_depth": ring,
                        "l2": "inputs larger than L2 (z+words+n_wk = %d MB per sweep vs 126 MB L2), no explicit flush" %
                              int((8 * ntok_local + 4 * sum(Vs) * eng.row_stride()) / 1e6),
                        "changed_frac": changed / max(1, ntok_local * args.steps), "invariant_violations": viol},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_nominal_8000": achieved / 8000.0,
-                         "traffic": traffic, "kernel": "k_sweep_view", "bytes_per_token": btok, "tokens_per_launch": ntok_local,
-                         "avg_launch_ms": kern_ms_max / args.steps / M, "peak_source": peak_src},
+            # `achieved` counts ALGORITHMIC bytes (one dense n_wk row per token); `bound` says what ncu shows limits the kernel:
+            # on Zipf corpora the hot rows are served from L2 and DRAM moves only `traffic` bytes per launch (dram_frac of peak)
+            "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "dram_frac": dram_frac, "l2_hit": l2_hit, "traffic": traffic,
+                         "kernel": f"k_sweep_view (view {dom})", "bytes_per_token": btok_dom, "tokens_per_launch": eng.ntok[dom],
+                         "avg_launch_ms": launch_ms, "bytes_per_token_all_views": btok_all,
+                         "whole_job_frac": btok_all * value / 1e9 / (peak * world),
+                         "peak_source": peak_src, "traffic_source": ent.get("source") if ent else None},
             "e2e": e2e, "clocks": clocks,
             # my kernels inside the timed region: one k_sweep_view per view and step, plus the exchange's finishing passes
             # (serial form: table and totals separately, overlapped form: one fused pass per view)

@@ -20,7 +20,8 @@ class MvtmConfig(C.Structure):
 
 class MvtmSweepStats(C.Structure):
     _fields_ = [("tokens", C.c_int64), ("changed", C.c_int64), ("new_topic", C.c_int64), ("ms_total", C.c_double),
-                ("ms_view", C.c_double * MAX_VIEWS), ("kernel_launches", C.c_int32)]
+                ("ms_view", C.c_double * MAX_VIEWS), ("kernel_launches", C.c_int32),
+                ("ring_depth", C.c_int32 * MAX_VIEWS), ("ring_locked", C.c_int32 * MAX_VIEWS)]
 
 
 FLAG_DOC_ORDER = 1

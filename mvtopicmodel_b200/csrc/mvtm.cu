@@ -37,7 +37,7 @@ struct ViewDev {
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
     std::vector<unsigned char> h_present;
     int tune_step = 0, ring_locked = 0;             // ring-depth autotune over the first sweeps (see ring_for_view)
-    float tune_ms[4] = { 0.f, 0.f, 0.f, 0.f };
+    float tune_ms[8] = { 0.f };
 };
 
 }  // namespace
@@ -66,8 +66,8 @@ struct mvtm_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;             // mvtm_sweep_host: H2D / D2H of z chunks beside the kernels
     std::vector<cudaEvent_t> host_ev;               // per (view, chunk): upload done
-    cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2];
-    cudaEvent_t ev_done[MVTM_MAX_VIEWS], ev_ready[MVTM_MAX_VIEWS];   // hand-over points with a caller-owned stream (async exchange)
+    cudaEvent_t ev[2 * MVTM_MAX_VIEWS + 2] = { nullptr };
+    cudaEvent_t ev_done[MVTM_MAX_VIEWS] = { nullptr }, ev_ready[MVTM_MAX_VIEWS] = { nullptr };   // hand-over points with a caller-owned stream (async exchange)
     bool ready_pending[MVTM_MAX_VIEWS] = { false }, pass_queued[MVTM_MAX_VIEWS] = { false };
     bool sweep_open = false;
     int open_launches = 0, open_mode = 1;
@@ -152,12 +152,13 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
     memset(&h->stats, 0, sizeof(h->stats));
     h->alpha.assign((size_t)h->M * (h->K + 1), 0.1);                    // S:149-159, M:195-239
     for (int m = 0; m < h->M; m++) {
-        if (cfg->vocab_sizes[m] < 1) { g_create_err = "mvtm_create: vocab size < 1"; delete h; return MVTM_ERR_ARG; }
+        if (cfg->vocab_sizes[m] < 1) { g_create_err = "mvtm_create: vocab size < 1"; delete h; return MVTM_ERR_ARG;   /* nothing allocated yet */ }
         h->v[m].V = cfg->vocab_sizes[m];
         h->alphaSum[m] = 0.1 * h->K; h->beta[m] = 0.01; h->betaSum[m] = 0.01 * h->v[m].V; h->gamma[m] = 1.0;
         for (int j = 0; j < h->M; j++) { h->p_a[m][j] = 0.2; h->p_b[m][j] = 1.0; }   // M:1055-1058
     }
-#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(_e); delete h; return MVTM_ERR_CUDA; } } while (0)
+    // a failure below goes through the same teardown as mvtm_destroy (every member starts NULL, the destroy calls accept that)
+#define CKC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(_e); mvtm_destroy(h); return MVTM_ERR_CUDA; } } while (0)
     CKC(cudaSetDevice(h->device));
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, h->device));
@@ -188,14 +189,17 @@ extern "C" int mvtm_destroy(mvtm_handle *h)
 {
     if (!h) return MVTM_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    // An overlapped exchange (the caller's all-reduce and mvtm_sum_exchange_finish_async on the caller's stream) and the copy
+    // stream of mvtm_sweep_host may still be touching the tables: wait for the whole device, not just the handle's stream.
+    cudaDeviceSynchronize();
+    cudaGetLastError();
     for (int m = 0; m < h->M; m++) free_view(h->v[m]);
-    for (auto &ev : h->ev) cudaEventDestroy(ev);
-    for (int m = 0; m < MVTM_MAX_VIEWS; m++) { cudaEventDestroy(h->ev_done[m]); cudaEventDestroy(h->ev_ready[m]); }
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (int m = 0; m < MVTM_MAX_VIEWS; m++) { if (h->ev_done[m]) cudaEventDestroy(h->ev_done[m]); if (h->ev_ready[m]) cudaEventDestroy(h->ev_ready[m]); }
     cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad); cudaFree(h->oc_scratch);
     for (auto &ev : h->host_ev) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    cudaStreamDestroy(h->stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MVTM_OK;
 }
@@ -298,7 +302,7 @@ static int rebuild_counts_view(mvtm_handle *h, int m)
     CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
     if (v.n_tok > 0) {
         int blocks = (int)std::min<long long>((v.n_tok + 255) / 256, (long long)h->num_sms * 8);
-        k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad);
+        k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad, 1);
         CK(h, cudaGetLastError());
     }
     int bad = 0;
@@ -505,9 +509,12 @@ static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
 
 struct LaunchCfg { int R, W, grid, oc_smem; size_t smem; };
 
-// Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first four timed sweeps
-// alternate R = 1, 2, 1, 2 and the faster of the last two is kept: cache-resident tables (Zipf corpora) favour R = 1
-// (more resident documents), genuinely HBM-bound ones R = 2 (the row fetch latency is then worth a slot).
+// Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first 2*RING_SAMPLES timed
+// passes of the view alternate R = 1, 2, 1, 2, ... and the depth with the smaller MEDIAN pass time is kept (one sample per depth
+// locked different depths on identical runs: BENCH_r01 vs SCALE_r01 N=1).  Cache-resident tables (Zipf corpora) favour R = 1
+// (more resident documents), genuinely HBM-bound ones R = 2 (the row fetch latency is then worth a slot).  A depth that is
+// within 2 % of the other is not worth a different launch shape: R = 1 wins ties.  The locked depth is reported in mvtm_stats.
+constexpr int RING_SAMPLES = 3;
 static int ring_for_view(mvtm_handle *h, int m)
 {
     if (h->cfg_ring > 0) return h->cfg_ring;
@@ -520,8 +527,13 @@ static void ring_record(mvtm_handle *h, int m, float ms)
 {
     ViewDev &v = h->v[m];
     if (h->cfg_ring > 0 || getenv("MVTM_RING") || v.ring_locked) return;
-    v.tune_ms[v.tune_step & 3] = ms;
-    if (++v.tune_step == 4) v.ring_locked = (v.tune_ms[3] < v.tune_ms[2]) ? 2 : 1;
+    v.tune_ms[v.tune_step] = ms;
+    if (++v.tune_step == 2 * RING_SAMPLES) {
+        float a[RING_SAMPLES], b[RING_SAMPLES];
+        for (int i = 0; i < RING_SAMPLES; i++) { a[i] = v.tune_ms[2 * i]; b[i] = v.tune_ms[2 * i + 1]; }
+        std::sort(a, a + RING_SAMPLES); std::sort(b, b + RING_SAMPLES);
+        v.ring_locked = (b[RING_SAMPLES / 2] < 0.98f * a[RING_SAMPLES / 2]) ? 2 : 1;
+    }
 }
 
 static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
@@ -599,7 +611,11 @@ static int activate_sampled_topics(mvtm_handle *h)
     if (h->inactive.empty()) return MVTM_OK;
     const int K = h->K;
     std::vector<std::vector<int>> nk((size_t)h->M, std::vector<int>((size_t)K));
-    for (int m = 0; m < h->M; m++) CK(h, cudaMemcpy(nk[m].data(), h->v[m].nk, (size_t)K * 4, cudaMemcpyDeviceToHost));
+    // on the handle's stream, behind anything a caller's stream still owes the views (the legacy default stream does not order
+    // against these non-blocking streams)
+    if (int rc = wait_all_ready(h)) return rc;
+    for (int m = 0; m < h->M; m++) CK(h, cudaMemcpyAsync(nk[m].data(), h->v[m].nk, (size_t)K * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     std::vector<int> keep;
     for (int t : h->inactive) {
         bool hit = false;
@@ -642,6 +658,7 @@ static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, i
         SweepParams P;
         fill_params(h, m, iteration, update_global, P);
         P.R = lc.R; P.oc_smem = lc.oc_smem;
+        h->stats.ring_depth[m] = lc.R;
         P.z_host = v.z_mirror;
         CK(h, launch_sweep(h, P, lc));
         (*launches)++;
@@ -819,7 +836,7 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
             CK(h, cudaEventRecord(ev_up(m, cidx), h->copy_stream));
             CK(h, cudaStreamWaitEvent(h->stream, ev_up(m, cidx), 0));
             int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
-            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(n, v.word + t0, v.z + t0, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad);
+            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(n, v.word + t0, v.z + t0, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad, 1);
             CK(h, cudaGetLastError());
         }
     }
@@ -838,6 +855,7 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
             SweepParams P;
             fill_params(h, m, iteration, 1, P);
             P.R = lc.R; P.oc_smem = lc.oc_smem;
+            h->stats.ring_depth[m] = lc.R;
             P.z_host = alias[m];
             CK(h, launch_sweep(h, P, lc));
             launches++;
@@ -871,6 +889,10 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
 extern "C" int mvtm_stats(mvtm_handle *h, mvtm_sweep_stats *out)
 {
     if (!h || !out) return MVTM_ERR_ARG;
+    for (int m = 0; m < h->M; m++) {
+        const char *e = getenv("MVTM_RING");
+        h->stats.ring_locked[m] = h->cfg_ring > 0 ? h->cfg_ring : (e ? atoi(e) : h->v[m].ring_locked);
+    }
     *out = h->stats;
     return MVTM_OK;
 }
@@ -888,14 +910,16 @@ extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t p
     if (int rc = upload_hyper(h)) return rc;
     if (int rc = ensure_oc_scratch(h, (size_t)(32 / h->G))) return rc;
     int w = 0;
-    CK(h, cudaMemcpy(&w, v.word + v.h_doc_off[(size_t)doc] + pos, 4, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpyAsync(&w, v.word + v.h_doc_off[(size_t)doc] + pos, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     if (w < 0 || w >= v.V) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: token has out-of-vocabulary word id %d (W:427-428 skips it)", w);
     double *d_out = nullptr, *d_p = nullptr;
     CK(h, cudaMalloc(&d_out, (size_t)(h->K + 1) * 8));
     std::vector<double> prow((size_t)h->M, 0.0);
     if (p_row) prow.assign(p_row, p_row + h->M); else prow[(size_t)m] = 1.0;
     CK(h, cudaMalloc(&d_p, (size_t)h->M * 8));
-    CK(h, cudaMemcpy(d_p, prow.data(), (size_t)h->M * 8, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpyAsync(d_p, prow.data(), (size_t)h->M * 8, cudaMemcpyHostToDevice, h->stream));   // ordered before the probe
+    CK(h, cudaStreamSynchronize(h->stream));                                                           // prow is a local
     SweepParams P;
     fill_params(h, m, 0, 0, P);
     P.nk_frozen = v.nk;                                                  // frozen counts = the current ones
@@ -1035,16 +1059,16 @@ extern "C" int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out)
     CK(h, cudaMalloc(&d_bad, 8));
     cudaError_t e = cudaMemsetAsync(d_bad, 0, 8, h->stream);
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaMemsetAsync(h->d_bad, 0, 4, h->stream));                 // once: out-of-range ids accumulate over the views
     for (int m = 0; m < h->M && e == cudaSuccess; m++) {
         ViewDev &v = h->v[m];
         const size_t n = (size_t)v.V * h->Kp;
         int *s_nwk = nullptr, *s_nk = nullptr;
         step(cudaMalloc(&s_nwk, n * 4)); step(cudaMalloc(&s_nk, (size_t)h->Kp * 4));
         step(cudaMemsetAsync(s_nwk, 0, n * 4, h->stream)); step(cudaMemsetAsync(s_nk, 0, (size_t)h->Kp * 4, h->stream));
-        step(cudaMemsetAsync(h->d_bad, 0, 4, h->stream));
         if (e == cudaSuccess && v.n_tok > 0) {
             int blocks = (int)std::min<long long>((v.n_tok + 255) / 256, (long long)h->num_sms * 8);
-            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, s_nwk, s_nk, h->d_bad);
+            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(v.n_tok, v.word, v.z, v.V, h->K, h->Kp, s_nwk, s_nk, h->d_bad, 0);
             step(cudaGetLastError());
         }
         if (e == cudaSuccess) {
@@ -1056,8 +1080,9 @@ extern "C" int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out)
         cudaFree(s_nwk); cudaFree(s_nk);
     }
     unsigned long long bad = 0; int badz = 0;
-    step(cudaMemcpy(&bad, d_bad, 8, cudaMemcpyDeviceToHost));
-    step(cudaMemcpy(&badz, h->d_bad, 4, cudaMemcpyDeviceToHost));
+    step(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, h->stream));
+    step(cudaMemcpyAsync(&badz, h->d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
+    step(cudaStreamSynchronize(h->stream));
     cudaFree(d_bad);
     CK(h, e);
     *violations_out = (int64_t)bad + badz;

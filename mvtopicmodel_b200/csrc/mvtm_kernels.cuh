@@ -739,7 +739,9 @@ __global__ void k_init_from_phi(int m, int K, int Kp, int V, long long n_docs, c
 }
 
 // buildInitialTypeTopicCounts M:600-652: n_wk / n_k from (word, z); n_k through a shared-memory histogram
-__global__ void k_build_counts(long long n_tok, const int *word, int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad)
+// fix != 0: an id >= K is rewritten to UNASSIGNED_TOPIC so that no sweep can index with it; fix == 0 (mvtm_check_invariants): the
+// assignments are only read
+__global__ void k_build_counts(long long n_tok, const int *word, int *z, int V, int K, int Kp, int *nwk, int *nk, int *bad, int fix)
 {
     extern __shared__ int hk[];
     for (int t = threadIdx.x; t < K; t += blockDim.x) hk[t] = 0;
@@ -747,7 +749,7 @@ __global__ void k_build_counts(long long n_tok, const int *word, int *z, int V, 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_tok; i += (long long)gridDim.x * blockDim.x) {
         int t = z[i], w = word[i];
         if (t < 0) continue;                                      // UNASSIGNED_TOPIC, M:634
-        if (t >= K) { atomicAdd(bad, 1); z[i] = -1; continue; }   // reported by the caller; never left where a sweep could index with it
+        if (t >= K) { atomicAdd(bad, 1); if (fix) z[i] = -1; continue; }   // reported by the caller; never left where a sweep could index with it
         atomicAdd(hk + t, 1);
         if ((unsigned)w < (unsigned)V) atomicAdd(nwk + (size_t)w * Kp + t, 1);
     }
@@ -796,7 +798,8 @@ __global__ void k_loglik_docs(long long n_docs, const long long *off, const int 
         const long long b = off[d]; const int len = (int)(off[d + 1] - b);
         const int arrlen = quirk_len2 ? (len < 2 ? 2 : len) : len;        // Q18
         if (!present[d] || arrlen == 0) { if (lane == 0) { doc_ll[d] = 0.0; counted[d] = 0; } continue; }
-        for (int i = lane; i < len; i += 32) atomicAdd(cnt + z[b + i], 1);
+        // UNASSIGNED_TOPIC (-1: a fresh handle, an out-of-range id k_build_counts rejected, a restored state) counts for nothing
+        for (int i = lane; i < len; i += 32) { const int t = z[b + i]; if (t >= 0 && t < K) atomicAdd(cnt + t, 1); }
         if (lane == 0 && arrlen > len) atomicAdd(cnt + 0, arrlen - len);
         __syncwarp();
         double acc = 0.0;

@@ -413,7 +413,9 @@ static int optimize_beta(mvtm_handle *h)
         ViewDev &v = h->v[m];
         const double prevBetaSum = h->betaSum[m];
         std::vector<int> nk((size_t)K);
-        CK(h, cudaMemcpy(nk.data(), v.nk, (size_t)K * 4, cudaMemcpyDeviceToHost));
+        if (int rc = wait_view_ready(h, m)) return rc;              // an overlapped exchange may still own the view's tables
+        CK(h, cudaMemcpyAsync(nk.data(), v.nk, (size_t)K * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
         const int maxTopicSize = *std::max_element(nk.begin(), nk.end());
         std::vector<long long> sizeHist((size_t)maxTopicSize + 1, 0);
         for (int t = 0; t < K; t++) sizeHist[(size_t)nk[(size_t)t]]++;

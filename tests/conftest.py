@@ -23,6 +23,10 @@ def oracle_mod():
 def engine_lib():
     """Builds (if stale) and loads libmvtm.so; GPU tests go through it, CPU tests only inspect its symbols."""
     from mvtopicmodel_b200 import build, _lib
+    # One launch shape for every parity test: without this the engine samples ring depths 1, 2, 1, 2, ... over a view's first
+    # passes and keeps the faster one -- a wall-clock decision that changes how many documents are resident, i.e. the
+    # asynchrony of a stochastic trajectory.  Tests of the autotune itself delete the variable; mvtm_config.ring_depth wins over it.
+    os.environ.setdefault("MVTM_RING", "1")
     if build.needs_build():
         build.build()
     return _lib.lib()

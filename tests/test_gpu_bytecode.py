@@ -1,0 +1,165 @@
+"""GPU parity tests against THE REFERENCE ITSELF: the engine (through the C ABI) vs vectors produced by executing the reference's
+own jars (tests/golden/reference_*.json, made by tools/jvm_mini.py + tests/golden/make_reference_*.py).
+
+This file sorts before test_gpu_parity.py on purpose: these are the strongest evidence for north_star gates (b) and (c), and
+`pytest -x` must reach them before any stochastic trajectory test can stop the run.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_COND = 1e-5      # north_star (b)
+REL_TOL_LL = 0.01        # north_star (c)
+
+
+# ---- the engine against vectors produced by the reference's own binary (tests/golden/reference_sampler_vectors.json) ----------
+def _reference_cases():
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_sampler_vectors.json")))
+    for case in gold["cases"]:
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        yield case, case["K"], case["V"], views
+
+
+def test_engine_conditionals_match_reference_bytecode(engine_lib):
+    """north_star check (b) against THE REFERENCE: the per-token conditional distributions the reference's sampler bytecode
+    (FastQMVWVWorkerRunnable.sampleTopicsForOneDoc from the shipped jar, executed by tools/jvm_mini.py) computed on frozen counts
+    -- its dense index, document masses, new-topic mass and F+tree leaves -- vs mvtm_cond_probs on the same state: 1e-5 relative
+    on every topic (fp32 scan on the device), incl. coupled views, inactive topics and the sparse-view sentinel."""
+    from mvtopicmodel_b200 import Engine
+    n = 0
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        e = Engine(K, Vs, views, seed=case["seed"])
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        frozen_z = [np.array(z, dtype=np.int32) for z in case["frozen_counts_z"]]
+        for m in range(M):
+            e.set_assignments(m, frozen_z[m])
+        frozen = [e.get_counts(m) for m in range(M)]
+        # tokens on which quirk Q1 has had no effect (the vectors also hold Q1-affected tokens, marked by `not_in_S`: on those the
+        # engine's documented index "topics the document holds" differs from the reference's by design)
+        for rec in [r for r in case["conditionals"] if not r.get("not_in_S")][::2]:
+            zs = [z.copy() for z in frozen_z]
+            for m, zd in enumerate(rec["z_doc"]):
+                if zd is not None:
+                    b = int(views[m][0][rec["doc"]])
+                    zs[m][b:b + len(zd)] = zd
+            for m in range(M):
+                e.set_assignments(m, zs[m])
+                e.set_counts(m, *frozen[m])                      # the document moved, the global tables did not
+            got = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"])
+            want = np.array(rec["probs"])
+            big = want > 1e-9
+            assert np.max(np.abs(got[:K][big] - want[big]) / want[big]) < REL_TOL_COND, (case["name"], rec["doc"], rec["view"], rec["pos"])
+            assert np.all(np.abs(got[:K][~big] - want[~big]) < 1e-12)
+            assert got[K] == pytest.approx(rec["new_share"], rel=REL_TOL_COND, abs=1e-12)
+            n += 1
+    assert n > 300
+
+
+def test_engine_loglik_matches_reference_bytecode(engine_lib):
+    """mvtm_loglik (quirk_len2 = 1, the reference's own behaviour Q18) vs FastQMVWVParallelTopicModel.modelLogLikelihood executed
+    from the shipped jar on the states its sampler reached: 1e-10 relative."""
+    from mvtopicmodel_b200 import Engine
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+        e = Engine(K, Vs, views, seed=case["seed"], present=present)
+        # the last live sweep's state: hyper-parameters as the reference held them then (activation may have changed alpha)
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        for m in range(M):
+            e.set_assignments(m, np.array(case["z_after"][-1][m], dtype=np.int32))
+        assert np.allclose(e.loglik(True), case["loglik_after"][-1], rtol=1e-10, atol=0), case["name"]
+
+
+def test_engine_counts_histograms_and_beta_step_match_reference_bytecode(engine_lib):
+    """Count tables, topicDocCounts (every bin, incl. bin 0 as buildInitialTypeTopicCounts writes it, M:647-649) and the
+    optimizeBeta step of mvtm_optimize_hyper vs the reference's own bytecode (buildInitialTypeTopicCounts, initializeHistograms,
+    optimizeBeta executed from the shipped jars): integers bit for bit, beta / betaSum to 1e-9 incl. the sentinel / NaN branches."""
+    from mvtopicmodel_b200 import Engine
+    for case, K, Vs, views in _reference_cases():
+        M = len(Vs)
+        present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+        e = Engine(K, Vs, views, seed=case["seed"], present=present)
+        e.set_hyper(alpha=np.array(case["frozen_alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), inactive=case["frozen_inactive"])
+        ref = case["counts_and_histograms"]
+        for m in range(M):
+            e.set_assignments(m, np.array(case["frozen_counts_z"][m], dtype=np.int32))
+            nwk, nk = e.get_counts(m)
+            assert np.array_equal(nwk, np.array(ref["typeTopicCounts"][m])) and np.array_equal(nk, np.array(ref["tokensPerTopic"][m]))
+            want, got = np.array(ref["topicDocCounts"][m]), e.doc_topic_hist(m)
+            w = min(want.shape[1], got.shape[1])
+            assert np.array_equal(got[:, :w], want[:, :w]) and not want[:, w:].any() and not got[:, w:].any(), (case["name"], m)
+        e.optimize_hyper(50, 8)                                         # MVTM_OPT_BETA
+        hf = e.get_hyper_full()
+        assert np.allclose(hf["beta"], case["optimize_beta"]["beta"], rtol=1e-9, atol=0), case["name"]
+        assert np.allclose(hf["betaSum"], case["optimize_beta"]["betaSum"], rtol=1e-9, atol=0), case["name"]
+
+
+def test_engine_trajectory_matches_reference_bytecode(engine_lib, oracle_mod):
+    """north_star check (c) against THE REFERENCE: the log-likelihood trajectory of the reference's own sampler + updater bytecode
+    (tests/golden/reference_trajectory.json: 30 sweeps over a 400-document two-view corpus, burn-in ramp of p_a, LL by the jar's
+    modelLogLikelihood every 5 sweeps) vs the engine from the same initial assignments with its own randomness and its
+    asynchronous sweeps.
+
+    One run on 11 K tokens is noisy -- the reference's own seed-to-seed spread here is +-0.9 % (text view) and +-2.6 % (the
+    1.5 K-token side view), measured with the reference-faithful oracle, which reproduces the jar's run token for token
+    (tests/test_reference_vectors.py) and is therefore the reference with other random numbers.  So the comparison is between
+    ENSEMBLES: the jar's trajectory plus five reference-faithful runs vs six engine runs; the means must agree within 1 % (text
+    view; 3 % = three standard errors on the tiny side view) at every checkpoint, and on the text view every engine run must
+    stay within 1 % + four reference standard deviations of the reference mean."""
+    import json
+    from mvtopicmodel_b200 import Engine
+    O = oracle_mod
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_trajectory.json")))
+    K, Vs = g["K"], g["V"]
+    views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in g["views"]]
+    M = len(Vs)
+    present = [np.ones(len(views[0][0]) - 1, dtype=np.uint8)] + [((v[0][1:] - v[0][:-1]) > 0).astype(np.uint8) for v in views[1:]]
+    marks = {it: np.array(ll) for it, ll in g["loglik"]}
+    checkpoints = [it for it in sorted(marks) if it > 0]
+    z0 = [np.array(z, dtype=np.int32) for z in g["z0"]]
+    ref_runs = [np.array([marks[it] for it in checkpoints])]                 # the jar's own run
+    for seed in range(1, 6):
+        o = O.Oracle(K, Vs, views, seed=seed, present=present)
+        o.set_assignments(z0); o.rebuild_trees()
+        traj = []
+        for it in range(1, checkpoints[-1] + 1):
+            o.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+            o.sweep(it, O.F_STALE_TREES | O.F_Q1_COMPAT)
+            if it in marks:
+                traj.append(o.loglik(True))
+        ref_runs.append(np.array(traj))
+    eng_runs = []
+    for seed in (77, 1, 2, 3, 4, 5):
+        e = Engine(K, Vs, views, seed=seed, present=present, max_ctas=2, warps_per_cta=2)     # a few documents in flight
+        for m in range(M):
+            e.set_assignments(m, z0[m])
+        assert np.allclose(e.loglik(True), marks[0], rtol=1e-10)          # same state, same formula (incl. Q18)
+        traj = []
+        for it in range(1, checkpoints[-1] + 1):
+            e.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+            e.sweep(it)
+            if it in marks:
+                traj.append(e.loglik(True))
+        assert e.check_invariants() == 0
+        eng_runs.append(np.array(traj))
+    ref_runs, eng_runs = np.array(ref_runs), np.array(eng_runs)           # [run, checkpoint, view]
+    ref_mean, eng_mean = ref_runs.mean(0), eng_runs.mean(0)
+    rel = np.abs(eng_mean - ref_mean) / np.abs(ref_mean)
+    print("checkpoints", checkpoints, "\n mean engine", eng_mean.round(0).tolist(), "\n mean reference", ref_mean.round(0).tolist(), "\n rel", rel.round(4).tolist())
+    # text view (9.8 K tokens): 1 % (observed over repeated trials: 0.1-0.6 %).  The side view has 1.5 K tokens and a run-to-run
+    # spread of +-2.6 % in the reference itself, so the standard error of a six-run mean is ~1 % there: it is held to 3 standard
+    # errors (observed: 0.1-1.4 %)
+    assert np.all(rel[:, 0] < REL_TOL_LL) and np.all(rel[:, 1:] < 3 * REL_TOL_LL), rel
+    # no single engine run strays from the reference mean on the text view by more than 1 % plus four run-to-run standard
+    # deviations of the reference itself (pooled over the checkpoints: ~0.35 %; the known engine runs stay within 0.9 %)
+    sd_rel = np.sqrt(np.mean((ref_runs[:, :, 0].std(0, ddof=1) / np.abs(ref_mean[:, 0])) ** 2))
+    dev = np.abs(eng_runs[:, :, 0] - ref_mean[:, 0]) / np.abs(ref_mean[:, 0])
+    assert dev.max() < REL_TOL_LL + 4 * sd_rel, (dev.max(), sd_rel)
