@@ -39,6 +39,16 @@ typedef enum {
 /* mvtm_config.flags */
 #define MVTM_FLAG_DOC_ORDER   1u   /* work list in plain document order instead of longest-first (tests)     */
 #define MVTM_FLAG_SINGLE_WARP 2u   /* run each view pass with one warp: fully sequential, deterministic (tests) */
+#define MVTM_FLAG_Q1_COMPAT   4u   /* reproduce the reference's dense topic index exactly (quirk Q1): a topic is removed from the
+                                      document's index when no view holds it any more (W:441-468) and is NEVER re-inserted (the
+                                      insertion code W:563-584 is dead), so a topic gained later in the same sweep keeps only its
+                                      F+tree mass until the next sweep.  Default off: the index is "topics the document holds".
+                                      Limits a document-view to 32767 tokens. */
+#define MVTM_FLAG_BETA_MALLET 8u   /* draw the view-coupling matrix p[m][i] (W:327-337) from the law of MALLET's Randoms.nextBeta, which the
+                                      reference calls at W:333, instead of the true Beta(p_a, 1): for p_a > 1 that is a truncated normal
+                                      N(1, 0.25/(p_a - 1)) on [0, 1] (quirk Q5: its rejection test compares against NaN).  Same law for
+                                      p_a <= 1. */
+#define MVTM_FLAG_REFERENCE_COMPAT (MVTM_FLAG_Q1_COMPAT | MVTM_FLAG_BETA_MALLET)   /* both: the reference's behaviour, quirks included */
 
 typedef struct mvtm_config {
     int32_t num_topics;              /* K, M:183 numTopics                                                   */
@@ -154,6 +164,14 @@ int mvtm_heldout_loglik(mvtm_handle *h, int32_t m, const int64_t *eval_off, cons
  * (NULL = identity).  probs_out[0..K) normalised, probs_out[K] = share of the new-topic bucket (W:515). */
 int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, double *probs_out);
 
+/* The same probe, extended.  tree_mode: 0 = the trainer's trees (gamma*alpha*phi leaves, inactive topics masked, M:2660-2691);
+ * 2 = the inferencer's trees (bare phi leaves, empty inactive set, I:561-576 / I:243, quirk Q13) -- what mvtm_sweep's
+ * update_global = 2 samples from.  not_in_S (n_not_in_S >= 0; -1 = none): the reference's dense index under quirk Q1 -- topics the
+ * document holds that the index lacks at this token (gained earlier in the sweep); their document and other-view terms are dropped
+ * exactly as W:501-513 does when it walks S.  The token's own removal (W:434-471) is applied on top.  Works on any handle. */
+int mvtm_cond_probs_ex(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, int32_t tree_mode,
+                       const int32_t *not_in_S, int32_t n_not_in_S, double *probs_out);
+
 /* n_wk == histogram of (word, z), n_k == histogram of z, no negative cell.
  * *violations_out = number of offending cells (0 = consistent). */
 int mvtm_check_invariants(mvtm_handle *h, int64_t *violations_out);
@@ -231,7 +249,7 @@ int mvtm_get_hyper_full(mvtm_handle *h, double *alpha, double *alpha_sum, double
                         double *p_a, double *p_b, double *p_mean, double *gamma_root, double *gamma_view, double *tables_cnt);
 
 /* Test hooks for the host-side samplers of the hyper-parameter step (no device work): `which` 0 = uniform, 1 = Gamma(a,1),
- * 2 = Beta(a,b), 3 = Antoniak(alpha = a, n = b); and MALLET's learnSymmetricConcentration as restated in this build. */
+ * 2 = Beta(a,b), 3 = Antoniak(alpha = a, n = b), 4 = the sweep's MVTM_FLAG_BETA_MALLET draw (MALLET's Randoms.nextBeta law); and MALLET's learnSymmetricConcentration as restated in this build. */
 int mvtm_test_sampler(uint64_t seed, int32_t which, double a, double b, int32_t n, double *out);
 double mvtm_test_learn_symmetric_concentration(const int64_t *count_hist, int32_t n_count, const int64_t *length_hist,
                                                int32_t n_length, int32_t num_dimensions, double current);

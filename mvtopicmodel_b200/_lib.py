@@ -26,6 +26,9 @@ class MvtmSweepStats(C.Structure):
 
 FLAG_DOC_ORDER = 1
 FLAG_SINGLE_WARP = 2
+FLAG_Q1_COMPAT = 4
+FLAG_BETA_MALLET = 8
+FLAG_REFERENCE_COMPAT = 12
 OPT_P, OPT_DP, OPT_GAMMA, OPT_BETA, OPT_ALL = 1, 2, 4, 8, 15
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -52,6 +55,7 @@ SIGNATURES = {
     "mvtm_loglik_parts": (_i32, [_vp, _vp, _vp, _i32]),
     "mvtm_heldout_loglik": (_i32, [_vp, _i32, _vp, _vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "mvtm_cond_probs": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "mvtm_cond_probs_ex": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _i32, _vp]),
     "mvtm_check_invariants": (_i32, [_vp, C.POINTER(_i64)]),
     "mvtm_stats": (_i32, [_vp, C.POINTER(MvtmSweepStats)]),
     "mvtm_delta_begin": (_i32, [_vp]),

@@ -72,6 +72,7 @@ struct mvtm_handle {
     bool sweep_open = false;
     int open_launches = 0, open_mode = 1;
     int *work_counter = nullptr;
+    unsigned *rbits = nullptr;                      // MVTM_FLAG_Q1_COMPAT: per document KS/32 flag words (see SweepParams::rbits)
     float *oc_scratch = nullptr;                    // multi-view: Kp floats per resident document slot
     size_t oc_scratch_floats = 0;
     unsigned long long *d_stats = nullptr;
@@ -196,7 +197,7 @@ extern "C" int mvtm_destroy(mvtm_handle *h)
     for (int m = 0; m < h->M; m++) free_view(h->v[m]);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (int m = 0; m < MVTM_MAX_VIEWS; m++) { if (h->ev_done[m]) cudaEventDestroy(h->ev_done[m]); if (h->ev_ready[m]) cudaEventDestroy(h->ev_ready[m]); }
-    cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad); cudaFree(h->oc_scratch);
+    cudaFree(h->work_counter); cudaFree(h->d_stats); cudaFree(h->d_bad); cudaFree(h->oc_scratch); cudaFree(h->rbits);
     for (auto &ev : h->host_ev) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -232,6 +233,8 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
         long long len = doc_off[d + 1] - doc_off[d];
         if (len < 0) FAIL(h, MVTM_ERR_ARG, "mvtm_add_view: doc_off not monotone at doc %lld", d);
         if (len > 65535) FAIL(h, MVTM_ERR_LIMIT, "mvtm_add_view: doc %lld holds %lld tokens in view %d (limit 65535)", d, len, m);
+        if ((h->flags & MVTM_FLAG_Q1_COMPAT) && len > 32767)
+            FAIL(h, MVTM_ERR_LIMIT, "mvtm_add_view: doc %lld holds %lld tokens in view %d (limit 32767 with MVTM_FLAG_Q1_COMPAT)", d, len, m);
         max_len = std::max<int>(max_len, (int)len);
     }
     const long long N = doc_off[D];
@@ -485,14 +488,16 @@ static void fill_params(mvtm_handle *h, int m, int iteration, int update_global,
     }
     P.word = v.word; P.nwk = v.nwk; P.nk_frozen = v.nk_snap; P.nk_live = v.nk;
     P.ga_tree = (update_global == 2) ? v.ga_one : v.ga_tree;            // 2 = inferencer mode with bare-phi trees (I:561-576, Q13)
-    if (update_global == 2) update_global = 0;
     P.beta = (float)h->beta[m]; P.betaSum = (float)h->betaSum[m];
     P.n_inactive = (int)h->inactive.size(); P.first_inactive = h->inactive.empty() ? 0 : h->inactive[0];
+    if (update_global == 2) { update_global = 0; P.n_inactive = 0; P.first_inactive = 0; }   // I:243: the inferencer's inactive set is empty
+    P.beta_mallet = (h->flags & MVTM_FLAG_BETA_MALLET) ? 1 : 0;
     P.seed_lo = (unsigned)h->seed; P.seed_hi = (unsigned)(h->seed >> 32); P.iteration = (unsigned)iteration;
     P.doc_id_base = h->doc_id_base; P.doc_id_stride = h->doc_id_stride;
     P.update_global = update_global;
     P.stats = h->d_stats;
     P.oc_scratch = h->oc_scratch;
+    P.rbits = h->rbits; P.rb_one = nullptr;
 }
 
 static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
@@ -568,21 +573,27 @@ static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
 }
 
 template <int KS, int G, bool MULTI>
-static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cudaStream_t s)
+static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cudaStream_t s, bool q1)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_sweep_view<KS, G, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
-    if (e != cudaSuccess) return e;
-    k_sweep_view<KS, G, MULTI><<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
+        return cudaGetLastError();
+    };
+    return q1 ? go(k_sweep_view<KS, G, MULTI, true>) : go(k_sweep_view<KS, G, MULTI, false>);
 }
 template <int KS, int G, bool MULTI>
-static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const double *p_row, double *out, cudaStream_t s)
+static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const double *p_row, double *out, cudaStream_t s, bool q1)
 {
     size_t smem = smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(32 / G) * smem_doc_bytes(KS, 1, MULTI);
-    cudaError_t e = cudaFuncSetAttribute(k_cond_probe<KS, G, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_cond_probe<KS, G, MULTI><<<1, 32, smem, s>>>(P, d, pos, p_row, out);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<1, 32, smem, s>>>(P, d, pos, p_row, out);
+        return cudaGetLastError();
+    };
+    return q1 ? go(k_cond_probe<KS, G, MULTI, true>) : go(k_cond_probe<KS, G, MULTI, false>);
 }
 
 #define DISPATCH_KG(KS_, G_, MULTI_, CALL)                                                        \
@@ -599,7 +610,7 @@ static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const do
 static cudaError_t launch_sweep(mvtm_handle *h, const SweepParams &P, const LaunchCfg &lc)
 {
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL_SWEEP(KS_, G_, MU_) e = launch_sweep_t<KS_, G_, MU_>(P, lc, h->stream)
+#define CALL_SWEEP(KS_, G_, MU_) e = launch_sweep_t<KS_, G_, MU_>(P, lc, h->stream, (h->flags & MVTM_FLAG_Q1_COMPAT) != 0)
     if (h->M > 1) { DISPATCH_KG(h->KS, h->G, true, CALL_SWEEP) } else { DISPATCH_KG(h->KS, h->G, false, CALL_SWEEP) }
 #undef CALL_SWEEP
     return e;
@@ -643,6 +654,17 @@ static int wait_all_ready(mvtm_handle *h)
     return MVTM_OK;
 }
 
+// MVTM_FLAG_Q1_COMPAT: the reference rebuilds a document's dense index at the start of every sweep (W:376-391), so the "not in the
+// index" flags that multi-view passes hand to each other start from zero each sweep.
+static int clear_q1_flags(mvtm_handle *h)
+{
+    if (!(h->flags & MVTM_FLAG_Q1_COMPAT) || h->M < 2 || h->D == 0) return MVTM_OK;
+    const size_t bytes = (size_t)h->D * (h->KS / 32) * 4;
+    if (!h->rbits) CK(h, cudaMalloc(&h->rbits, bytes));
+    CK(h, cudaMemsetAsync(h->rbits, 0, bytes, h->stream));
+    return MVTM_OK;
+}
+
 // Queues view m's pass (n_k snapshot, work counter reset, k_sweep_view) on the handle's stream; no host synchronisation.
 static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, int m, int *launches)
 {
@@ -674,6 +696,7 @@ static int open_sweep(mvtm_handle *h)
     if (int rc = require_views(h, "mvtm_sweep")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = upload_hyper(h)) return rc;
+    if (int rc = clear_q1_flags(h)) return rc;
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(h, cudaEventRecord(h->ev[0], h->stream));
     for (int m = 0; m < h->M; m++) h->pass_queued[m] = false;
@@ -840,6 +863,7 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
             CK(h, cudaGetLastError());
         }
     }
+    if (int rc = clear_q1_flags(h)) return rc;
     CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     CK(h, cudaEventRecord(h->ev[0], h->stream));
     int launches = 0;
@@ -897,9 +921,29 @@ extern "C" int mvtm_stats(mvtm_handle *h, mvtm_sweep_stats *out)
     return MVTM_OK;
 }
 
+static int cond_probs_impl(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, const int32_t *not_in_S, int32_t n_not,
+                           double *probs_out, int tree_mode = 0);
+
 extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, double *probs_out)
 {
     if (!h) return MVTM_ERR_ARG;
+    return cond_probs_impl(h, m, doc, pos, p_row, nullptr, -1, probs_out);
+}
+
+extern "C" int mvtm_cond_probs_ex(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, int32_t tree_mode,
+                                  const int32_t *not_in_S, int32_t n_not_in_S, double *probs_out)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (tree_mode != 0 && tree_mode != 2) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs_ex: tree_mode must be 0 (trainer) or 2 (inferencer)");
+    if (n_not_in_S < -1 || (n_not_in_S > 0 && !not_in_S)) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs_ex: bad not_in_S list");
+    for (int i = 0; i < n_not_in_S; i++)
+        if (not_in_S[i] < 0 || not_in_S[i] >= h->K) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs_ex: topic %d out of range", not_in_S[i]);
+    return cond_probs_impl(h, m, doc, pos, p_row, not_in_S, n_not_in_S, probs_out, tree_mode);
+}
+
+static int cond_probs_impl(mvtm_handle *h, int32_t m, int64_t doc, int32_t pos, const double *p_row, const int32_t *not_in_S, int32_t n_not,
+                           double *probs_out, int tree_mode)
+{
     if (int rc = require_views(h, "mvtm_cond_probs")) return rc;
     if (m < 0 || m >= h->M || doc < 0 || doc >= h->D || !probs_out) FAIL(h, MVTM_ERR_ARG, "mvtm_cond_probs: bad argument");
     ViewDev &v = h->v[m];
@@ -921,16 +965,26 @@ extern "C" int mvtm_cond_probs(mvtm_handle *h, int32_t m, int64_t doc, int32_t p
     CK(h, cudaMemcpyAsync(d_p, prow.data(), (size_t)h->M * 8, cudaMemcpyHostToDevice, h->stream));   // ordered before the probe
     CK(h, cudaStreamSynchronize(h->stream));                                                           // prow is a local
     SweepParams P;
-    fill_params(h, m, 0, 0, P);
+    fill_params(h, m, 0, tree_mode, P);
     P.nk_frozen = v.nk;                                                  // frozen counts = the current ones
     P.R = 1;
+    P.rbits = nullptr;
+    unsigned *d_rb = nullptr;
+    const bool q1 = n_not >= 0;                                          // Q1 probe: the caller names the held topics the index lacks
+    if (q1) {
+        std::vector<unsigned> words((size_t)h->KS / 32, 0u);
+        for (int i = 0; i < n_not; i++) words[(size_t)not_in_S[i] >> 5] |= 1u << (not_in_S[i] & 31);
+        CK(h, cudaMalloc(&d_rb, words.size() * 4));
+        CK(h, cudaMemcpy(d_rb, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+        P.rb_one = d_rb;
+    }
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL_PROBE(KS_, G_, MU_) e = launch_probe_t<KS_, G_, MU_>(P, (int)doc, pos, d_p, d_out, h->stream)
+#define CALL_PROBE(KS_, G_, MU_) e = launch_probe_t<KS_, G_, MU_>(P, (int)doc, pos, d_p, d_out, h->stream, q1)
     if (h->M > 1) { DISPATCH_KG(h->KS, h->G, true, CALL_PROBE) } else { DISPATCH_KG(h->KS, h->G, false, CALL_PROBE) }
 #undef CALL_PROBE
     if (e == cudaSuccess) e = cudaMemcpyAsync(probs_out, d_out, (size_t)(h->K + 1) * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_out); cudaFree(d_p);
+    cudaFree(d_out); cudaFree(d_p); cudaFree(d_rb);
     CK(h, e);
     return MVTM_OK;
 }

@@ -48,10 +48,14 @@ struct SweepParams {
     unsigned seed_lo, seed_hi, iteration;
     long long doc_id_base, doc_id_stride;
     int update_global;
+    int beta_mallet;                  // MVTM_FLAG_BETA_MALLET: the view-coupling draw follows MALLET's Randoms.nextBeta (quirk Q5)
     int R;                            // ring depth
     unsigned long long *stats;        // [0] tokens, [1] changed, [2] new-topic draws
     float *oc_scratch;                // (multi-view) per resident document slot: Kp floats, see DocCtx::oc
     int oc_smem;                      // (multi-view) 1: keep DocCtx::oc in shared memory instead (views of short documents)
+    unsigned *rbits;                  // Q1 mode: per document KS/32 words, bit t = "topic t is NOT in the document's dense index for the
+                                      //   rest of this sweep" (it left it, or was gained while absent); carried across the view passes
+    unsigned *rb_one;                 // probe: the flags of the probed document (overrides rbits)
     int *z_host;                      // mvtm_sweep_host: device alias of the caller's pinned array of view m (NULL: none); every
                                       //   token block's new assignments are stored there too, so no copy follows the pass
 };
@@ -59,12 +63,20 @@ struct SweepParams {
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+__host__ __device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t h0 = mulhi_u32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = mulhi_u32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
         uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
         c0 = n0; c1 = l1; c2 = n2; c3 = l0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -126,6 +138,7 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 // lane gl = c % G and is that lane's j = c / G -th chunk (JG = KS / (4 G) chunks per lane).
 // ------------------------------------------------------------------------------------------------
 struct DocCtx {
+    unsigned *rb;          // (Q1) the document's flag words in global memory, NULL if none are kept (single-view sweeps)
     uint32_t sa;           // .shared address of the document's area: q at +0, n_d at +4*KS (see carve_doc)
     float *q;              // KS
     unsigned short *nd;    // KS
@@ -159,19 +172,35 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
 
 // n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over the chunk).  Executed by the lane that
 // owns topic t (gl == (t >> 2) % G), W:434-471 / W:557-584.
-template <int KS, int G, bool MULTI>
+// Q1 (reference-exact dense index, MVTM_FLAG_Q1_COMPAT): bit 15 of n_d[t] flags "t is not in S for the rest of the sweep".  The
+// reference removes a topic from S when no view of the document holds it any more (W:441-468) and never inserts one (W:563-584 is
+// dead code), so S = {held and not flagged} with the flag set when the topic leaves or is gained while absent
+// (tests/test_reference_vectors.py::test_flag_rule_equals_reference_dense_index).  A flagged topic keeps only its tree mass.
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl, int gl, float (&bsq)[KS / (4 * G)])
 {
     constexpr int JG = KS / (4 * G);
     const uint32_t nd_a = c.sa + (uint32_t)KS * 4u + 2u * (uint32_t)t;
-    const unsigned ndv_i = (unsigned)((int)lds_u16(nd_a) + dl);
-    sts_u16(nd_a, ndv_i);
-    const float ndv = (float)ndv_i;
+    const unsigned raw = lds_u16(nd_a);
+    unsigned flag = Q1 ? (raw >> 15) : 0u;
+    const unsigned before = Q1 ? (raw & 0x7fffu) : raw;
+    const unsigned ndv_i = (unsigned)((int)before + dl);
+    bool oth = false;
+    if (MULTI) oth = (c.om[t >> 5] >> (t & 31)) & 1u;
+    if (Q1) {
+        const bool leaves = (dl < 0) && (ndv_i == 0u) && !oth;
+        const bool gained_absent = (dl > 0) && (before == 0u) && !oth;
+        if (!flag && (leaves || gained_absent)) {
+            flag = 1u;
+            if (c.rb) atomicOr(c.rb + (t >> 5), 1u << (t & 31));
+        }
+    }
+    sts_u16(nd_a, Q1 ? (ndv_i | (flag << 15)) : ndv_i);
+    const float ndv = (Q1 && flag) ? 0.f : (float)ndv_i;
     bool inS = false; float ocv = 0.f, pri = 0.f;
     if (MULTI) {
         // branch-light on purpose: the lane groups of a warp hold different documents and would serialise on branches
-        const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
-        inS = (ndv_i > 0u) || oth;
+        inS = ((ndv_i > 0u) || oth) && !(Q1 && flag);
         pri = prior_other<MULTI>(P, c, t);
         if (oth) ocv = c.oc[t];
     }
@@ -187,7 +216,7 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
 // one step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the owners
 // differ (a second pass runs only when one lane owns both).  No warp-level synchronisation inside: the lane groups of a
 // warp may diverge here.
-template <int KS, int G, bool MULTI>
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int tinc, int tdec, int gl, float (&bsq)[KS / (4 * G)])
 {
     if (tinc == tdec) return;                                   // same topic: the two changes cancel
@@ -196,9 +225,50 @@ __device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int 
     if (gl == own_i) { t = tinc; dl = 1; if (own_i == own_d) t2 = tdec; } else if (gl == own_d) { t = tdec; dl = -1; }
 #pragma unroll 1
     while (t >= 0) {
-        apply_count_delta<KS, G, MULTI>(P, c, t, dl, gl, bsq);
+        apply_count_delta<KS, G, MULTI, Q1>(P, c, t, dl, gl, bsq);
         t = t2; t2 = -1; dl = -1;
     }
+}
+
+// cc.mallet.util.Randoms.nextBeta(a, b) -- the law the reference draws p[m][i] from at W:333 -- restated literally over a
+// counter-based stream (block k of the stream = Philox(k, c1, c2, c3); its words 1..3 are used, word 0 of block 0 is the default
+// law's inversion uniform).  Quirk Q5: for a > 1, b == 1 the acceptance test compares against NaN (0 * log(inf)), so the first
+// normal proposal inside [0, 1] is returned: a truncated N(1, 0.25/(a-1)) instead of Beta(a, 1).  a, b < 1 (the burn-in ramp
+// starts at 0.31): Joehnk's method, which IS Beta(a, b).  Pinned against draws of the MALLET jar's own bytecode by
+// tests/test_optim_host.py::test_engine_mallet_beta_law_matches_mallet_bytecode (mvtm_test_sampler which = 4).
+struct BetaStream {
+    uint32_t c1, c2, c3, k0, k1, blk; uint4 x; int used;
+    __host__ __device__ double next()
+    {   // 24-bit uniforms, three per Philox block
+        if (used == 3) { x = philox4x32_10(blk++, c1, c2, c3, k0, k1); used = 0; }
+        const uint32_t w = used == 0 ? x.y : (used == 1 ? x.z : x.w);
+        used++;
+        return (double)(w >> 8) * (1.0 / 16777216.0);
+    }
+    __host__ __device__ double gauss()
+    {   double u1; do { u1 = next(); } while (u1 <= 0.0); const double u2 = next();
+        return sqrt(-2.0 * log(u1)) * cos(2.0 * 3.14159265358979323846 * u2); }
+};
+__host__ __device__ inline double mallet_next_beta(BetaStream &r, double a, double b)
+{
+    if (a == 1.0 && b == 1.0) return r.next();
+    if (a >= 1.0 && b >= 1.0) {
+        const double A = a - 1.0, B = b - 1.0, C = A + B, L = C * log(C), mu = A / C, sigma = 0.5 / sqrt(C);
+        double y = r.gauss(), x = sigma * y + mu;
+        int guard = 0;
+        while ((x < 0.0 || x > 1.0) && ++guard < 4096) { y = r.gauss(); x = sigma * y + mu; }
+        double u = r.next();
+        // b == 1: B*log((1-x)/B) = 0*log(inf) = NaN -> the comparison is false -> the first proposal is accepted (Q5)
+        while (log(u) >= A * log(x / A) + B * log((1.0 - x) / B) + L + 0.5 * y * y && ++guard < 4096) {
+            y = r.gauss(); x = sigma * y + mu;
+            while ((x < 0.0 || x > 1.0) && ++guard < 4096) { y = r.gauss(); x = sigma * y + mu; }
+            u = r.next();
+        }
+        return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
+    }
+    double v1, v2; int guard = 0;
+    do { v1 = pow(r.next(), 1.0 / a); v2 = pow(r.next(), 1.0 / b); } while (v1 + v2 > 1.0 && ++guard < 4096);
+    return v1 / (v1 + v2);
 }
 
 // the view-coupling draw p[m][i] of W:327-337 for document gdoc (every lane of the group computes the same value)
@@ -211,9 +281,16 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
     else if (P.pa[i] == 0.0) r = 0.0;
     else {
         int lo = m < i ? m : i, hi = m < i ? i : m;
-        uint4 x = philox4x32_10(0u, gdoc, P.iteration, ((uint32_t)(lo * P.M + hi) << 8) | PURPOSE_PDRAW, P.seed_lo, P.seed_hi);
-        double u = (double)(x.x >> 8) * (1.0 / 16777216.0);
-        double b = pow(u, 1.0 / P.pa[i]);                       // Beta(a,1) by inversion (Q5: true law)
+        const uint32_t tag = ((uint32_t)(lo * P.M + hi) << 8) | PURPOSE_PDRAW;
+        uint4 x = philox4x32_10(0u, gdoc, P.iteration, tag, P.seed_lo, P.seed_hi);
+        double b;
+        if (P.beta_mallet) {
+            BetaStream st{ gdoc, P.iteration, tag, P.seed_lo, P.seed_hi, 1u, x, 0 };
+            b = mallet_next_beta(st, P.pa[i], P.pb[i]);
+        } else {
+            double u = (double)(x.x >> 8) * (1.0 / 16777216.0);
+            b = pow(u, 1.0 / P.pa[i]);                          // Beta(a,1) by inversion (Q5: true law)
+        }
         r = floor(1000.0 * b + 0.5) / 1000.0;                   // W:333 Math.round(1000*x)/1000
     }
     if (!p_override && i != 0 && P.sparse[i]) r = 0.0;          // W:335-336 (column i zeroed, incl. the diagonal)
@@ -229,12 +306,14 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
 // leaves it empty again, so nothing is scanned densely.  (The first version zeroed, histogrammed and scanned all KS
 // topics per other view and evaluated the full q expression for every topic: ~4000 instructions per document at
 // K = 1000 -- more than sampling the 6-12 tokens of a side view.)
-template <int KS, int G, bool MULTI>
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d, int len, int gl, const double *p_override,
                                           bool skip_first, float (&bsq)[KS / (4 * G)])
 {
     constexpr int JG = KS / (4 * G);
     const int m = P.m;
+    c.rb = nullptr;
+    if (Q1) c.rb = P.rb_one ? P.rb_one : ((MULTI && P.rbits) ? P.rbits + (size_t)d * (KS / 32) : nullptr);   // one pass: nothing to carry
     const long long b = P.doc_off[m][d];
     const uint32_t gdoc = (uint32_t)(P.doc_id_base + (long long)d * P.doc_id_stride);
     unsigned *nd32 = reinterpret_cast<unsigned *>(c.nd);
@@ -290,16 +369,44 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         c.C = (P.n_inactive > 0) ? (P.ga_new[m] / ((float)len + P.gas[m]) * c.coefm) / (float)P.K : 0.f;
     }
     __syncwarp();
+    if (Q1) {
+        // flags raised while an earlier view of this document was sampled in this sweep: the reference keeps ONE dense index per
+        // document across its views (W:376-391 builds it once), so they still apply.  The barrier below is reached by every lane of
+        // the warp (the lane groups hold different documents: the WORK is predicated, never the __syncwarp)
+        if (c.rb && len != 0) {
+            for (int k = gl; k < KS / 32; k += G) {
+                unsigned wbits = c.rb[k];
+                while (wbits) {
+                    const int t = 32 * k + (__ffs(wbits) - 1);
+                    wbits &= wbits - 1u;
+                    atomicOr(&nd32[t >> 1], 0x8000u << ((t & 1) * 16));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    int t_first = -1;
     {   // own-view histogram (W:352-359).  With skip_first the document's first token is left out: it is the first to
         // be resampled, so its removal (W:434-471) is folded into the setup
         const int *zm = P.zv[m] + b;
         for (int k = gl; k < len; k += G) {
             int t = zm[k];
-            if (k == 0 && skip_first && (unsigned)__ldg(P.word + b) < (unsigned)P.V) t = -1;
+            if (k == 0 && skip_first && (unsigned)__ldg(P.word + b) < (unsigned)P.V) { t_first = t; t = -1; }
             if (t >= 0) atomicAdd(&nd32[t >> 1], 1u << ((t & 1) * 16));
         }
     }
     __syncwarp();
+    if (Q1 && t_first >= 0) {
+        // the folded removal of the first token may take its topic out of the index (no view holds it any more, W:441-468)
+        const unsigned raw = c.nd[t_first];
+        bool oth = false;
+        if (MULTI) oth = (c.om[t_first >> 5] >> (t_first & 31)) & 1u;
+        if (raw == 0u && !oth) {
+            c.nd[t_first] = (unsigned short)0x8000u;
+            if (c.rb) atomicOr(c.rb + (t_first >> 5), 1u << (t_first & 31));
+        }
+    }
+    if (Q1) __syncwarp();
     // q of the topics some token of the document holds (S of W:376-391 plus, harmlessly, the skipped first token's topic):
     // one token per lane, duplicates recompute the same value
     for (int i = 0; i < (MULTI ? P.M : 1); i++) {
@@ -310,7 +417,9 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         for (int k = gl; k < leni; k += G) {
             const int t = zi[k];
             if (t < 0) continue;
-            const float ndv = (float)c.nd[t];
+            const unsigned raw = c.nd[t];
+            if (Q1 && (raw >> 15)) continue;                      // held but not in the index: only its tree mass, already in q
+            const float ndv = (float)(Q1 ? (raw & 0x7fffu) : raw);
             bool inS = false; float ocv = 0.f, pri = 0.f;
             if (MULTI) {
                 const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
@@ -446,7 +555,7 @@ __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bo
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int sweep_max_threads(int JG) { return JG <= 8 ? 768 : 512; }
 
-template <int KS, int G, bool MULTI>
+template <int KS, int G, bool MULTI, bool Q1>
 __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_view(const SweepParams P)
 {
     constexpr int JG = KS / (4 * G), NSUB = 32 / G;
@@ -527,7 +636,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             if ((unsigned)w >= (unsigned)P.V) w = 0;
             if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
-        doc_setup<KS, G, MULTI>(P, c, d, len, gl, nullptr, true, bsq);
+        doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, nullptr, true, bsq);
         // pipeline stage 2 (d_n has arrived during the setup): next document's extent and first tokens
         const long long b_n = P.doc_off[m][d_n];
         const int len_n = have_n ? (int)(P.doc_off[m][d_n + 1] - b_n) : 0;
@@ -575,7 +684,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
-                apply_pair<KS, G, MULTI>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
+                apply_pair<KS, G, MULTI, Q1>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
                 if (valid) {
                     if (nt != ot && P.update_global) {                       // U:197-218
                         const int tsel = (gl & 1) ? ot : nt, v = (gl & 1) ? -1 : 1;
@@ -631,7 +740,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
 // parity probe: conditional of one token on frozen counts, same device functions as the sweep.  One warp; every lane
 // group works on the same document in its own shared-memory area, group 0 writes the result.
 // ------------------------------------------------------------------------------------------------
-template <int KS, int G, bool MULTI>
+template <int KS, int G, bool MULTI, bool Q1>
 __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d, int pos, const double *p_row, double *out)
 {
     constexpr int JG = KS / (4 * G);
@@ -657,9 +766,9 @@ __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d
     float bsq[JG];
     const long long b = P.doc_off[P.m][d];
     const int len = (int)(P.doc_off[P.m][d + 1] - b);
-    doc_setup<KS, G, MULTI>(P, c, d, len, gl, p_row, false, bsq);
+    doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, p_row, false, bsq);
     const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
-    apply_pair<KS, G, MULTI>(P, c, -1, ot, gl, bsq);
+    apply_pair<KS, G, MULTI, Q1>(P, c, -1, ot, gl, bsq);
     for (int t = gl; t < KS; t += G) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
     __syncwarp();
     float cum[JG];

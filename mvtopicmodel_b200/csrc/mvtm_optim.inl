@@ -497,6 +497,11 @@ extern "C" int mvtm_test_sampler(uint64_t seed, int32_t which, double a, double 
             case 1: out[i] = rand_gamma(g, a); break;
             case 2: out[i] = rand_beta(g, a, b); break;
             case 3: try { out[i] = rand_antoniak(g, a, (int)b); } catch (...) { out[i] = 1; } break;
+            case 4: {   // the sweep kernel's MVTM_FLAG_BETA_MALLET draw (mallet_next_beta, mvtm_kernels.cuh) evaluated on the host
+                BetaStream st{ (uint32_t)i, 0u, PURPOSE_PDRAW, (uint32_t)seed, (uint32_t)(seed >> 32), 0u, make_uint4(0u, 0u, 0u, 0u), 3 };
+                out[i] = mallet_next_beta(st, a, b);
+                break;
+            }
             default: return MVTM_ERR_ARG;
         }
     }

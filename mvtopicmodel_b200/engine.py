@@ -182,10 +182,17 @@ class Engine:
                 "ring_depth": [s.ring_depth[m] for m in range(self.M)], "ring_locked": [s.ring_locked[m] for m in range(self.M)]}
 
     # --- readers -----------------------------------------------------------------------------------
-    def cond_probs(self, m, doc, pos, p_row=None):
+    def cond_probs(self, m, doc, pos, p_row=None, not_in_S=None, tree_mode=0):
+        """not_in_S (optional): held topics the reference's dense index lacks at this token (quirk Q1); tree_mode 2 = the
+        inferencer's bare-phi trees (mvtm_cond_probs_ex)."""
         out = np.empty(self.K + 1, dtype=np.float64)
         pr = None if p_row is None else np.ascontiguousarray(p_row, dtype=np.float64)
-        self._ck(self.L.mvtm_cond_probs(self.h, int(m), int(doc), int(pos), _ptr(pr), _ptr(out)))
+        if not_in_S is None and tree_mode == 0:
+            self._ck(self.L.mvtm_cond_probs(self.h, int(m), int(doc), int(pos), _ptr(pr), _ptr(out)))
+        else:
+            ex = None if not_in_S is None else np.ascontiguousarray(list(not_in_S), dtype=np.int32)
+            self._ck(self.L.mvtm_cond_probs_ex(self.h, int(m), int(doc), int(pos), _ptr(pr), int(tree_mode), _ptr(ex),
+                                               -1 if ex is None else len(ex), _ptr(out)))
         return out
 
     def loglik(self, quirk_len2=False):

@@ -812,13 +812,16 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
 /* ------------------------------------------------------------------------------------------------ */
 /* conditional distribution of one token on frozen counts                                            */
 /* ------------------------------------------------------------------------------------------------ */
-int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, double *out);
+int orc_cond_probs_ex(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, unsigned flags, double *out);
+int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, double *out)
+{ return orc_cond_probs_ex(o, m, d, pos, p_in, engine_form, not_in_S, 0, out); }
 int orc_cond_probs(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, double *out)
-{ return orc_cond_probs_q1(o, m, d, pos, p_in, engine_form, NULL, out); }
+{ return orc_cond_probs_ex(o, m, d, pos, p_in, engine_form, NULL, 0, out); }
 
 /* not_in_S (K flags, may be NULL): topics the document holds that the reference's dense index lacks at this token (quirk Q1:
  * gained earlier in the sweep); the token's own removal (W:434-471) is applied here on top of it. */
-int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, double *out)
+/* flags: ORC_F_BARE_TREES = the inferencer's trees (I:561-576: leaves hold phi without gamma*alpha and ignore the inactive set, Q13) */
+int orc_cond_probs_ex(orc_t *o, int m, int64_t d, int pos, const double *p_in, int engine_form, const uint8_t *not_in_S, unsigned flags, double *out)
 {   /* reference form: masses of the three buckets of W:495-538 with freshly built trees (M:2660-2691);
      * engine form: the dense net distribution.  Both from the sweep-start state of the document (Q1/Q3
      * do not matter there).  out[0..K) normalised probabilities, out[K] = share of the new-topic bucket. */
@@ -845,7 +848,9 @@ int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, i
     double total = C;
     if (engine_form) {
         g_not_in_S = not_in_S;
+        g_engine_weight_flags = flags;
         engine_weights(o, m, w, s->nd, len, p, o->n_k[m], out);
+        g_engine_weight_flags = 0;
         g_not_in_S = NULL;
         for (int t = 0; t < K; t++) total += out[t];
     } else {
@@ -864,7 +869,8 @@ int orc_cond_probs_q1(orc_t *o, int m, int64_t d, int pos, const double *p_in, i
                 double phi = (row[t] + o->beta[m]) / (o->n_k[m][t] + o->betaSum[m]);
                 A = (p[m][m] * s->nd[m * K + t] + O) * phi;
             }
-            double leaf = (o->n_inactive && is_inactive(o, t)) ? 0.0 : leaf_value(o, m, w, t);
+            double leaf = (flags & ORC_F_BARE_TREES) ? phi_value(o, m, w, t)
+                                                     : ((o->n_inactive && is_inactive(o, t)) ? 0.0 : leaf_value(o, m, w, t));
             out[t] = A + leaf;
             total += out[t];
         }

@@ -100,6 +100,7 @@ def lib():
             "orc_cond_probs": (i32, [p, i32, i64, i32, p, i32, p]),
             "orc_rule_violations": (C.c_longlong, [p]),
             "orc_cond_probs_q1": (i32, [p, i32, i64, i32, p, i32, p, p]),
+            "orc_cond_probs_ex": (i32, [p, i32, i64, i32, p, i32, p, u32, p]),
             "orc_engine_select": (i32, [p, i32, dbl, dbl, i32]),
             "orc_loglik": (i32, [p, p, i32]),
             "orc_check_invariants": (i64, [p]),
@@ -269,14 +270,15 @@ class Oracle:
         if rc:
             raise RuntimeError(f"orc_sweep_mt rc={rc}")
 
-    def cond_probs(self, m, doc, pos, p=None, engine_form=False, not_in_S=None):
-        """not_in_S: topics the document holds that the reference's dense index lacks at this token (quirk Q1)."""
+    def cond_probs(self, m, doc, pos, p=None, engine_form=False, not_in_S=None, flags=0):
+        """not_in_S: topics the document holds that the reference's dense index lacks at this token (quirk Q1).
+        flags: F_BARE_TREES for the inferencer's trees (phi leaves without gamma*alpha, Q13)."""
         out = np.zeros(self.K + 1, dtype=np.float64)
         pm = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
         ex = None
         if not_in_S is not None:
             ex = np.zeros(self.K, dtype=np.uint8); ex[list(not_in_S)] = 1
-        rc = lib().orc_cond_probs_q1(self.h, int(m), int(doc), int(pos), _ptr(pm), int(engine_form), _ptr(ex), _ptr(out))
+        rc = lib().orc_cond_probs_ex(self.h, int(m), int(doc), int(pos), _ptr(pm), int(engine_form), _ptr(ex), int(flags), _ptr(out))
         if rc:
             raise ValueError(f"orc_cond_probs rc={rc}")
         return out

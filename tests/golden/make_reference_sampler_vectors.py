@@ -325,7 +325,7 @@ def reference_optimize_beta(ref):
     return {"beta": model.fields["beta"], "betaSum": model.fields["betaSum"]}
 
 
-def reference_conditionals(ref, iteration, max_tokens=600):
+def reference_conditionals(ref, iteration, max_tokens=600, rebuild=True):
     """north_star check (b) against the reference itself: one sweep of the jar's sampler with the GLOBAL counts frozen (deltas
     dropped, the inferencer's nut = 0 mode, W:587) while the per-token masses it computes are read out of its frame at the moment
     it draws u (W:517): dense index S, cumulative document masses (W:496-513), new-topic mass C (W:515) and the leaves of the
@@ -335,7 +335,8 @@ def reference_conditionals(ref, iteration, max_tokens=600):
     on which Q1 HAS had an effect are recorded too, with the list of held topics the index lacks (`not_in_S`)."""
     vm, K, M = ref.vm, ref.K, ref.M
     recs = []
-    ref.rebuild_trees()          # fresh trees: during a sweep only two leaves per delta are refreshed (Q3), the check is on frozen, consistent state
+    if rebuild:                  # (the inferencer's own trees -- make_reference_inference_vectors.py -- must stay as they are)
+        ref.rebuild_trees()      # fresh trees: during a sweep only two leaves per delta are refreshed (Q3), the check is on frozen, consistent state
     saved_apply = vm.shims["java/util/Queue.add:(Ljava/lang/Object;)Z"]
     vm.shims["java/util/Queue.add:(Ljava/lang/Object;)Z"] = lambda loc, r, a, pc: 1          # counts stay frozen
     saved_nd = vm.shims["java/util/concurrent/ThreadLocalRandom.nextDouble:()D"]

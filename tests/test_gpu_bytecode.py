@@ -28,9 +28,11 @@ def test_engine_conditionals_match_reference_bytecode(engine_lib):
     """north_star check (b) against THE REFERENCE: the per-token conditional distributions the reference's sampler bytecode
     (FastQMVWVWorkerRunnable.sampleTopicsForOneDoc from the shipped jar, executed by tools/jvm_mini.py) computed on frozen counts
     -- its dense index, document masses, new-topic mass and F+tree leaves -- vs mvtm_cond_probs on the same state: 1e-5 relative
-    on every topic (fp32 scan on the device), incl. coupled views, inactive topics and the sparse-view sentinel."""
+    on every topic (fp32 scan on the device), incl. coupled views, inactive topics and the sparse-view sentinel -- and incl. the
+    tokens on which quirk Q1 is at work (a held topic is missing from the reference's dense index because it was gained earlier
+    in the sweep, `not_in_S`): those go through mvtm_cond_probs_ex with the reference's index, no record is filtered out."""
     from mvtopicmodel_b200 import Engine
-    n = 0
+    n = n_q1 = n_differs = 0
     for case, K, Vs, views in _reference_cases():
         M = len(Vs)
         e = Engine(K, Vs, views, seed=case["seed"])
@@ -40,9 +42,7 @@ def test_engine_conditionals_match_reference_bytecode(engine_lib):
         for m in range(M):
             e.set_assignments(m, frozen_z[m])
         frozen = [e.get_counts(m) for m in range(M)]
-        # tokens on which quirk Q1 has had no effect (the vectors also hold Q1-affected tokens, marked by `not_in_S`: on those the
-        # engine's documented index "topics the document holds" differs from the reference's by design)
-        for rec in [r for r in case["conditionals"] if not r.get("not_in_S")][::2]:
+        for rec in case["conditionals"]:
             zs = [z.copy() for z in frozen_z]
             for m, zd in enumerate(rec["z_doc"]):
                 if zd is not None:
@@ -51,14 +51,19 @@ def test_engine_conditionals_match_reference_bytecode(engine_lib):
             for m in range(M):
                 e.set_assignments(m, zs[m])
                 e.set_counts(m, *frozen[m])                      # the document moved, the global tables did not
-            got = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"])
+            got = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"], not_in_S=rec.get("not_in_S"))
             want = np.array(rec["probs"])
             big = want > 1e-9
             assert np.max(np.abs(got[:K][big] - want[big]) / want[big]) < REL_TOL_COND, (case["name"], rec["doc"], rec["view"], rec["pos"])
             assert np.all(np.abs(got[:K][~big] - want[~big]) < 1e-12)
             assert got[K] == pytest.approx(rec["new_share"], rel=REL_TOL_COND, abs=1e-12)
             n += 1
-    assert n > 300
+            if rec.get("not_in_S"):
+                # the default probe (index = held topics) differs on most of these tokens: they are what the flag exists for
+                plain = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"])
+                n_q1 += 1
+                n_differs += bool(np.max(np.abs(plain[:K][big] - want[big]) / want[big]) > 10 * REL_TOL_COND)
+    assert n > 1500 and n_q1 > 800 and n_differs > n_q1 // 2
 
 
 def test_engine_loglik_matches_reference_bytecode(engine_lib):
@@ -163,3 +168,60 @@ def test_engine_trajectory_matches_reference_bytecode(engine_lib, oracle_mod):
     sd_rel = np.sqrt(np.mean((ref_runs[:, :, 0].std(0, ddof=1) / np.abs(ref_mean[:, 0])) ** 2))
     dev = np.abs(eng_runs[:, :, 0] - ref_mean[:, 0]) / np.abs(ref_mean[:, 0])
     assert dev.max() < REL_TOL_LL + 4 * sd_rel, (dev.max(), sd_rel)
+
+
+# ---- the inference path (FastQMVWVTopicInferencer I:114-330) against the executed jar ------------------------------------------
+def _inference_cases():
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_inference_vectors.json")))
+    for case in gold["cases"]:
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        yield case, case["K"], case["V"], views
+
+
+def test_engine_inference_matches_reference_bytecode(engine_lib):
+    """SURVEY 8(f) rank 2 pinned to the reference's binary (tests/golden/make_reference_inference_vectors.py: `new FTree(phi)`,
+    FTree.sample and sampleTopicsForOneDoc executed from the jar the way FastQMVWVTopicInferencer drives them):
+    (1) mvtm_init_assignments_from_counts equals the jar's FTree draws token for token (out-of-vocabulary tokens keep topic 0);
+    (2) the conditionals of the frozen inference sweep -- document masses + bare-phi leaves, quirk Q13 -- as the jar's sampler
+        computed them vs mvtm_cond_probs_ex(tree_mode = 2): 1e-5 relative on every topic, Q1-affected tokens included;
+    (3) the trained tables are untouched by update_global = 2 sweeps."""
+    from mvtopicmodel_b200 import Engine
+    n_init = n_cond = 0
+    for case, K, Vs, views in _inference_cases():
+        M = len(Vs)
+        e = Engine(K, Vs, views, seed=case["seed"])
+        e.set_hyper(alpha=np.array(case["alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                    betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), p_a=np.array(case["p_a"]), p_b=np.array(case["p_b"]),
+                    inactive=[])
+        counts = [(np.array(case["n_wk"][m], dtype=np.int32), np.array(case["n_k"][m], dtype=np.int32)) for m in range(M)]
+        for m in range(M):
+            e.set_counts(m, *counts[m])
+        e.init_assignments_from_counts()
+        for m in range(M):
+            want = np.array(case["z_init"][m], dtype=np.int32)
+            assert np.array_equal(e.get_assignments(m), want), (case["name"], "init", m)
+            n_init += len(want)
+        if not case["conditionals"]:
+            continue
+        base = [np.array(z, dtype=np.int32) for z in case["z_after"][-1]]
+        for rec in case["conditionals"]:
+            zs = [z.copy() for z in base]
+            for m, zd in enumerate(rec["z_doc"]):
+                if zd is not None:
+                    b = int(views[m][0][rec["doc"]])
+                    zs[m][b:b + len(zd)] = zd
+            for m in range(M):
+                e.set_assignments(m, zs[m])
+                e.set_counts(m, *counts[m])                      # the trained tables, not the histogram of the new documents
+            got = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"], not_in_S=rec.get("not_in_S"), tree_mode=2)
+            want = np.array(rec["probs"])
+            assert np.max(np.abs(got[:K] - want) / want) < REL_TOL_COND, (case["name"], rec["doc"], rec["view"], rec["pos"])
+            assert got[K] == 0.0
+            n_cond += 1
+        for it in range(1, 4):
+            e.sweep(it, update_global=2)
+        for m in range(M):
+            nwk, nk = e.get_counts(m)
+            assert np.array_equal(nwk, counts[m][0]) and np.array_equal(nk, counts[m][1])
+    assert n_init > 2000 and n_cond > 500

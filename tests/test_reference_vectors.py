@@ -235,3 +235,83 @@ def test_mallet_next_beta_law_matches_mallet_bytecode(oracle_mod):
         if case["a"] > 1 and case["b"] == 1:
             assert case["uniforms_per_draw"] == 1.0                    # Q5: never a second round of the rejection loop
             assert ref.mean() < case["a"] / (case["a"] + 1) - 0.01     # ... and not the Beta(a, 1) law
+
+
+# ---- the inference path (FastQMVWVTopicInferencer) pinned to the executed jar ---------------------------------
+def _inference_cases():
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_inference_vectors.json")))
+    for case in gold["cases"]:
+        views = [(np.array(v["off"], dtype=np.int64), np.array(v["word"], dtype=np.int32)) for v in case["views"]]
+        yield case, case["K"], case["V"], views
+
+
+def _inference_oracle(O, case, K, Vs, views):
+    o = O.Oracle(K, Vs, views, seed=case["seed"])
+    o.set_hyper(alpha=np.array(case["alpha"]), alphaSum=np.array(case["alphaSum"]), beta=np.array(case["beta"]),
+                betaSum=np.array(case["betaSum"]), gamma=np.array(case["gamma"]), p_a=np.array(case["p_a"]), p_b=np.array(case["p_b"]), inactive=[])
+    for m in range(len(Vs)):
+        o.set_counts(m, np.array(case["n_wk"][m], dtype=np.int32), np.array(case["n_k"][m], dtype=np.int32))
+    return o
+
+
+def test_inference_path_matches_reference_bytecode(oracle_mod):
+    """What FastQMVWVTopicInferencer does (I:114-330) as executed from the shipped jar (tests/golden/
+    make_reference_inference_vectors.py: `new FTree(phi)` per word, FTree.sample for every in-vocabulary token's first topic,
+    sampleTopicsForOneDoc with nut = 0 and those gamma*alpha-less trees) vs the oracle's inference mode: initial assignments
+    (incl. out-of-vocabulary tokens keeping topic 0) and the assignments after every frozen sweep TOKEN FOR TOKEN; the trained
+    tables never move."""
+    O = oracle_mod
+    n_tok = n_oov = 0
+    for case, K, Vs, views in _inference_cases():
+        M = len(Vs)
+        o = _inference_oracle(O, case, K, Vs, views)
+        o.init_from_phi()
+        for m in range(M):
+            want = np.array(case["z_init"][m], dtype=np.int32)
+            assert np.array_equal(o.get_assignments(m), want), (case["name"], "init", m)
+            oov = views[m][1] >= Vs[m]
+            assert np.all(want[oov] == 0)
+            n_oov += int(oov.sum())
+        for it, want in enumerate(case["z_after"], start=1):
+            o.sweep(it, O.F_FROZEN | O.F_BARE_TREES | O.F_Q1_COMPAT)
+            for m in range(M):
+                got, w = o.get_assignments(m), np.array(want[m], dtype=np.int32)
+                assert np.array_equal(got, w), (case["name"], "sweep", it, "view", m, "first mismatch at", int(np.argmax(got != w)))
+                n_tok += len(w)
+        for m in range(M):
+            nwk, nk = o.get_counts(m)
+            assert np.array_equal(nwk, np.array(case["n_wk"][m])) and np.array_equal(nk, np.array(case["n_k"][m]))
+    assert n_tok > 1500 and n_oov > 10
+
+
+def test_inference_conditionals_match_reference_bytecode(oracle_mod):
+    """Per-token conditionals of the inference path on the trained (frozen) tables as the jar's sampler computed them with the
+    inferencer's trees (document masses + phi leaves, no gamma*alpha: quirk Q13), vs the oracle's three-bucket masses and its
+    engine-form dense distribution in bare-tree mode: 1e-9 relative.  Q1-affected tokens included."""
+    O = oracle_mod
+    n = n_q1 = 0
+    for case, K, Vs, views in _inference_cases():
+        if not case["conditionals"]:
+            continue
+        M = len(Vs)
+        o = _inference_oracle(O, case, K, Vs, views)
+        base = [np.array(z, dtype=np.int32) for z in case["z_after"][-1]]
+        counts = [(np.array(case["n_wk"][m], dtype=np.int32), np.array(case["n_k"][m], dtype=np.int32)) for m in range(M)]
+        for rec in case["conditionals"][::2]:
+            zs = [z.copy() for z in base]
+            for m, zd in enumerate(rec["z_doc"]):
+                if zd is not None:
+                    b = int(views[m][0][rec["doc"]])
+                    zs[m][b:b + len(zd)] = zd
+            o.set_assignments(zs)                       # (rebuilds counts from z: put the trained tables back)
+            for m in range(M):
+                o.set_counts(m, *counts[m])
+            p = np.eye(M); p[rec["view"]] = rec["p_row"]
+            for engine_form in (False, True):
+                got = o.cond_probs(rec["view"], rec["doc"], rec["pos"], p=p, engine_form=engine_form, not_in_S=rec.get("not_in_S"),
+                                   flags=O.F_BARE_TREES)
+                assert np.allclose(got[:K], rec["probs"], rtol=1e-9, atol=1e-15), (case["name"], rec["doc"], rec["view"], rec["pos"], engine_form)
+                assert got[K] == 0.0 and rec["new_share"] == 0.0          # the inferencer's inactive set is empty (I:243)
+            n += 1
+            n_q1 += bool(rec.get("not_in_S"))
+    assert n > 250
