@@ -63,7 +63,7 @@ def test_engine_conditionals_match_reference_bytecode(engine_lib):
                 plain = e.cond_probs(rec["view"], rec["doc"], rec["pos"], p_row=rec["p_row"])
                 n_q1 += 1
                 n_differs += bool(np.max(np.abs(plain[:K][big] - want[big]) / want[big]) > 10 * REL_TOL_COND)
-    assert n > 1500 and n_q1 > 800 and n_differs > n_q1 // 2
+    assert n > 1500 and n_q1 > 700 and n_differs > n_q1 // 2
 
 
 def test_engine_loglik_matches_reference_bytecode(engine_lib):
