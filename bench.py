@@ -224,34 +224,24 @@ def main():
     overlap = world > 1 and M > 1 and not args.no_overlap
     import torch
     from mvtopicmodel_b200 import Engine
-    from mvtopicmodel_b200.dist import CountExchange, EngineAdapter, OverlapAdapter, OverlappedSweep
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # torch.distributed is used for two things only: handing NCCL's 128-byte unique id to the ranks and the max-over-ranks of
+        # the timings.  The count exchange itself runs inside libmvtm.so (mvtm_comm_init / mvtm_sweep_dist, NCCL behind the C ABI).
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     eng = Engine(K, Vs, views, seed=2026, device=local_rank, doc_id_base=rank, doc_id_stride=world,
                  max_ctas=(n_sms - args.reserve_sms) if overlap else 0)
     ntok_local = sum(eng.ntok)
-    xch, ovl = None, None
     if world > 1:
-        xch = CountExchange(EngineAdapter(eng, local_rank))
-        xch.reset()
+        box = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world, hidden_ctas=args.reserve_sms if overlap else 0)
     eng.init_assignments()
-    if xch:
-        xch.exchange()
-    if overlap:
-        # two communicators: exchanges hidden under another view's pass live on the SMs the sweep leaves free (max_ctas);
-        # the exchange of the view with the longest pass cannot be hidden (only the short passes separate two of its own),
-        # so it runs on the default communicator, which may spread over the SMs that are idle while it is waited for
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.config.max_ctas = max(1, args.reserve_sms)
-        opts.config.min_ctas = 1
-        narrow = dist.new_group(pg_options=opts)
-        critical = int(np.argmax(eng.ntok))
-        ovl_adapter = OverlapAdapter(eng, local_rank)
-        ovl = OverlappedSweep(ovl_adapter, view_groups={m: narrow for m in range(M) if m != critical or args.narrow_all})
+    if world > 1:
+        eng.sync_counts()               # local counts -> global counts, snapshots for the sum-form exchange
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,16 +250,14 @@ def main():
         torch.cuda.synchronize()
 
     def step(it):
-        if ovl:
-            ovl.step(it)                # view m's all-reduce runs under the passes of the following views / next sweep
-            return
-        eng.sweep(it)
-        if xch:
-            xch.exchange_sum()          # every rank holds the same global counts at sweep start
+        if world > 1:
+            eng.sweep_dist(it)          # passes + exchange; view m's all-reduce runs under the following passes / the next sweep
+        else:
+            eng.sweep(it)
 
     def drain():
-        if ovl:
-            ovl_adapter.drain()         # the last views' exchange belongs to the timed region
+        if world > 1:
+            eng.comm_drain()            # the last views' exchange belongs to the timed region
 
     it = 0
     for _ in range(6):          # set-up: the engine's ring-depth autotune takes three samples per depth (not warm-up, not timed)
@@ -297,6 +285,9 @@ def main():
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     ring = eng.stats()["ring_locked"]
+    if world > 1:
+        ci = eng.comm_info()
+        allreduce_bytes, nccl_version = ci["bytes_last_sweep"], ci["nccl_version"]
     clocks = sampler.stop() if rank == 0 else None
     if dist:
         t = torch.tensor([ms_total] + list(view_ms), device="cuda", dtype=torch.float64)
@@ -329,23 +320,9 @@ def main():
         for m in range(M):
             zn[m][:] = eng.get_assignments(m)
 
-        if xch:
-            from mvtopicmodel_b200.dist import _DevBuf
-            whole = []
-            for m in range(M):
-                (p1, n1), (p2, n2) = eng.sum_exchange_buffers(m)
-                whole.append(torch.as_tensor(_DevBuf(p1, n1 + n2), device=f"cuda:{local_rank}"))
-                eng.set_host_mirror(m, zn[m])              # the sweep kernel keeps the pinned arrays current
-
         def e2e_step(i):
-            if xch:
-                for m in range(M):
-                    eng.set_assignments(m, zn[m])          # H2D + rebuild of the LOCAL counts
-                for m in range(M):
-                    dist.all_reduce(whole[m])              # local counts -> global counts (table and totals, one buffer)
-                torch.cuda.synchronize()
-                eng.delta_begin()                          # snapshot = global counts
-                step(i); drain()                           # new z lands in zn through the host mirror
+            if world > 1:
+                eng.sweep_host_dist(i, zn)                 # upload + local recount, ONE all-reduce per view, passes, z written back
             else:
                 eng.sweep_host(i, zn)
         e2e_steps = max(3, min(args.steps, 10))
@@ -366,12 +343,10 @@ def main():
             e2e_ms = float(t[0])
         e2e = {"value": ntok_global * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * ntok_local,
                "d2h_bytes_per_step": 4 * ntok_local, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-               "call": "mvtm_sweep_host (pinned host z in/out: chunked upload + count rebuild, sweep, new z stored to the pinned arrays by the kernel)" if not xch else
-                       "mvtm_set_assignments (H2D + local counts) + count all-reduce + sweep with mvtm_set_host_mirror (kernel-written D2H) + count exchange"}
-        if xch:
-            for m in range(M):
-                assert np.array_equal(zn[m], eng.get_assignments(m)), "host mirror out of date"
-                eng.set_host_mirror(m, None)
+               "call": "mvtm_sweep_host (pinned host z in/out: chunked upload + count rebuild, sweep, new z stored to the pinned arrays by the kernel)" if world == 1 else
+                       "mvtm_sweep_host_dist (per rank: pinned host z in/out, chunked upload + local count rebuild, one NCCL all-reduce per view inside the library, sweep, new z stored to the pinned arrays by the kernel)"}
+        for m in range(M):
+            assert np.array_equal(zn[m], eng.get_assignments(m)), "host arrays differ from the device assignments"
 
     if rank != 0:
         if dist:
@@ -413,13 +388,14 @@ def main():
                          "whole_job_frac": btok_all * value / 1e9 / (peak * world),
                          "peak_source": peak_src, "traffic_source": ent.get("source") if ent else None},
             "e2e": e2e, "clocks": clocks,
-            # my kernels inside the timed region: one k_sweep_view per view and step, plus the exchange's finishing passes
-            # (serial form: table and totals separately, overlapped form: one fused pass per view)
-            "gpu_launches": args.steps * M * (1 + (0 if not xch else (1 if ovl else 2)))}
-    if xch:
-        line["config"]["allreduce_bytes_per_sweep"] = ovl.bytes_per_exchange if ovl else xch.bytes_per_exchange
-        line["config"]["exchange"] = (f"overlapped: view m's all-reduce under the following passes, sweep grid {n_sms - args.reserve_sms} CTAs, "
-                                      f"hidden exchanges on a communicator with max_ctas={args.reserve_sms}, view {critical}'s on the default one") if ovl else "after the sweep (serial)"
+                    # my kernels inside the timed region: one k_sweep_view per view and step, plus the exchange's finishing pass
+            # (one fused k_finish_sum_exchange4 per view)
+            "gpu_launches": args.steps * M * (1 + (1 if world > 1 else 0))}
+    if world > 1:
+        line["config"]["allreduce_bytes_per_sweep"] = allreduce_bytes
+        line["config"]["exchange"] = ("inside libmvtm.so (mvtm_sweep_dist, NCCL %s): " % nccl_version) + (
+            f"overlapped -- view m's all-reduce under the following passes, sweep grid {n_sms - args.reserve_sms} CTAs, hidden exchanges on a "
+            f"communicator with maxCTAs={args.reserve_sms}, the longest view's on the wide one" if overlap else "after the pass (single view: nothing to hide it under)")
     if world == 1 and not args.no_cpu_baseline:
         val, ms, ntok_s, _ = cpu_reference_run(args.workload, args.cpu_sample_docs, 3, 1, threads)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",

@@ -214,6 +214,40 @@ int mvtm_stream_wait_view(mvtm_handle *h, int32_t m, void *stream);
 int mvtm_view_wait_stream(mvtm_handle *h, int32_t m, void *stream);
 int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size, void *stream, int32_t max_ctas);
 
+/* ---- Multi-GPU inside the library ("NCCL communicators created" by the boundary; 8e) --------------------------------
+ * One handle per GPU / rank, documents sharded over the ranks (mvtm_config.doc_id_base / doc_id_stride name the global ids),
+ * n_wk / n_k replicated.  The host only moves 128 bytes: rank 0 calls mvtm_comm_unique_id and hands the id to every rank (over
+ * whatever it has: a socket, MPI, a Java RMI call), then every rank calls mvtm_comm_init.  NCCL itself is loaded at run time
+ * (libnccl.so.2), so single-GPU hosts do not need it.  Replaces, across GPUs, what the reference's barrier M:1231 and its
+ * updater threads (U:164-297) do across CPU threads.
+ *   mvtm_comm_init(h, id, rank, world, hidden_ctas)  communicator over `world` ranks; hidden_ctas > 0 additionally creates a
+ *       CTA-limited communicator for exchanges that run UNDER another view's pass -- create the handle with
+ *       mvtm_config.max_ctas = SMs - hidden_ctas so that those SMs stay free (the sweep kernel is persistent).
+ *   mvtm_sync_counts(h, rebuild)   local counts -> global counts (one in-place all-reduce per view) + snapshot; call after
+ *       mvtm_init_assignments / mvtm_set_assignments on every rank (rebuild != 0 first recounts from the resident assignments).
+ *   mvtm_sweep_dist(h, it)         one Gibbs sweep over this rank's shard + the count exchange: per view, the pass, then an all-reduce
+ *       of the replica and a fused finishing pass on the library's own stream -- view m's exchange runs while the following
+ *       views (and the next sweep's earlier views) are sampled; only the view with the longest pass is exchanged on the wide
+ *       communicator.  Returns when the PASSES are done (mvtm_stats valid); the exchanges are ordered on the device before
+ *       anything that touches the view again.  Inactive topics sampled by a sweep are activated (U:263-270) at the start of
+ *       the next one, on the global counts.  mvtm_comm_drain waits for everything.
+ *   mvtm_sweep_host_dist(h, it, z) the stateless step through HOST buffers on every rank: upload + local recount, ONE all-reduce
+ *       per view (overlapped with the next view's upload), the passes, new z written to the caller's arrays.  No exchange
+ *       follows (the next stateless step recounts anyway): call mvtm_sync_counts(h, 1) before going back to mvtm_sweep_dist.
+ *   mvtm_loglik_dist(h, ll, q)     modelLogLikelihood of the whole corpus (document parts summed over ranks).
+ * With a communicator and no mvtm_set_stat_reducer callback, mvtm_optimize_hyper reduces its statistics over the communicator
+ * itself, so every rank installs identical hyper-parameters. */
+#define MVTM_COMM_ID_BYTES 128
+int mvtm_comm_unique_id(void *id_out);
+int mvtm_comm_init(mvtm_handle *h, const void *unique_id, int32_t rank, int32_t world, int32_t hidden_ctas);
+int mvtm_comm_destroy(mvtm_handle *h);
+int mvtm_comm_info(mvtm_handle *h, int32_t *rank, int32_t *world, int32_t *nccl_version, int64_t *bytes_last_sweep);
+int mvtm_sync_counts(mvtm_handle *h, int32_t rebuild_from_assignments);
+int mvtm_sweep_dist(mvtm_handle *h, int32_t iteration);
+int mvtm_comm_drain(mvtm_handle *h);
+int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout);
+int mvtm_loglik_dist(mvtm_handle *h, double *ll_out, int32_t quirk_len2);
+
 /* Scan layout of the sampler (for order-exact checkers): a document-view is sampled by `lanes_per_doc` lanes (8, 16 or
  * 32); topic t sits in 4-topic chunk c = t/4 owned by lane c % lanes_per_doc as its (c / lanes_per_doc)-th chunk, and the
  * cumulative scan runs lane-major (all chunks of lane 0, then lane 1, ...). */

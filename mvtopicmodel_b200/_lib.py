@@ -70,6 +70,15 @@ SIGNATURES = {
     "mvtm_stream_wait_view": (_i32, [_vp, _i32, _vp]),
     "mvtm_view_wait_stream": (_i32, [_vp, _i32, _vp]),
     "mvtm_sum_exchange_finish_async": (_i32, [_vp, _i32, _i32, _vp, _i32]),
+    "mvtm_comm_unique_id": (_i32, [_vp]),
+    "mvtm_comm_init": (_i32, [_vp, _vp, _i32, _i32, _i32]),
+    "mvtm_comm_destroy": (_i32, [_vp]),
+    "mvtm_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64)]),
+    "mvtm_sync_counts": (_i32, [_vp, _i32]),
+    "mvtm_sweep_dist": (_i32, [_vp, _i32]),
+    "mvtm_comm_drain": (_i32, [_vp]),
+    "mvtm_sweep_host_dist": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "mvtm_loglik_dist": (_i32, [_vp, _vp, _i32]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),
     "mvtm_activate_topics": (_i32, [_vp]),

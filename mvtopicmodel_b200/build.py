@@ -7,11 +7,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "mvtm.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "mvtm_kernels.cuh"), os.path.join(HERE, "csrc", "mvtm_optim.inl"),
+        os.path.join(HERE, "csrc", "mvtm_comm.inl"),
         os.path.join(ROOT, "include", "mvtm.h")]
 OUT = os.path.join(HERE, "libmvtm.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC"]
+              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-ldl"]
 
 
 def needs_build():

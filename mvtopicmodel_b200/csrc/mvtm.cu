@@ -42,7 +42,10 @@ struct ViewDev {
 
 }  // namespace
 
+struct CommState;                                   // NCCL communicators and exchange state (mvtm_comm.inl)
+
 struct mvtm_handle {
+    CommState *comm = nullptr;                      // multi-GPU inside the library (mvtm_comm_init)
     int K = 0, M = 0, Kp = 0, J = 0, KS = 0, G = 32;
     long long D = 0;
     int device = 0, num_sms = 0;
@@ -96,6 +99,8 @@ static std::string g_create_err;
 
 static int wait_view_ready(mvtm_handle *h, int m);
 static int wait_all_ready(mvtm_handle *h);
+static void comm_teardown(mvtm_handle *h);
+static int comm_reduce_stats(mvtm_handle *h, int op, long long *ints, long long n_ints, double *reals, long long n_reals);
 
 static int pick_J(int K)
 {
@@ -194,6 +199,7 @@ extern "C" int mvtm_destroy(mvtm_handle *h)
     // stream of mvtm_sweep_host may still be touching the tables: wait for the whole device, not just the handle's stream.
     cudaDeviceSynchronize();
     cudaGetLastError();
+    comm_teardown(h);
     for (int m = 0; m < h->M; m++) free_view(h->v[m]);
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (int m = 0; m < MVTM_MAX_VIEWS; m++) { if (h->ev_done[m]) cudaEventDestroy(h->ev_done[m]); if (h->ev_ready[m]) cudaEventDestroy(h->ev_ready[m]); }
@@ -727,7 +733,7 @@ static int close_sweep(mvtm_handle *h, int update_global)
     }
     h->stats.kernel_launches = h->open_launches;
     // multi-rank runs (a statistics reducer is installed) activate on the GLOBAL counts after the exchange: mvtm_activate_topics
-    if (update_global == 1 && !h->reducer) if (int rc = activate_sampled_topics(h)) return rc;
+    if (update_global == 1 && !h->reducer && !h->comm) if (int rc = activate_sampled_topics(h)) return rc;
     return MVTM_OK;
 }
 
@@ -1312,3 +1318,4 @@ extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
 }
 
 #include "mvtm_optim.inl"
+#include "mvtm_comm.inl"

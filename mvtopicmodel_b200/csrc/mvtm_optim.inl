@@ -204,7 +204,7 @@ __global__ void k_value_hist(int V, int K, int Kp, const int *nwk, int max_value
 // the ranks) before they are used, so every rank derives the same hyper-parameters (mvtm_set_stat_reducer).
 static int reduce_stats(mvtm_handle *h, int op, long long *ints, long long n_ints, double *reals, long long n_reals)
 {
-    if (!h->reducer) return MVTM_OK;
+    if (!h->reducer) return h->comm ? comm_reduce_stats(h, op, ints, n_ints, reals, n_reals) : MVTM_OK;   // NCCL inside the library
     if (h->reducer(h->reducer_ctx, op, (int64_t *)ints, n_ints, reals, n_reals) != 0)
         FAIL(h, MVTM_ERR_STATE, "mvtm_optimize_hyper: the statistics reducer reported a failure");
     return MVTM_OK;

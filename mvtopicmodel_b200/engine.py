@@ -168,6 +168,47 @@ class Engine:
             ptrs[m] = z.ctypes.data
         self._ck(self.L.mvtm_sweep_host(self.h, int(iteration), ptrs))
 
+    # --- multi-GPU inside the library (NCCL behind the C ABI, include/mvtm.h "Multi-GPU inside the library") ------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId; rank 0 creates it, the host hands it to every rank."""
+        buf = C.create_string_buffer(128)
+        L = _lib.lib()
+        rc = L.mvtm_comm_unique_id(buf)
+        if rc:
+            raise MvtmError(rc, L.mvtm_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world, hidden_ctas=0):
+        assert len(unique_id) == 128
+        self._ck(self.L.mvtm_comm_init(self.h, C.c_char_p(unique_id), int(rank), int(world), int(hidden_ctas)))
+
+    def comm_info(self):
+        r, w, v, b = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        self._ck(self.L.mvtm_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v), C.byref(b)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value, "bytes_last_sweep": b.value}
+
+    def sync_counts(self, rebuild=False):
+        self._ck(self.L.mvtm_sync_counts(self.h, int(bool(rebuild))))
+
+    def sweep_dist(self, iteration):
+        self._ck(self.L.mvtm_sweep_dist(self.h, int(iteration)))
+
+    def comm_drain(self):
+        self._ck(self.L.mvtm_comm_drain(self.h))
+
+    def sweep_host_dist(self, iteration, z_arrays):
+        ptrs = (C.c_void_p * self.M)()
+        for m, z in enumerate(z_arrays):
+            assert z.dtype == np.int32 and z.flags["C_CONTIGUOUS"] and len(z) == self.ntok[m]
+            ptrs[m] = z.ctypes.data
+        self._ck(self.L.mvtm_sweep_host_dist(self.h, int(iteration), ptrs))
+
+    def loglik_dist(self, quirk_len2=False):
+        out = np.empty(self.M, dtype=np.float64)
+        self._ck(self.L.mvtm_loglik_dist(self.h, _ptr(out), int(bool(quirk_len2))))
+        return out
+
     def set_host_mirror(self, m, z_host):
         """z_host: pinned int32 numpy array (e.g. torch.empty(n, dtype=torch.int32).pin_memory().numpy()) or None."""
         if z_host is not None:

@@ -1233,3 +1233,100 @@ def test_loglik_and_invariants_tolerate_unassigned_tokens(engine_lib):
     assert (zb[:7] == -1).all()
     e.set_assignments(0, np.where(zb < 0, 0, zb))
     assert e.check_invariants() == 0 and np.all(np.isfinite(e.loglik())) and ll0.shape == (2,)
+
+
+# ---- parity at the BASELINE shapes (round-2 review item 5) --------------------------------------------------------------------
+BASELINE_SHAPES = {
+    "lda_20k": ("lda_100k", 20000, 24),          # (corpus config, documents, max_ctas: <= ~5 % of the documents in flight)
+    "acm_20k": ("acm_2v", 20000, 32),
+    "k2000_5k": (dict(D=5000, K=2000, views=[(30_000, 100, 0.5, 1.0, 1024)]), 5000, 16),
+}
+
+
+def _baseline_corpus(name):
+    import zlib
+    from mvtopicmodel_b200 import corpus
+    cfg, docs, ctas = BASELINE_SHAPES[name]
+    K, Vs, views = corpus.generate(cfg, docs=docs)
+    c = 0
+    for off, w in views:
+        c = zlib.crc32(np.ascontiguousarray(w).tobytes(), zlib.crc32(np.ascontiguousarray(off).tobytes(), c))
+    return K, Vs, views, c, ctas
+
+
+@pytest.mark.parametrize("name", list(BASELINE_SHAPES))
+def test_conditionals_at_baseline_shapes(engine_lib, oracle_mod, name):
+    """Gate (b) at the sizes the bench runs -- K = 500 / V = 50 K (configs[1]), K = 1000 with two views and V = 100 K / 50 K
+    (configs[2]), K = 2000 with V = 30 K (the slot size of configs[4]) -- after five engine sweeps (ragged rows, real
+    vocabulary widths): 1e-5 relative on every topic vs the oracle, 120 tokens per shape spread over views, documents and
+    positions, with the coupled-view matrix and an inactive topic where the shape has them."""
+    O = oracle_mod
+    K, Vs, views, _, _ = _baseline_corpus(name)
+    M = len(Vs)
+    e, o = make_pair(O, K, Vs, views, seed=17)
+    e.init_assignments()
+    for it in range(1, 6):
+        e.sweep(it)
+    zs = [e.get_assignments(m) for m in range(M)]
+    # free one topic so that the new-topic bucket is exercised: its tokens move to a neighbour, the topic becomes inactive
+    dead = K // 3
+    zs = [np.where(z == dead, dead + 1, z).astype(np.int32) for z in zs]
+    for m in range(M):
+        e.set_assignments(m, zs[m])
+    o.set_assignments(zs)
+    alpha = np.full((M, K + 1), 0.1); alpha[:, K] = 2.5
+    for x in (e, o):
+        x.set_hyper(alpha=alpha, inactive=[dead])
+    rng = np.random.default_rng(5)
+    p = np.eye(M)
+    if M > 1:
+        p = rng.uniform(0.2, 0.9, size=(M, M)); p = np.round((p + p.T) / 2, 3); np.fill_diagonal(p, 1.0)
+    n = 0
+    for m in range(M):
+        off = views[m][0]
+        lens = off[1:] - off[:-1]
+        docs = rng.choice(np.nonzero(lens > 0)[0], size=120 // M, replace=False)
+        for d in docs:
+            pos = int(rng.integers(0, lens[d]))
+            want = o.cond_probs(m, int(d), pos, p=p)
+            got = e.cond_probs(m, int(d), pos, p_row=p[m])
+            big = want[:K] > 1e-12
+            assert np.max(np.abs(got[:K][big] - want[:K][big]) / want[:K][big]) < REL_TOL_COND, (name, m, int(d), pos)
+            assert got[K] == pytest.approx(want[K], rel=REL_TOL_COND) and want[K] > 0
+            n += 1
+    assert n >= 100
+
+
+@pytest.mark.parametrize("name", list(BASELINE_SHAPES))
+def test_loglik_trajectory_at_baseline_shapes(engine_lib, name):
+    """Gate (c) at the BASELINE shapes: LL per view after 10 / 20 / 30 sweeps, three engine seeds vs three seeds of the sequential
+    reference-faithful oracle on the SAME corpus (tests/golden/baseline_shape_trajectories.json, computed once by
+    make_baseline_shape_trajectories.py -- the sequential oracle needs 4-5 s per sweep at these sizes; the corpus checksum is
+    verified).  Ensemble means within 1 % at every checkpoint and view."""
+    import json
+    from mvtopicmodel_b200 import Engine
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "baseline_shape_trajectories.json")))["shapes"][name]
+    K, Vs, views, crc, ctas = _baseline_corpus(name)
+    assert crc == g["corpus_crc32"] and [len(v[1]) for v in views] == g["tokens"], "the generator no longer makes the fixture's corpus"
+    M = len(Vs)
+    want = np.array(g["ll"]).mean(0)                              # [checkpoint, view]
+    runs = []
+    for seed in g["seeds"]:
+        e = Engine(K, Vs, views, seed=seed, max_ctas=ctas, ring_depth=1)
+        e.init_assignments()
+        assert np.allclose(e.loglik(), g["ll_init"][g["seeds"].index(seed)], rtol=1e-10)     # same initial state as the oracle's run
+        traj = []
+        for it in range(1, g["checkpoints"][-1] + 1):
+            if M > 1:
+                e.set_hyper(p_a=np.full((M, M), min(it / 100.0 + 0.3, 1.1)))
+            e.sweep(it)
+            if it in g["checkpoints"]:
+                traj.append(e.loglik())
+        assert e.check_invariants() == 0
+        runs.append(np.array(traj))
+        e.close()
+    got = np.array(runs).mean(0)
+    rel = np.abs(got - want) / np.abs(want)
+    print(name, "LL/token engine", (got / np.array(g["tokens"])).round(4).tolist(), "oracle", (want / np.array(g["tokens"])).round(4).tolist(),
+          "rel", rel.round(5).tolist())
+    assert np.all(rel < REL_TOL_LL), rel
