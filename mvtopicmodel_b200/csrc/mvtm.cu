@@ -1093,15 +1093,18 @@ static int loglik_impl(mvtm_handle *h, double *ll_out, double *doc_out, double *
         for (long long d = 0; d < D; d++) { ll += doc_ll[(size_t)d]; modalityCnt += counted[(size_t)d]; }
         ll += (double)modalityCnt * host_log_gamma_stirling(gas);                                 // M:3373
         const double doc_part = ll;                      // everything above sums over THIS handle's documents
+        // the topic-word terms are accumulated on their own: functions of the (global) count tables only, so that every rank of a
+        // multi-GPU run computes bit-identical values whatever its local document part is
+        double wp = 0.0;
         long long nnz = 0;
-        for (int bidx = 0; bidx < cell_blocks; bidx++) { ll += part[(size_t)bidx]; nnz += nnzp[(size_t)bidx]; }
+        for (int bidx = 0; bidx < cell_blocks; bidx++) { wp += part[(size_t)bidx]; nnz += nnzp[(size_t)bidx]; }
         const double bV = h->beta[m] * v.V;
-        for (int t = 0; t < K; t++) ll -= host_log_gamma_stirling(bV + nk[(size_t)t]);           // M:3417-3419
-        ll += host_log_gamma_stirling(bV) * K;                                                    // M:3438
-        ll -= host_log_gamma_stirling(h->beta[m]) * (double)nnz;                                  // M:3441
-        if (ll_out) ll_out[m] = ll;
+        for (int t = 0; t < K; t++) wp -= host_log_gamma_stirling(bV + nk[(size_t)t]);           // M:3417-3419
+        wp += host_log_gamma_stirling(bV) * K;                                                    // M:3438
+        wp -= host_log_gamma_stirling(h->beta[m]) * (double)nnz;                                  // M:3441
+        if (ll_out) ll_out[m] = doc_part + wp;
         if (doc_out) doc_out[m] = doc_part;
-        if (word_out) word_out[m] = ll - doc_part;      // the topic-word terms: functions of the (global) count tables only
+        if (word_out) word_out[m] = wp;
     }
     cudaFree(d_ga); cudaFree(d_tlg); cudaFree(d_doc); cudaFree(d_cnt); cudaFree(d_part); cudaFree(d_nnz);
     CK(h, e);

@@ -110,11 +110,15 @@ int main(int argc, char **argv)
             for (size_t i = 0; i < sh.word[m].size(); i++) { int t = res[(size_t)r].z[m][i]; nwk[(size_t)sh.word[m][i] * K + t]++; nk[(size_t)t]++; ntok++; }
         }
         for (int r = 0; r < world; r++) {
-            bad += res[(size_t)r].nk[m] != nk;
-            bad += res[(size_t)r].nwk[m] != nwk;
-            bad += res[(size_t)r].ll1[m] != res[0].ll1[m] || res[(size_t)r].ll0[m] != res[0].ll0[m];
-            bad += !(res[(size_t)r].ll1[m] > res[(size_t)r].ll0[m]);
-            bad += res[(size_t)r].alpha != res[0].alpha;
+            const Result &R = res[(size_t)r];
+            auto report = [&](bool wrong, const char *what) { if (wrong) { bad++; std::printf("MISMATCH rank %d view %d: %s\n", r, m, what); } };
+            report(R.nk[m] != nk, "n_k != histogram of all ranks' assignments");
+            report(R.nwk[m] != nwk, "n_wk != histogram of all ranks' assignments");
+            report(R.ll0[m] != res[0].ll0[m], "initial global LL differs between ranks");
+            report(R.ll1[m] != res[0].ll1[m], "final global LL differs between ranks");
+            report(!(R.ll1[m] > R.ll0[m]), "LL did not improve");
+            report(R.alpha != res[0].alpha, "alpha differs between ranks after mvtm_optimize_hyper");
+            if (R.ll1[m] != res[0].ll1[m]) std::printf("   %.17g vs %.17g\n", R.ll1[m], res[0].ll1[m]);
         }
         std::printf("view %d: %lld tokens, LL/token %.4f -> %.4f\n", m, ntok, res[0].ll0[m] / (double)ntok, res[0].ll1[m] / (double)ntok);
     }
