@@ -12,7 +12,7 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "mvtm_kernels.cuh"), os.path.join(HERE, 
 OUT = os.path.join(HERE, "libmvtm.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-ldl"]
+              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-ldl", "-split-compile", "0"]
 
 
 def needs_build():
