@@ -49,10 +49,6 @@ typedef enum {
                                       N(1, 0.25/(p_a - 1)) on [0, 1] (quirk Q5: its rejection test compares against NaN).  Same law for
                                       p_a <= 1. */
 #define MVTM_FLAG_REFERENCE_COMPAT (MVTM_FLAG_Q1_COMPAT | MVTM_FLAG_BETA_MALLET)   /* both: the reference's behaviour, quirks included */
-#define MVTM_FLAG_DENSE_SCAN  16u  /* sample every view with the dense O(K) scan.  Default: views of long documents use the bucketed
-                                      sampler -- document bucket over the document's topic list + tree bucket through a per-word
-                                      mass kept current per delta, the reference's own decomposition (W:495-538, U:242-260) -- which
-                                      draws from the same conditional but consumes the uniform in bucket order. */
 
 typedef struct mvtm_config {
     int32_t num_topics;              /* K, M:183 numTopics                                                   */
@@ -79,9 +75,6 @@ typedef struct mvtm_sweep_stats {
     int32_t kernel_launches;         /* kernels launched by the last sweep                                   */
     int32_t ring_depth[MVTM_MAX_VIEWS];  /* TMA ring depth each view's last pass ran with                       */
     int32_t ring_locked[MVTM_MAX_VIEWS]; /* the depth the autotune settled on (0 = still sampling; = the configured depth when fixed) */
-    int64_t tree_draws;              /* bucketed passes: draws that fell into the word's tree bucket (W:531-538 wordFTreeMassCnt);
-                                        changed - ... the rest of the draws came from the document bucket (W:527-530)   */
-    int32_t bucketed[MVTM_MAX_VIEWS];/* 1: the view's last pass used the bucketed sampler, 0: the dense scan          */
 } mvtm_sweep_stats;
 
 typedef struct mvtm_handle mvtm_handle;

@@ -21,8 +21,7 @@ class MvtmConfig(C.Structure):
 class MvtmSweepStats(C.Structure):
     _fields_ = [("tokens", C.c_int64), ("changed", C.c_int64), ("new_topic", C.c_int64), ("ms_total", C.c_double),
                 ("ms_view", C.c_double * MAX_VIEWS), ("kernel_launches", C.c_int32),
-                ("ring_depth", C.c_int32 * MAX_VIEWS), ("ring_locked", C.c_int32 * MAX_VIEWS), ("tree_draws", C.c_int64),
-                ("bucketed", C.c_int32 * MAX_VIEWS)]
+                ("ring_depth", C.c_int32 * MAX_VIEWS), ("ring_locked", C.c_int32 * MAX_VIEWS)]
 
 
 FLAG_DOC_ORDER = 1
@@ -30,7 +29,6 @@ FLAG_SINGLE_WARP = 2
 FLAG_Q1_COMPAT = 4
 FLAG_BETA_MALLET = 8
 FLAG_REFERENCE_COMPAT = 12
-FLAG_DENSE_SCAN = 16
 OPT_P, OPT_DP, OPT_GAMMA, OPT_BETA, OPT_ALL = 1, 2, 4, 8, 15
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64

@@ -33,7 +33,6 @@ struct ViewDev {
     int *z_mirror = nullptr;                        // device alias of a caller-owned pinned array that mirrors z (mvtm_set_host_mirror)
     std::vector<long long> chunk_tok_off;           // mvtm_sweep_host: HOST_CHUNKS + 1 token offsets of contiguous document ranges
     float *ga_tree = nullptr, *ga_full = nullptr, *ga_one = nullptr;   // ga_one: all ones, the inferencer's bare trees (Q13)
-    float *tw = nullptr;                            // bucketed sampling: tree mass per word (k_tree_mass), V floats
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
     std::vector<long long> h_doc_off;               // host copy (lengths, probe argument checks)
     std::vector<unsigned char> h_present;
@@ -188,7 +187,7 @@ static void free_view(ViewDev &v)
 {
     // nk / snap_nk are row V of the nwk / snap_nwk allocations (one all-reduce covers table and totals)
     cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk);
-    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk); cudaFree(v.tw);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk);
     v = ViewDev();
 }
 
@@ -519,7 +518,7 @@ static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
     return MVTM_OK;
 }
 
-struct LaunchCfg { int R, W, grid, oc_smem, bkt; size_t smem; };
+struct LaunchCfg { int R, W, grid, oc_smem; size_t smem; };
 
 // Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first 2*RING_SAMPLES timed
 // passes of the view alternate R = 1, 2, 1, 2, ... and the depth with the smaller MEDIAN pass time is kept (one sample per depth
@@ -548,18 +547,6 @@ static void ring_record(mvtm_handle *h, int m, float ms)
     }
 }
 
-// Bucketed sampling (document bucket over the document's topic list + tree bucket through a per-word mass, mvtm_kernels.cuh) for
-// views whose documents are long enough to amortise the list set-up; the dense scan for short side views, for the
-// reference-compat index (MVTM_FLAG_Q1_COMPAT keeps its flags in the dense n_d array) and when MVTM_FLAG_DENSE_SCAN asks for it.
-static bool use_bucketed(mvtm_handle *h, int m)
-{
-    if (h->flags & (MVTM_FLAG_Q1_COMPAT | MVTM_FLAG_DENSE_SCAN)) return false;
-    if (const char *e = getenv("MVTM_BUCKETED")) { if (atoi(e) == 0) return false; if (atoi(e) == 2) return true; }
-    const ViewDev &v = h->v[m];
-    const int min_len = getenv("MVTM_BUCKETED_MINLEN") ? atoi(getenv("MVTM_BUCKETED_MINLEN")) : 24;
-    return v.n_items > 0 && v.n_tok >= (long long)min_len * v.n_items;
-}
-
 static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
 {
     const int KS = h->KS, G = h->G, NSUB = 32 / G, JG = KS / (4 * G);
@@ -569,12 +556,11 @@ static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
     // back, even for the side views (5.7 vs 4.8 ms), so the default keeps it in global memory for every view.
     (void)m;
     const bool oc_smem = multi && getenv("MVTM_OC_SMEM") && atoi(getenv("MVTM_OC_SMEM")) != 0;
-    const bool bkt = use_bucketed(h, m);
     R = std::max(1, std::min(R, 8));
     const size_t budget = 227 * 1024 - 1024;
     int docs;
     for (;;) {
-        docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0, bkt)) / smem_doc_bytes(KS, R, multi, oc_smem, bkt, G));
+        docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0)) / smem_doc_bytes(KS, R, multi, oc_smem));
         if (docs >= NSUB || R == 1) break;
         R--;
     }
@@ -587,8 +573,8 @@ static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
     if (h->cfg_ctas > 0) grid = std::min(grid, h->cfg_ctas);
     if (const char *e = getenv("MVTM_CTAS")) grid = std::max(1, std::min(grid, atoi(e)));
     if (h->flags & MVTM_FLAG_SINGLE_WARP) { W = 1; grid = 1; }
-    lc.R = R; lc.W = W; lc.grid = grid; lc.oc_smem = oc_smem ? 1 : 0; lc.bkt = bkt ? 1 : 0;
-    lc.smem = smem_cta_bytes(KS, multi ? h->M : 0, bkt) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi, oc_smem, bkt, G);
+    lc.R = R; lc.W = W; lc.grid = grid; lc.oc_smem = oc_smem ? 1 : 0;
+    lc.smem = smem_cta_bytes(KS, multi ? h->M : 0) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi, oc_smem);
     return MVTM_OK;
 }
 
@@ -601,8 +587,7 @@ static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cud
         kernel<<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
         return cudaGetLastError();
     };
-    if (q1) return go(k_sweep_view<KS, G, MULTI, true, false>);
-    return lc.bkt ? go(k_sweep_view<KS, G, MULTI, false, true>) : go(k_sweep_view<KS, G, MULTI, false, false>);
+    return q1 ? go(k_sweep_view<KS, G, MULTI, true>) : go(k_sweep_view<KS, G, MULTI, false>);
 }
 template <int KS, int G, bool MULTI>
 static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const double *p_row, double *out, cudaStream_t s, bool q1)
@@ -686,27 +671,6 @@ static int clear_q1_flags(mvtm_handle *h)
     return MVTM_OK;
 }
 
-// One view pass on the handle's stream: n_k snapshot, work counter reset, (bucketed) the per-word tree masses, k_sweep_view.
-static int launch_view_pass(mvtm_handle *h, int m, int iteration, int update_global, const LaunchCfg &lc, int *z_host)
-{
-    ViewDev &v = h->v[m];
-    CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-    SweepParams P;
-    fill_params(h, m, iteration, update_global, P);
-    P.R = lc.R; P.oc_smem = lc.oc_smem;
-    h->stats.ring_depth[m] = lc.R; h->stats.bucketed[m] = lc.bkt;
-    P.z_host = z_host;
-    if (lc.bkt) {
-        if (!v.tw) CK(h, cudaMalloc(&v.tw, (size_t)v.V * 4));
-        k_tree_mass<<<h->num_sms * 4, 256, (size_t)h->Kp * 4, h->stream>>>(v.V, h->K, h->Kp, v.nwk, v.nk_snap, P.ga_tree, P.beta, P.betaSum, v.tw);
-        CK(h, cudaGetLastError());
-        P.tw = v.tw;
-    }
-    CK(h, launch_sweep(h, P, lc));
-    return MVTM_OK;
-}
-
 // Queues view m's pass (n_k snapshot, work counter reset, k_sweep_view) on the handle's stream; no host synchronisation.
 static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, int m, int *launches)
 {
@@ -717,8 +681,15 @@ static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, i
     if (int rc = wait_view_ready(h, m)) return rc;
     CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
     if (v.n_items > 0) {
-        if (int rc = launch_view_pass(h, m, iteration, update_global, lc, v.z_mirror)) return rc;
-        (*launches) += 1 + lc.bkt;
+        CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, (size_t)h->Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+        SweepParams P;
+        fill_params(h, m, iteration, update_global, P);
+        P.R = lc.R; P.oc_smem = lc.oc_smem;
+        h->stats.ring_depth[m] = lc.R;
+        P.z_host = v.z_mirror;
+        CK(h, launch_sweep(h, P, lc));
+        (*launches)++;
     }
     CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
     h->pass_queued[m] = true;
@@ -749,7 +720,7 @@ static int close_sweep(mvtm_handle *h, int update_global)
     unsigned long long st[4];
     CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2]; h->stats.tree_draws = (long long)st[3];
+    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
     float ms = 0.f;
     CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;
@@ -909,8 +880,15 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
         if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
         CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
         if (v.n_items > 0) {
-            if (int rc = launch_view_pass(h, m, iteration, 1, lc, alias[m])) return rc;
-            launches += 1 + lc.bkt;
+            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+            SweepParams P;
+            fill_params(h, m, iteration, 1, P);
+            P.R = lc.R; P.oc_smem = lc.oc_smem;
+            h->stats.ring_depth[m] = lc.R;
+            P.z_host = alias[m];
+            CK(h, launch_sweep(h, P, lc));
+            launches++;
         }
         CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
         if (v.n_tok > 0 && !alias[m])
@@ -925,7 +903,7 @@ extern "C" int mvtm_sweep_host(mvtm_handle *h, int32_t iteration, int32_t *const
     if (bad) {      // those tokens were treated as UNASSIGNED_TOPIC on the device; the caller's arrays may hold their new topics
         FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host: the assignments hold %d topic ids >= K", bad);
     }
-    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2]; h->stats.tree_draws = (long long)st[3];
+    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
     float ms = 0.f;
     CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;

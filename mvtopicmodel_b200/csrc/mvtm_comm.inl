@@ -305,8 +305,15 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
         if (int rc = wait_view_ready(h, m)) return rc;                  // the view's global counts
         CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
         if (v.n_items > 0) {
-            if (int rc = launch_view_pass(h, m, iteration, 1, lc, alias[m])) return rc;
-            launches += 1 + lc.bkt;
+            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
+            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
+            SweepParams P;
+            fill_params(h, m, iteration, 1, P);
+            P.R = lc.R; P.oc_smem = lc.oc_smem;
+            h->stats.ring_depth[m] = lc.R;
+            P.z_host = alias[m];
+            CK(h, launch_sweep(h, P, lc));
+            launches++;
         }
         CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
         if (v.n_tok > 0 && !alias[m])
@@ -319,7 +326,7 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
     CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (bad) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: the assignments hold %d topic ids >= K", bad);
-    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2]; h->stats.tree_draws = (long long)st[3];
+    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
     float ms = 0.f;
     CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;

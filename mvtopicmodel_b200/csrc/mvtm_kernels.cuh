@@ -56,9 +56,6 @@ struct SweepParams {
     unsigned *rbits;                  // Q1 mode: per document KS/32 words, bit t = "topic t is NOT in the document's dense index for the
                                       //   rest of this sweep" (it left it, or was gained while absent); carried across the view passes
     unsigned *rb_one;                 // probe: the flags of the probed document (overrides rbits)
-    float *tw;                        // bucketed sampling: per word of view m, the tree mass T_w = sum_t (n_wk[w][t] + beta) * q0[t]
-                                      //   (what the reference keeps as the root of the word's F+tree, FT:96-109); computed by
-                                      //   k_tree_mass before the pass and kept current by one float RED per changed token
     int *z_host;                      // mvtm_sweep_host: device alias of the caller's pinned array of view m (NULL: none); every
                                       //   token block's new assignments are stored there too, so no copy follows the pass
 };
@@ -131,12 +128,6 @@ __device__ __forceinline__ void sts_u16(uint32_t a, unsigned v)
 { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v)
 { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ unsigned lds_u32(uint32_t a)
-{ unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ float lds_f32(uint32_t a)
-{ float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts_u32(uint32_t a, unsigned v)
-{ asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 #define FULL 0xffffffffu
 __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
@@ -159,21 +150,14 @@ struct DocCtx {
     const float *gaf;      // (MULTI) CTA-shared gamma_i*alpha_i[t] of every view, [M][KS] (W:404)
     int gaf_stride;        // = KS
     float pmm, coefm, C;   // p[m][m]; len_m + gas_m; new-topic mass per token (W:515)
-    // bucketed sampling (BKT): the document's topic list S as u16 entries (first-occurrence order, appended to when a topic
-    // enters; entries whose topic has left keep a zero weight), a bit per topic "is listed", the number of entries
-    uint32_t list_sa, inl_sa;
-    unsigned *inl;
-    int cnt;
 };
 
-// BKT: the document part only, dq[t] = (p_mm*n_d[t] + [t in S]*O_m[t]) / (n_k[t] + betaSum); the prior part
-// q0[t] = gamma*alpha[t] / (n_k[t] + betaSum) is document-independent and lives once per CTA (q[t] = q0[t] + dq[t])
-template <bool MULTI, bool BKT = false>
+template <bool MULTI>
 __device__ __forceinline__ float q_value(float ndv, bool inS, float ocv, float pri, float coefm, float pmm, float2 gi)
 {
     float v = ndv * pmm;
     if (MULTI) v += inS ? coefm * (ocv + pri) : 0.f;
-    return BKT ? v * gi.y : (v + gi.x) * gi.y;
+    return (v + gi.x) * gi.y;
 }
 
 template <bool MULTI>
@@ -181,7 +165,9 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
 {   // sum_i c_i * gamma_i*alpha_i[t] (W:404); c_i = 0 for the own view and for absent views, so no branch is needed
     float pri = 0.f;
     if (MULTI) {
+#ifdef MVTM_AB_PRIOR_ROLLED
 #pragma unroll 1
+#endif
         for (int i = 0; i < P.M; i++) pri = fmaf(c.cpar[i], c.gaf[(size_t)i * c.gaf_stride + t], pri);
     }
     return pri;
@@ -193,7 +179,7 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
 // reference removes a topic from S when no view of the document holds it any more (W:441-468) and never inserts one (W:563-584 is
 // dead code), so S = {held and not flagged} with the flag set when the topic leaves or is gained while absent
 // (tests/test_reference_vectors.py::test_flag_rule_equals_reference_dense_index).  A flagged topic keeps only its tree mass.
-template <int KS, int G, bool MULTI, bool Q1, bool BKT = false>
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl, int gl, float (&bsq)[KS / (4 * G)])
 {
     constexpr int JG = KS / (4 * G);
@@ -221,8 +207,7 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
         pri = prior_other<MULTI>(P, c, t);
         if (oth) ocv = c.oc[t];
     }
-    sts_f32(c.sa + 4u * (uint32_t)t, q_value<MULTI, BKT>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t)));
-    if (BKT) return;                                                    // no per-chunk beta*sum(q) registers in this mode
+    sts_f32(c.sa + 4u * (uint32_t)t, q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t)));
     constexpr int LG = ilog2(G);
     const int j = t >> (2 + LG);
     const float4 qq = lds_f4(c.sa + 16u * (uint32_t)(gl + G * j));      // own store is visible in program order
@@ -234,7 +219,7 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
 // one step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the owners
 // differ (a second pass runs only when one lane owns both).  No warp-level synchronisation inside: the lane groups of a
 // warp may diverge here.
-template <int KS, int G, bool MULTI, bool Q1, bool BKT = false>
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int tinc, int tdec, int gl, float (&bsq)[KS / (4 * G)])
 {
     if (tinc == tdec) return;                                   // same topic: the two changes cancel
@@ -243,7 +228,7 @@ __device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int 
     if (gl == own_i) { t = tinc; dl = 1; if (own_i == own_d) t2 = tdec; } else if (gl == own_d) { t = tdec; dl = -1; }
 #pragma unroll 1
     while (t >= 0) {
-        apply_count_delta<KS, G, MULTI, Q1, BKT>(P, c, t, dl, gl, bsq);
+        apply_count_delta<KS, G, MULTI, Q1>(P, c, t, dl, gl, bsq);
         t = t2; t2 = -1; dl = -1;
     }
 }
@@ -289,6 +274,13 @@ __host__ __device__ inline double mallet_next_beta(BetaStream &r, double a, doub
     return v1 / (v1 + v2);
 }
 
+// (kept out of line: the default law's path through draw_p stays as short as it was before this mode existed)
+__device__ __noinline__ double draw_beta_mallet(const SweepParams &P, int i, uint32_t gdoc, uint32_t tag, uint4 x)
+{
+    BetaStream st{ gdoc, P.iteration, tag, P.seed_lo, P.seed_hi, 1u, x, 0 };
+    return mallet_next_beta(st, P.pa[i], P.pb[i]);
+}
+
 // the view-coupling draw p[m][i] of W:327-337 for document gdoc (every lane of the group computes the same value)
 __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
 {
@@ -302,10 +294,12 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
         const uint32_t tag = ((uint32_t)(lo * P.M + hi) << 8) | PURPOSE_PDRAW;
         uint4 x = philox4x32_10(0u, gdoc, P.iteration, tag, P.seed_lo, P.seed_hi);
         double b;
+#ifndef MVTM_AB_NO_MALLET
         if (P.beta_mallet) {
-            BetaStream st{ gdoc, P.iteration, tag, P.seed_lo, P.seed_hi, 1u, x, 0 };
-            b = mallet_next_beta(st, P.pa[i], P.pb[i]);
-        } else {
+            b = draw_beta_mallet(P, i, gdoc, tag, x);
+        } else
+#endif
+        {
             double u = (double)(x.x >> 8) * (1.0 / 16777216.0);
             b = pow(u, 1.0 / P.pa[i]);                          // Beta(a,1) by inversion (Q5: true law)
         }
@@ -324,12 +318,11 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
 // leaves it empty again, so nothing is scanned densely.  (The first version zeroed, histogrammed and scanned all KS
 // topics per other view and evaluated the full q expression for every topic: ~4000 instructions per document at
 // K = 1000 -- more than sampling the 6-12 tokens of a side view.)
-template <int KS, int G, bool MULTI, bool Q1, bool BKT = false>
+template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d, int len, int gl, const double *p_override,
                                           bool skip_first, float (&bsq)[KS / (4 * G)])
 {
     constexpr int JG = KS / (4 * G);
-    constexpr int NSUB = 32 / G;
     const int m = P.m;
     c.rb = nullptr;
     if (Q1) c.rb = P.rb_one ? P.rb_one : ((MULTI && P.rbits) ? P.rbits + (size_t)d * (KS / 32) : nullptr);   // one pass: nothing to carry
@@ -340,18 +333,11 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         uint4 *nd128 = reinterpret_cast<uint4 *>(c.nd);
 #pragma unroll
         for (int k = 0; k < (KS / 8 + G - 1) / G; k++) { const int i = gl + G * k; if (i < KS / 8) nd128[i] = make_uint4(0u, 0u, 0u, 0u); }
-        if (BKT) {      // dq = 0 everywhere, nothing listed yet
-#pragma unroll
-            for (int j = 0; j < JG; j++) reinterpret_cast<float4 *>(c.q)[gl + G * j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int k = gl; k < KS / 32; k += G) c.inl[k] = 0u;
-            c.cnt = 0;
-        } else {
 #pragma unroll(MULTI ? 2 : JG)
-            for (int j = 0; j < JG; j++) {
-                const int cidx = gl + G * j;
-                const float4 g01 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx), g23 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx + 16u);
-                reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(g01.x * g01.y, g01.z * g01.w, g23.x * g23.y, g23.z * g23.w);
-            }
+        for (int j = 0; j < JG; j++) {
+            const int cidx = gl + G * j;
+            const float4 g01 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx), g23 = lds_f4(c.ginv_sa + 32u * (uint32_t)cidx + 16u);
+            reinterpret_cast<float4 *>(c.q)[cidx] = make_float4(g01.x * g01.y, g01.z * g01.w, g23.x * g23.y, g23.z * g23.w);
         }
     }
     c.pmm = 1.f; c.coefm = (float)len + P.gas[m]; c.C = 0.f;
@@ -433,55 +419,9 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         }
     }
     if (Q1) __syncwarp();
-    if (BKT) {
-        // The document's topic list S (W:376-391) in first-occurrence order -- own view's tokens by position, then the other
-        // views in view order -- and dq of every listed topic.  Blocks of G tokens with a warp-uniform trip count; inside a
-        // block the lowest lane holding a topic is its leader (match.any), a leader whose topic is not listed yet appends it at
-        // count + (number of appending leaders below it): deterministic whatever the hardware's atomic order.  More than
-        // BKT_CAP distinct topics: the count keeps running (entries beyond the capacity are not stored) and the document is
-        // sampled by the dense form.
-        const int lane = threadIdx.x & 31;
-        const unsigned sh = (unsigned)(lane - gl), gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
-        for (int i = 0; i < (MULTI ? P.M : 1); i++) {
-            const int vi = MULTI ? ((i == 0) ? m : (i <= m ? i - 1 : i)) : m;          // own view first
-            const long long bi = P.doc_off[vi][d];
-            const int leni = (len != 0) ? (int)(P.doc_off[vi][d + 1] - bi) : 0;
-            const int *zi = P.zv[vi] + bi;
-            const int maxl = (NSUB == 1) ? leni : __reduce_max_sync(FULL, leni);
-            for (int base = 0; base < maxl; base += G) {
-                const int k = base + gl;
-                const int t = (k < leni) ? zi[k] : -1;
-                const bool have = t >= 0;
-                const unsigned peers = __match_any_sync(FULL, have ? (unsigned)(t | ((lane / G) << 16)) : (0x40000000u | (unsigned)lane));
-                const bool leader = have && (__ffs(peers) - 1 == lane);
-                bool fresh = false;
-                unsigned word = 0u;
-                if (leader) { word = lds_u32(c.inl_sa + 4u * (uint32_t)(t >> 5)); fresh = !((word >> (t & 31)) & 1u); }
-                __syncwarp();
-                if (leader && fresh) atomicOr(c.inl + (t >> 5), 1u << (t & 31));
-                const unsigned win = (__ballot_sync(FULL, leader && fresh) >> sh) & gmask;
-                if (leader && fresh) {
-                    const int idx = c.cnt + __popc(win & ((1u << gl) - 1u));
-                    if (idx < 16 * G) sts_u16(c.list_sa + 2u * (uint32_t)idx, (unsigned)t);
-                }
-                c.cnt += __popc(win);
-                if (leader) {
-                    const float ndv = (float)c.nd[t];
-                    bool inS = false; float ocv = 0.f, pri = 0.f;
-                    if (MULTI) {
-                        const bool oth = (c.om[t >> 5] >> (t & 31)) & 1u;
-                        inS = (ndv > 0.f) || oth;
-                        if (inS) { ocv = oth ? c.oc[t] : 0.f; pri = prior_other<MULTI>(P, c, t); }
-                    }
-                    c.q[t] = q_value<MULTI, true>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t));
-                }
-                __syncwarp();
-            }
-        }
-    }                                                               // (no per-chunk beta*sum(q) registers in this mode)
     // q of the topics some token of the document holds (S of W:376-391 plus, harmlessly, the skipped first token's topic):
     // one token per lane, duplicates recompute the same value
-    for (int i = 0; i < ((MULTI ? P.M : 1) & (BKT ? 0 : 0xff)); i++) {
+    for (int i = 0; i < (MULTI ? P.M : 1); i++) {
         const int vi = MULTI ? i : m;
         const long long bi = P.doc_off[vi][d];
         const int leni = (len != 0) ? (int)(P.doc_off[vi][d + 1] - bi) : 0;
@@ -502,12 +442,10 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         }
     }
     __syncwarp();
-    if (!BKT) {
 #pragma unroll
-        for (int j = 0; j < JG; j++) {
-            const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];
-            bsq[j] = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
-        }
+    for (int j = 0; j < JG; j++) {
+        const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];
+        bsq[j] = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
     }
     __syncwarp();
 }
@@ -517,24 +455,15 @@ __device__ __forceinline__ float topic_weight(int n, float q, float beta) { retu
 
 // per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, each topic weighted (n + beta) * q,
 // evaluated as beta*sum(q) (registers, bsq) + sum n*q.  Returns the lane total (= cum[JG-1]).
-// DUAL: q is the sum of two arrays (the CTA's q0 + the document's dq: the dense form of a bucketed document whose topic list
-// overflowed) and beta*sum(q) is evaluated on the spot instead of being read from registers.
-template <int JG, int G, bool DUAL = false>
-__device__ __forceinline__ float lane_weights(uint32_t row_gl_sa, uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG], uint32_t q2_gl_sa = 0u,
-                                              float beta = 0.f)
+template <int JG, int G>
+__device__ __forceinline__ float lane_weights(uint32_t row_gl_sa, uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG])
 {   // row_gl_sa / q_gl_sa: .shared address of the lane's first chunk (base + 16*gl); chunk j sits 16*G*j bytes further
     float tot = 0.f;
 #pragma unroll
     for (int j = 0; j < JG; j++) {
         const int4 r = lds_i4(row_gl_sa + 16u * G * j);
-        float4 qq = lds_f4(q_gl_sa + 16u * G * j);
-        float bs = bsq[j];
-        if (DUAL) {
-            const float4 q2 = lds_f4(q2_gl_sa + 16u * G * j);
-            qq.x += q2.x; qq.y += q2.y; qq.z += q2.z; qq.w += q2.w;
-            bs = beta * ((qq.x + qq.y) + (qq.z + qq.w));
-        }
-        float a = fmaf(__int2float_rn(r.x), qq.x, bs);
+        const float4 qq = lds_f4(q_gl_sa + 16u * G * j);
+        float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
         a = fmaf(__int2float_rn(r.y), qq.y, a);
         a = fmaf(__int2float_rn(r.z), qq.z, a);
         a = fmaf(__int2float_rn(r.w), qq.w, a);
@@ -550,12 +479,11 @@ __device__ __forceinline__ float next_below(float x) { return __int_as_float(__f
 // group-cooperative selection: returns the topic whose cumulative weight (lane-major scan order inside the group) first
 // exceeds target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket (W:522).  Every lane of the warp
 // must call it (full-mask shuffles); groups whose document is exhausted compute on stale data and ignore the result.
-template <int JG, int G, bool DUAL = false>
-__device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C,
-                                            uint32_t q2_gl_sa = 0u)
+template <int JG, int G>
+__device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
 {
     float cum[JG];
-    const float lane_total = lane_weights<JG, G, DUAL>(row_gl_sa, q_gl_sa, bsq, cum, q2_gl_sa, beta);
+    const float lane_total = lane_weights<JG, G>(row_gl_sa, q_gl_sa, bsq, cum);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
@@ -595,8 +523,7 @@ __device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa
     }
     const int cidx = gl + G * jsel;
     const int4 rr = lds_i4(row_gl_sa + 16u * G * (uint32_t)jsel);
-    float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
-    if (DUAL) { const float4 q2 = lds_f4(q2_gl_sa + 16u * G * (uint32_t)jsel); qq.x += q2.x; qq.y += q2.y; qq.z += q2.z; qq.w += q2.w; }
+    const float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
     const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
     const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
     const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
@@ -607,97 +534,32 @@ __device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa
     return newbucket ? -1 : sel;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Bucketed sampling (BKT) -- the reference's own decomposition of the conditional (W:495-538), evaluated by a lane group:
-//   new-topic bucket C (W:515)  |  document bucket D = sum over the listed topics t in S of (n_wk[w][t] + beta) * dq[t]  (W:496-513)
-//   |  tree bucket T_w = sum over ALL topics of (n_wk[w][t] + beta) * q0[t]  (the root of the word's F+tree, W:531-538)
-// with q[t] = q0[t] + dq[t].  D costs O(|S| / G) per lane instead of O(K / G); T_w is read from a per-word array (SweepParams::tw)
-// that k_tree_mass fills before the pass and every changed token keeps current, exactly what the reference's updater does to
-// the two leaves of the word's tree (U:242-260); only a draw that FALLS into the tree bucket scans the row densely (against the
-// fresh row: the stale T_w only decided the bucket, like the reference's stale trees, Q3).
-// doc_bucket<E>: per-lane entry weights w[j] (entry e = gl + G*j of the list), returns the lane sum.
-// ------------------------------------------------------------------------------------------------
-template <int G, int E>
-__device__ __forceinline__ float doc_bucket(const DocCtx &c, uint32_t row_sa, int gl, float beta, float (&w)[E])
-{
-    float ls = 0.f;
-#pragma unroll
-    for (int j = 0; j < E; j++) {
-        const int e = gl + G * j;
-        float wj = 0.f;
-        if (e < c.cnt) {
-            const uint32_t t = lds_u16(c.list_sa + 2u * (uint32_t)e);
-            const float dqv = lds_f32(c.sa + 4u * t);
-            wj = fmaf(__int2float_rn((int)lds_u32(row_sa + 4u * t)), dqv, beta * dqv);
-        }
-        w[j] = wj; ls += wj;
-    }
-    return ls;
-}
-
-// Returns the sampled topic (>= 0), -1 for the new-topic bucket, or -2 when the draw fell into the tree bucket: then *frac is the
-// position inside it, in [0, 1), and the caller scans the row (group_select over q0).  Every lane of the warp calls it.
-template <int G, int E>
-__device__ __forceinline__ int bucket_select(const DocCtx &c, uint32_t row_sa, int lane, int gl, float beta, float u, float C, float tw, float *frac)
-{
-    float w[E];
-    const float ls = doc_bucket<G, E>(c, row_sa, gl, beta, w);
-    float incl = ls;
-#pragma unroll
-    for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
-    const float D = __shfl_sync(FULL, incl, G - 1, G);
-    tw = fmaxf(tw, 0.f);
-    const float x = u * (C + D + tw) - C;                                       // position behind the new-topic bucket (W:522)
-    const bool in_doc = (D > 0.f) && (x < D);
-    // document bucket: lane by ballot, entry by a linear search over the register-resident weights (clamped like group_select)
-    const float target = fminf(fmaxf(x, 0.f), next_below(D));
-    const unsigned sh = (unsigned)(lane - gl), gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
-    const unsigned hit = (__ballot_sync(FULL, incl > target) >> sh) & gmask;
-    const int L = __ffs(hit) - 1;
-    const float r = fminf(target - (incl - ls), next_below(ls));
-    int jsel = 0; float run = 0.f;
-#pragma unroll
-    for (int j = 0; j < E - 1; j++) { run += w[j]; jsel += (r >= run) ? 1 : 0; }
-    const int mine = (int)lds_u16(c.list_sa + 2u * (uint32_t)(gl + G * jsel));
-    const int sel = __shfl_sync(FULL, mine, L & (G - 1), G);
-    *frac = fminf(fmaxf((x - D) / fmaxf(tw, 1e-30f), 0.f), 0.99999994f);
-    return (x < 0.f) ? -1 : (in_doc ? sel : -2);
-}
-
 // shared-memory carve-up -------------------------------------------------------------------------
-// CTA level: {ga_tree, 1/(n_k + betaSum)} float2[KS], delta n_k int[KS], (multi) gamma_i*alpha_i float[M][KS], (bucketed) q0 float[KS]
-__host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi, bool bkt = false)
-{ return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4 + (bkt ? (size_t)KS * 4 : 0); }
-__host__ __device__ constexpr uint32_t bkt_cap(int G) { return 16u * (uint32_t)G; }         // list entries: up to 16 per lane of the group
-// per-document area: [q KS*4][n_d KS*2][om 256 + cpar 64 (multi)][list 2*cap + listed-bits KS/8 (bucketed)][mbarriers 128]
-// [ring R*KS*4][oc KS*4 (multi, optional)] -- everything the hot loop addresses sits at a compile-time offset from the area's
-// base, the ring (whose size depends on the run-time depth R) comes last
-__host__ __device__ constexpr uint32_t doc_off_list(int KS, bool multi) { return (uint32_t)KS * 6u + (multi ? 320u : 0u); }
-__host__ __device__ constexpr uint32_t doc_off_inl(int KS, bool multi, int G) { return doc_off_list(KS, multi) + 2u * bkt_cap(G); }
-__host__ __device__ constexpr uint32_t doc_off_mbar(int KS, bool multi, bool bkt = false, int G = 32)
-{ return bkt ? doc_off_inl(KS, multi, G) + (uint32_t)KS / 8u : doc_off_list(KS, multi); }
-__host__ __device__ constexpr uint32_t doc_off_ring(int KS, bool multi, bool bkt = false, int G = 32) { return doc_off_mbar(KS, multi, bkt, G) + 128u; }
-__host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi, bool oc_smem = false, bool bkt = false, int G = 32)
+__host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi) { return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4; }
+// per-document area: [q KS*4][n_d KS*2][om 256 + cpar 64 (multi)][mbarriers 128][ring R*KS*4][oc KS*4 (multi, optional)]
+// -- everything the hot loop addresses sits at a compile-time offset from the area's base, the ring (whose size depends on
+// the run-time depth R) comes last
+__host__ __device__ constexpr uint32_t doc_off_mbar(int KS, bool multi) { return (uint32_t)KS * 6u + (multi ? 320u : 0u); }
+__host__ __device__ constexpr uint32_t doc_off_ring(int KS, bool multi) { return doc_off_mbar(KS, multi) + 128u; }
+__host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi, bool oc_smem = false)
 {
-    size_t b = doc_off_ring(KS, multi, bkt, G) + (size_t)R * KS * 4;
+    size_t b = doc_off_ring(KS, multi) + (size_t)R * KS * 4;
     if (multi && oc_smem) b += (size_t)KS * 4;                    // oc in shared memory
     return (b + 127) & ~(size_t)127;
 }
 
 __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bool multi, DocCtx &c, int *&ring, unsigned long long *&mbar,
-                                          bool oc_smem = false, bool bkt = false, int G = 32)
+                                          bool oc_smem = false)
 {
     c.sa = smem_u32(base);
     c.q = reinterpret_cast<float *>(base);
     c.nd = reinterpret_cast<unsigned short *>(base + (size_t)KS * 4);
     if (multi) { c.om = reinterpret_cast<unsigned *>(base + (size_t)KS * 6); c.cpar = reinterpret_cast<float *>(base + (size_t)KS * 6 + 256); }
     else { c.om = nullptr; c.cpar = nullptr; }
-    c.list_sa = c.sa + doc_off_list(KS, multi); c.inl_sa = c.sa + doc_off_inl(KS, multi, G);
-    c.inl = reinterpret_cast<unsigned *>(base + doc_off_inl(KS, multi, G)); c.cnt = 0;
-    mbar = reinterpret_cast<unsigned long long *>(base + doc_off_mbar(KS, multi, bkt, G));
-    ring = reinterpret_cast<int *>(base + doc_off_ring(KS, multi, bkt, G));
+    mbar = reinterpret_cast<unsigned long long *>(base + doc_off_mbar(KS, multi));
+    ring = reinterpret_cast<int *>(base + doc_off_ring(KS, multi));
     c.oc = nullptr;
-    if (multi && oc_smem) c.oc = reinterpret_cast<float *>(base + doc_off_ring(KS, multi, bkt, G) + (size_t)R * KS * 4);
+    if (multi && oc_smem) c.oc = reinterpret_cast<float *>(base + doc_off_ring(KS, multi) + (size_t)R * KS * 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,7 +567,7 @@ __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bo
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int sweep_max_threads(int JG) { return JG <= 8 ? 768 : 512; }
 
-template <int KS, int G, bool MULTI, bool Q1, bool BKT = false>
+template <int KS, int G, bool MULTI, bool Q1>
 __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_view(const SweepParams P)
 {
     constexpr int JG = KS / (4 * G), NSUB = 32 / G;
@@ -728,14 +590,10 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             for (int i = 0; i < P.M; i++)
                 for (int t = threadIdx.x; t < KS; t += blockDim.x) gaf[(size_t)i * KS + t] = (t < P.K) ? __ldg(P.ga_full[i] + t) : 0.f;
         }
-        if (BKT) {      // q0[t] = gamma*alpha[t] / (n_k[t] + betaSum): the document-independent part of q
-            float *q0 = reinterpret_cast<float *>(smem + (size_t)KS * 12 + (MULTI ? (size_t)P.M * KS * 4 : 0));
-            for (int t = threadIdx.x; t < KS; t += blockDim.x) q0[t] = ginv[t].x * ginv[t].y;
-        }
     }
     DocCtx c; int *ring; unsigned long long *mbar;
-    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0, BKT) + (size_t)(warp * NSUB + sub) * smem_doc_bytes(KS, R, MULTI, P.oc_smem != 0, BKT, G),
-              KS, R, MULTI, c, ring, mbar, P.oc_smem != 0, BKT, G);
+    carve_doc(smem + smem_cta_bytes(KS, MULTI ? P.M : 0) + (size_t)(warp * NSUB + sub) * smem_doc_bytes(KS, R, MULTI, P.oc_smem != 0), KS, R, MULTI,
+              c, ring, mbar, P.oc_smem != 0);
     c.gaf = reinterpret_cast<const float *>(smem + (size_t)KS * 12); c.gaf_stride = KS;
     if (MULTI && !P.oc_smem) c.oc = P.oc_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) * NSUB + (size_t)(warp * NSUB + sub)) * P.Kp;
     uint32_t cta_sa = smem_u32(smem);
@@ -749,21 +607,13 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
 
     const uint32_t row_bytes = (uint32_t)P.Kp * 4u;
     asm volatile("" : "+r"(c.sa));                                // opaque: ONE register carries the document area's base
-    const uint32_t mbar_u32 = c.sa + doc_off_mbar(KS, MULTI, BKT, G), ring_u32 = c.sa + doc_off_ring(KS, MULTI, BKT, G);
+    const uint32_t mbar_u32 = c.sa + doc_off_mbar(KS, MULTI), ring_u32 = c.sa + doc_off_ring(KS, MULTI);
     const uint32_t q_gl_sa = c.sa + 16u * (uint32_t)gl;
     unsigned phasebits = 0u;
     unsigned n_tok = 0, n_changed = 0, n_new = 0;                 // per lane group: far below 2^32 per launch
     const int m = P.m;
     int *zmv = P.zv[m];
     float bsq[JG];
-    // BKT: the tree bucket's scan runs over q0; its beta*sum(q0) per chunk is a per-thread constant of the whole pass
-    const uint32_t q0_sa = cta_sa + (uint32_t)KS * 12u + (MULTI ? (uint32_t)P.M * KS * 4u : 0u);
-    const uint32_t q0_gl_sa = q0_sa + 16u * (uint32_t)gl;
-    unsigned n_tree = 0;
-    if (BKT) {
-#pragma unroll
-        for (int j = 0; j < JG; j++) { const float4 qq = lds_f4(q0_gl_sa + 16u * G * j); bsq[j] = P.beta * ((qq.x + qq.y) + (qq.z + qq.w)); }
-    }
 
     // Work items are claimed two documents ahead and the next document's offsets and first tokens are loaded while the
     // current one is being sampled, so a new document starts with everything in registers (short documents -- side
@@ -772,8 +622,6 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
     int item0 = __shfl_sync(FULL, claim(), 0);
     int item_next_raw = claim();                                   // lane 0 holds it; broadcast when consumed
     int d = 0, len = 0, wcur = 0, zcur = -1, wnext = 0, wahead = 0;
-    float twcur = 0.f, twnext = 0.f;                               // BKT: tree masses of the words in wcur / wnext
-    auto tree_mass_of = [&](int w) { return (BKT && (unsigned)w < (unsigned)P.V) ? __ldcg(P.tw + w) : 0.f; };
     long long b = 0;
     {
         const bool have = item0 + sub < P.n_items;
@@ -784,7 +632,6 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
         zcur = (gl < len) ? zmv[b + gl] : -1;
         wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
         wahead = (R + gl < len) ? __ldg(P.word + b + R + gl) : 0;  // word of the token R positions ahead
-        twcur = (gl < len) ? tree_mass_of(wcur) : 0.f; twnext = (G + gl < len) ? tree_mass_of(wnext) : 0.f;
     }
     while (item0 < P.n_items) {
         const int maxlen = (NSUB == 1) ? len : __reduce_max_sync(FULL, len);
@@ -801,12 +648,11 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             if ((unsigned)w >= (unsigned)P.V) w = 0;
             if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
-        doc_setup<KS, G, MULTI, Q1, BKT>(P, c, d, len, gl, nullptr, true, bsq);
+        doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, nullptr, true, bsq);
         // pipeline stage 2 (d_n has arrived during the setup): next document's extent and first tokens
         const long long b_n = P.doc_off[m][d_n];
         const int len_n = have_n ? (int)(P.doc_off[m][d_n + 1] - b_n) : 0;
         int wcur_n = 0, zcur_n = -1, wnext_n = 0, wahead_n = 0;    // loaded after the first token block (stage 3)
-        float twcur_n = 0.f, twnext_n = 0.f;
 
         int slot = 0;
         for (int base = 0; base < maxlen; base += G) {
@@ -840,27 +686,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                     phasebits ^= 1u << slot;
                 }
                 __syncwarp();
-                int nt;
-                const uint32_t row_gl_sa = q_gl_sa + doc_off_ring(KS, MULTI, BKT, G) + (uint32_t)slot * (KS * 4u);
-                if (BKT) {
-                    const float tw = __shfl_sync(FULL, twcur, i, G);
-                    const uint32_t row_sa = ring_u32 + (uint32_t)slot * (KS * 4u);
-                    // entries per lane: a warp-uniform choice (the groups of a warp hold documents of near-equal length)
-                    const int cmax = (NSUB == 1) ? c.cnt : __reduce_max_sync(FULL, c.cnt);
-                    float frac = 0.f;
-                    if (cmax <= 2 * G) nt = bucket_select<G, 2>(c, row_sa, lane, gl, P.beta, u, c.C, tw, &frac);
-                    else if (cmax <= 4 * G) nt = bucket_select<G, 4>(c, row_sa, lane, gl, P.beta, u, c.C, tw, &frac);
-                    else if (cmax <= 8 * G) nt = bucket_select<G, 8>(c, row_sa, lane, gl, P.beta, u, c.C, tw, &frac);
-                    else if (cmax <= 16 * G) nt = bucket_select<G, 16>(c, row_sa, lane, gl, P.beta, u, c.C, tw, &frac);
-                    else nt = group_select<JG, G, true>(row_gl_sa, q0_gl_sa, lane, gl, P.beta, bsq, u, c.C, q_gl_sa);   // list overflow: dense form
-                    const bool tree = valid && (nt == -2);
-                    if (__any_sync(FULL, tree)) {                               // every lane scans: full-mask shuffles inside
-                        const int tt = group_select<JG, G>(row_gl_sa, q0_gl_sa, lane, gl, P.beta, bsq, frac, 0.f);
-                        if (tree) { nt = tt; n_tree++; }
-                    }
-                } else {
-                    nt = group_select<JG, G>(row_gl_sa, q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
-                }
+                int nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
                 if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
                 else nt = ot;
                 __syncwarp();
@@ -870,17 +696,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
-                apply_pair<KS, G, MULTI, Q1, BKT>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
-                if (BKT && valid) {     // a topic that enters the document joins the list once (first-occurrence order)
-                    const unsigned word = lds_u32(c.inl_sa + 4u * (uint32_t)(nt >> 5));
-                    if (!((word >> (nt & 31)) & 1u)) {
-                        if (gl == 0) {
-                            sts_u32(c.inl_sa + 4u * (uint32_t)(nt >> 5), word | (1u << (nt & 31)));
-                            if (c.cnt < (int)bkt_cap(G)) sts_u16(c.list_sa + 2u * (uint32_t)c.cnt, (unsigned)nt);
-                        }
-                        c.cnt++;
-                    }
-                }
+                apply_pair<KS, G, MULTI, Q1>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
                 if (valid) {
                     if (nt != ot && P.update_global) {                       // U:197-218
                         const int tsel = (gl & 1) ? ot : nt, v = (gl & 1) ? -1 : 1;
@@ -888,8 +704,6 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                             if (gl < 2) atomicAdd(P.nwk + (size_t)w * P.Kp + tsel, v);
                             else if (gl < 4) reds_add(dnk_sa + 4u * (uint32_t)tsel, v);
                         }
-                        // the word's tree mass follows the two leaves that changed (U:242-260)
-                        if (BKT && gl == 4) atomicAdd(P.tw + w, lds_f32(q0_sa + 4u * (uint32_t)nt) - (ot >= 0 ? lds_f32(q0_sa + 4u * (uint32_t)ot) : 0.f));
                     }
                     n_changed += (nt != ot);
                     n_tok++;
@@ -902,17 +716,15 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                 zmv[b + base + gl] = znew;
                 if (P.z_host) P.z_host[b + base + gl] = znew;       // posted write over PCIe, one 4*G-byte run per block
             }
-            wcur = wnext; twcur = twnext;
+            wcur = wnext;
             wahead = (base + G + R + gl < len) ? __ldg(P.word + b + base + G + R + gl) : 0;
             zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;
             wnext = (base + 2 * G + gl < len) ? __ldg(P.word + b + base + 2 * G + gl) : 0;
-            twnext = (base + 2 * G + gl < len) ? tree_mass_of(wnext) : 0.f;
             if (base == 0) {   // pipeline stage 3: the next document's first tokens (its offsets arrived long ago)
                 wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
                 zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
                 wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
                 wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
-                twcur_n = (gl < len_n) ? tree_mass_of(wcur_n) : 0.f; twnext_n = (G + gl < len_n) ? tree_mass_of(wnext_n) : 0.f;
             }
         }
         if (maxlen == 0) {     // (cannot happen: the work list holds non-empty documents only; keeps the pipeline total)
@@ -920,16 +732,14 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
             wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
             wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
-            twcur_n = (gl < len_n) ? tree_mass_of(wcur_n) : 0.f; twnext_n = (G + gl < len_n) ? tree_mass_of(wnext_n) : 0.f;
         }
         item0 = item_n; d = d_n; b = b_n; len = len_n;
-        wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n; twcur = twcur_n; twnext = twnext_n;
+        wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n;
     }
     if (gl == 0) {
         if (n_tok) atomicAdd(P.stats + 0, (unsigned long long)n_tok);
         if (n_changed) atomicAdd(P.stats + 1, (unsigned long long)n_changed);
         if (n_new) atomicAdd(P.stats + 2, (unsigned long long)n_new);
-        if (n_tree) atomicAdd(P.stats + 3, (unsigned long long)n_tree);
     }
     __syncthreads();
     if (P.update_global) {
@@ -1046,31 +856,6 @@ __global__ void k_init_from_phi(int m, int K, int Kp, int V, long long n_docs, c
             }
             z[b + i] = pick < 0 ? last : pick;
         }
-    }
-}
-
-// Tree masses for the bucketed sampler: tw[w] = sum_t (n_wk[w][t] + beta) * gamma*alpha[t] / (n_k[t] + betaSum) -- the root value
-// of the word's F+tree as buildFTrees (M:2660-2696) would compute it from the same counts (0 for inactive topics, M:2670).  One
-// warp per word, 128-bit row loads; HBM-bound, one pass over the table per view pass.
-__global__ void k_tree_mass(int V, int K, int Kp, const int *nwk, const int *nk_frozen, const float *ga_tree, float beta, float betaSum, float *tw)
-{
-    extern __shared__ float q0s[];
-    for (int t = threadIdx.x; t < Kp; t += blockDim.x)
-        q0s[t] = (t < K) ? ga_tree[t] / ((float)nk_frozen[t] + betaSum) : 0.f;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int w = blockIdx.x * nwarp + (threadIdx.x >> 5); w < V; w += gridDim.x * nwarp) {
-        const int4 *row = reinterpret_cast<const int4 *>(nwk + (size_t)w * Kp);
-        float acc = 0.f;
-        for (int c4 = lane; c4 < Kp / 4; c4 += 32) {
-            const int4 r = row[c4];
-            const float4 q = reinterpret_cast<const float4 *>(q0s)[c4];
-            acc = fmaf((float)r.x + beta, q.x, acc); acc = fmaf((float)r.y + beta, q.y, acc);
-            acc = fmaf((float)r.z + beta, q.z, acc); acc = fmaf((float)r.w + beta, q.w, acc);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) tw[w] = acc;
     }
 }
 

@@ -220,8 +220,7 @@ class Engine:
         self._ck(self.L.mvtm_stats(self.h, C.byref(s)))
         return {"tokens": s.tokens, "changed": s.changed, "new_topic": s.new_topic, "ms_total": s.ms_total,
                 "ms_view": [s.ms_view[m] for m in range(self.M)], "kernel_launches": s.kernel_launches,
-                "ring_depth": [s.ring_depth[m] for m in range(self.M)], "ring_locked": [s.ring_locked[m] for m in range(self.M)],
-                "tree_draws": s.tree_draws, "bucketed": [s.bucketed[m] for m in range(self.M)]}
+                "ring_depth": [s.ring_depth[m] for m in range(self.M)], "ring_locked": [s.ring_locked[m] for m in range(self.M)]}
 
     # --- readers -----------------------------------------------------------------------------------
     def cond_probs(self, m, doc, pos, p_row=None, not_in_S=None, tree_mode=0):

@@ -47,9 +47,6 @@
 #define ORC_F_ENGINE_MIRROR 16u  /* view-major order, dense single-scan sampler in the engine's order     */
 #define ORC_F_DOC_ORDER     32u  /* (engine mirror) plain document order, no length sort                 */
 #define ORC_F_FROZEN        64u  /* global counts frozen: the inferencer's nut = 0 mode, I:211-256 */
-#define ORC_F_BUCKETED     512u /* engine mirror of the bucketed sampler: new-topic bucket, document bucket over the document's topic
-                                   list (first-occurrence order, entries visited lane-major over the engine's G lanes), tree bucket
-                                   scanned densely at the position the draw has inside it */
 #define ORC_F_BARE_TREES    128u /* Q13: the inferencer's trees hold phi without gamma*alpha and ignore the inactive set (I:561-576) */
 
 typedef struct {
@@ -703,21 +700,6 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
     int64_t b = o->doc_off[m][d];
     uint8_t *rf = ((flags & ORC_F_Q1_COMPAT) && o->rflag) ? o->rflag + (size_t)d * K : NULL;
     g_not_in_S = rf;
-    /* bucketed mirror: the document's topic list, own view first, then the other views in view order, first occurrences only */
-    int *blist = NULL; uint8_t *listed = NULL; int bcnt = 0;
-    double *wtree = NULL;
-    const int G = o->engine_G;
-    if (flags & ORC_F_BUCKETED) {
-        blist = (int *)malloc((size_t)K * sizeof(int)); listed = (uint8_t *)calloc((size_t)K, 1);
-        wtree = (double *)malloc((size_t)K * 8);
-        for (int ii = 0; ii < M; ii++) {
-            int vi = (ii == 0) ? m : (ii <= m ? ii - 1 : ii);
-            for (int64_t k = o->doc_off[vi][d]; k < o->doc_off[vi][d + 1]; k++) {
-                int t = o->z[vi][k];
-                if (t >= 0 && !listed[t]) { listed[t] = 1; blist[bcnt++] = t; }
-            }
-        }
-    }
     for (int pos = 0; pos < len[m]; pos++) {
         int w = o->word[m][b + pos];
         if (w >= o->V[m] || w < 0) continue;
@@ -733,37 +715,7 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
         engine_weights(o, m, w, s->nd, len, p, nk_frozen, s->cum);
         uint32_t x[4];
         orc_draw(o, (uint32_t)pos, (uint32_t)(o->doc_base + d * o->doc_stride), (uint32_t)iteration, (uint32_t)m, ORC_PURPOSE_SAMPLE, x);
-        int new_t;
-        if ((flags & ORC_F_BUCKETED) && bcnt <= 16 * G) {
-            const int32_t *row = o->n_wk[m] + (size_t)w * K;
-            double T = 0, D = 0;
-            for (int t = 0; t < K; t++) {
-                double ga = (o->n_inactive && is_inactive(o, t)) ? 0.0 : o->gamma[m] * o->alpha[m][t];
-                if (flags & ORC_F_BARE_TREES) ga = 1.0;
-                wtree[t] = (row[t] + o->beta[m]) / (nk_frozen[t] + o->betaSum[m]) * ga;
-                T += wtree[t];
-            }
-            for (int e = 0; e < bcnt; e++) { double dv = s->cum[blist[e]] - wtree[blist[e]]; D += dv > 0 ? dv : 0; }
-            double xx = u24(x[0]) * (C + D + T) - C;
-            if (xx < 0) new_t = o->inactive[0];
-            else if (D > 0 && xx < D) {          /* document bucket, entries in the engine's lane-major order */
-                double cumw = 0; new_t = -1; int last = -1;
-                for (int gl = 0; gl < G && new_t < 0; gl++)
-                    for (int e = gl; e < bcnt; e += G) {
-                        double dv = s->cum[blist[e]] - wtree[blist[e]]; if (dv < 0) dv = 0;
-                        cumw += dv; if (dv > 0) last = blist[e];
-                        if (cumw > xx) { new_t = blist[e]; break; }
-                    }
-                if (new_t < 0) new_t = last;
-            } else {
-                double frac = (xx - D) / T; if (frac < 0) frac = 0; if (frac > 0.99999994) frac = 0.99999994;
-                new_t = orc_engine_select_g(wtree, K, frac, 0.0, -1, G);
-                cnt[2]++;
-            }
-        } else {
-            new_t = orc_engine_select_g(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1, o->engine_G);
-        }
-        if ((flags & ORC_F_BUCKETED) && !listed[new_t]) { listed[new_t] = 1; blist[bcnt++] = new_t; }
+        int new_t = orc_engine_select_g(s->cum, K, u24(x[0]), C, o->n_inactive ? o->inactive[0] : -1, o->engine_G);
         o->z[m][b + pos] = new_t;
         if (rf) {                                       /* W:563-584 is dead code: a topic gained while absent is never inserted */
             int held = 0;
@@ -778,7 +730,6 @@ static void sample_docview_engine(orc_t *o, int64_t d, int m, int iteration, uns
             cnt[3]++;
         }
     }
-    free(blist); free(listed); free(wtree);
 }
 
 static int cmp_len_desc(const void *a, const void *b, void *arg)
@@ -835,14 +786,7 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
             for (int64_t d = 0; d < o->D; d++) order[d] = d;
             if (!(flags & ORC_F_DOC_ORDER)) qsort_r(order, (size_t)o->D, 8, cmp_len_desc, o->doc_off[m]);
             memset(dnk, 0, (size_t)K * 4);
-            /* the engine samples a view with the bucketed form when its documents hold >= 24 tokens on average (use_bucketed, mvtm.cu) */
-            unsigned vflags = flags;
-            if (flags & ORC_F_BUCKETED) {
-                int64_t items = 0;
-                for (int64_t dd = 0; dd < o->D; dd++) items += (o->doc_off[m][dd + 1] > o->doc_off[m][dd]);
-                if (!(items > 0 && o->total_tokens[m] >= 24 * items)) vflags &= ~ORC_F_BUCKETED;
-            }
-            for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, vflags, s, nk_frozen, dnk, cnt);
+            for (int64_t k = 0; k < o->D; k++) sample_docview_engine(o, order[k], m, iteration, flags, s, nk_frozen, dnk, cnt);
             g_not_in_S = NULL;
             if (!(flags & ORC_F_FROZEN)) {       /* the engine flushes its n_k deltas at the end of the view pass */
                 memcpy(nk_frozen, o->n_k[m], (size_t)K * 4);

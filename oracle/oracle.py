@@ -14,7 +14,6 @@ _SO = os.path.join(_HERE, "libmvtm_oracle.so")
 
 F_Q1_COMPAT, F_STALE_TREES, F_DEFERRED, F_BETA_MALLET, F_ENGINE_MIRROR, F_DOC_ORDER, F_FROZEN, F_BARE_TREES = 1, 2, 4, 8, 16, 32, 64, 128
 F_CHECK_RULE = 256
-F_BUCKETED = 512
 
 
 _STAMP = _SO + ".cpuflags"

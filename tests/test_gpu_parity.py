@@ -165,15 +165,10 @@ def _scan_rank(K, G, JG):
     return rank
 
 
-@pytest.mark.parametrize("dense", [True, False])
 @pytest.mark.parametrize("K,Vs,means", [(50, [300], [6]), (130, [300, 100, 50], [20, 4, 2]), (500, [800], [40]),
-                                        (1000, [500, 200], [30, 5]), (2000, [300], [25]), (500, [800], [150]), (1000, [400, 60], [120, 6])])
-def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means, dense):
-    """dense = True: every view through the dense O(K) scan (MVTM_FLAG_DENSE_SCAN); False: the default, where views of long
-    documents go through the bucketed sampler (new-topic / document-list / tree bucket) and the mirror walks the same buckets
-    in the same order (ORC_F_BUCKETED).
-
-    With the global counts frozen (the inferencer's mode, I:211-256) documents are independent, so the fully
+                                        (1000, [500, 200], [30, 5]), (2000, [300], [25])])
+def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means):
+    """With the global counts frozen (the inferencer's mode, I:211-256) documents are independent, so the fully
     parallel engine is deterministic: same Philox uniforms + same scan order => the engine and the fp64 mirror pick
     the same topic for every token except where fp32 rounding moves a boundary past the uniform.  A single such
     "root" flips the rest of its document (common-uniform CDF coupling), so the check is per document: at most
@@ -181,7 +176,7 @@ def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means,
     O = oracle_mod
     M = len(Vs)
     views = random_corpus(K + 3, 400, K, Vs, means)
-    e, o = make_pair(O, K, Vs, views, seed=77, flags=16 if dense else 0)          # MVTM_FLAG_DENSE_SCAN
+    e, o = make_pair(O, K, Vs, views, seed=77)
     e.init_assignments(); o.init_assignments()
     G, JG = e.scan_layout()
     o.set_engine_group(G)
@@ -191,13 +186,7 @@ def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means,
         if M > 1:
             P = np.full((M, M), 0.3 + it / 100)
             e.set_hyper(p_a=P); o.set_hyper(p_a=P)
-        tree0 = int(o.bucket_counters()[2])
-        e.sweep(it, update_global=False); o.sweep(it, O.F_ENGINE_MIRROR | O.F_FROZEN | (0 if dense else O.F_BUCKETED))
-        bucketed = e.stats()["bucketed"]
-        if any(bucketed):       # the tree bucket (W:531-538) is hit as often as in the mirror
-            want_tree = int(o.bucket_counters()[2]) - tree0
-            assert abs(e.stats()["tree_draws"] - want_tree) <= 0.02 * want_tree + 10, (e.stats()["tree_draws"], want_tree)
-        assert not (dense and any(bucketed)) and (dense or bucketed[0] == int(means[0] >= 30))
+        e.sweep(it, update_global=False); o.sweep(it, O.F_ENGINE_MIRROR | O.F_FROZEN)
         ze = [e.get_assignments(m) for m in range(M)]
         zo = [o.get_assignments(m) for m in range(M)]
         bad_docs = 0
@@ -208,8 +197,7 @@ def test_frozen_sweep_tracks_oracle_mirror(engine_lib, oracle_mod, K, Vs, means,
                 if len(diff):
                     bad_docs += 1
                     i = b + diff[0]
-                    if not bucketed[m]:                     # (a bucket boundary is not a neighbourhood in the dense scan order)
-                        assert abs(rank[ze[m][i]] - rank[zo[m][i]]) <= 2, (d, m, int(diff[0]), ze[m][i], zo[m][i])
+                    assert abs(rank[ze[m][i]] - rank[zo[m][i]]) <= 2, (d, m, int(diff[0]), ze[m][i], zo[m][i])
                     break
         assert bad_docs <= max(2, 0.02 * D), (it, bad_docs)
         o.set_assignments(zo)                               # both sides rebuild their counts from the same assignments
@@ -610,7 +598,7 @@ def test_inference_matches_oracle(engine_lib, oracle_mod, bare):
         assert oov.any() and np.all(ze[oov] == 0)
     G, JG = e.scan_layout()
     o.set_engine_group(G)
-    flags = O.F_ENGINE_MIRROR | O.F_FROZEN | O.F_BUCKETED | (O.F_BARE_TREES if bare else 0)
+    flags = O.F_ENGINE_MIRROR | O.F_FROZEN | (O.F_BARE_TREES if bare else 0)
     D = len(new[0][0]) - 1
     for it in range(1, 11):
         e.sweep(it, update_global=2 if bare else 0); o.sweep(it, flags)
@@ -1187,7 +1175,7 @@ def test_ring_depths_keep_invariants_and_track_mirror(engine_lib, oracle_mod, ri
     e = Engine(K, Vs, views, seed=3, ring_depth=ring); o = O.Oracle(K, Vs, views, seed=3)
     e.init_assignments(); o.init_assignments()
     o.set_engine_group(e.scan_layout()[0])
-    e.sweep(1, update_global=False); o.sweep(1, O.F_ENGINE_MIRROR | O.F_FROZEN | O.F_BUCKETED)
+    e.sweep(1, update_global=False); o.sweep(1, O.F_ENGINE_MIRROR | O.F_FROZEN)
     assert e.stats()["ring_depth"] == [ring] * 3 and e.stats()["ring_locked"] == [ring] * 3
     same = sum(int((e.get_assignments(m) == o.get_assignments(m)).sum()) for m in range(3))
     assert same / sum(e.ntok) > 0.99

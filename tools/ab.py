@@ -5,8 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import os, sys
 sys.path.insert(0, %r)
-import mvtopicmodel_b200._lib as L
+import ctypes, mvtopicmodel_b200._lib as L
 L.SO_PATH = sys.argv[1]
+_so = ctypes.CDLL(L.SO_PATH)          # an older build may lack entry points added since: bind what it has
+L.SIGNATURES = {k: v for k, v in L.SIGNATURES.items() if hasattr(_so, k)}
 from mvtopicmodel_b200 import Engine, corpus
 wl, docs = sys.argv[2], (int(sys.argv[3]) if sys.argv[3] != "0" else None)
 K, Vs, views = corpus.generate(wl, docs=docs)
