@@ -33,3 +33,50 @@ def test_cpp_dist_driver_without_torch(engine_lib, tmp_path, world):
     r = subprocess.run([str(exe), str(world), "8"], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0 and "OK" in r.stdout
+
+
+def test_native_comm_layer_single_rank(engine_lib):
+    """The library-side NCCL layer on ONE GPU (world = 1: every collective is the identity, every code path still runs): the
+    communicator is created from a unique id, mvtm_sync_counts / mvtm_sweep_dist / mvtm_comm_drain keep the count invariants bit
+    for bit and sample exactly what mvtm_sweep samples from the same state (same Philox keys, single-warp launch), the stateless
+    mvtm_sweep_host_dist returns the device assignments and leaves the handle refusing mvtm_sweep_dist until the counts are
+    synchronised again, mvtm_loglik_dist equals mvtm_loglik, mvtm_optimize_hyper runs through the library's own reducer."""
+    import numpy as np
+    from helpers import random_corpus
+    from mvtopicmodel_b200 import Engine, MvtmError
+    K, Vs = 130, [300, 100, 50]
+    views = random_corpus(7, 600, K, Vs, [20, 4, 2], oov=True)
+    a = Engine(K, Vs, views, seed=3, flags=2, ring_depth=1)              # MVTM_FLAG_SINGLE_WARP: deterministic
+    b = Engine(K, Vs, views, seed=3, flags=2, ring_depth=1)
+    uid = Engine.comm_unique_id()
+    assert len(uid) == 128
+    with pytest.raises(MvtmError):
+        a.sweep_dist(1)                                                   # no communicator yet
+    a.comm_init(uid, 0, 1, hidden_ctas=8)
+    info = a.comm_info()
+    assert info["rank"] == 0 and info["world"] == 1 and info["nccl_version"] >= 21800
+    a.init_assignments(); b.init_assignments()
+    with pytest.raises(MvtmError):
+        a.sweep_dist(1)                                                   # counts not synchronised yet
+    a.sync_counts()
+    for it in range(1, 5):
+        a.sweep_dist(it); b.sweep(it)
+        a.comm_drain()
+        assert a.check_invariants() == 0
+        for m in range(3):
+            assert np.array_equal(a.get_assignments(m), b.get_assignments(m))
+    assert np.allclose(a.loglik_dist(), b.loglik(), rtol=1e-13, atol=0)
+    z = [a.get_assignments(m).copy() for m in range(3)]
+    a.sweep_host_dist(5, z); b.sweep(5)
+    for m in range(3):
+        assert np.array_equal(z[m], a.get_assignments(m)) and np.array_equal(z[m], b.get_assignments(m))
+    with pytest.raises(MvtmError):
+        a.sweep_dist(6)                                                   # replicas are local-stale after a stateless step
+    a.sync_counts(rebuild=True)
+    a.sweep_dist(6); b.sweep(6); a.comm_drain()
+    assert a.check_invariants() == 0 and all(np.array_equal(a.get_assignments(m), b.get_assignments(m)) for m in range(3))
+    a.optimize_hyper(60); b.optimize_hyper(60)
+    ha, hb = a.get_hyper_full(), b.get_hyper_full()
+    for k in ("alpha", "gamma", "beta", "p_a"):
+        assert np.array_equal(ha[k], hb[k]), k
+    a.close(); b.close()
