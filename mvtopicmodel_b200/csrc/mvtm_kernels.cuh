@@ -150,8 +150,6 @@ struct DocCtx {
     const float *gaf;      // (MULTI) CTA-shared gamma_i*alpha_i[t] of every view, [M][KS] (W:404)
     int gaf_stride;        // = KS
     float pmm, coefm, C;   // p[m][m]; len_m + gas_m; new-topic mass per token (W:515)
-    int oth_n, oth_i;      // (MULTI) number of views with c_i != 0 and the last of them
-    float oth_c;           //         its c_i (0 when there is none)
 };
 
 template <bool MULTI>
@@ -167,10 +165,8 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
 {   // sum_i c_i * gamma_i*alpha_i[t] (W:404); c_i = 0 for the own view and for absent views, so no branch is needed
     float pri = 0.f;
     if (MULTI) {
-#ifndef MVTM_AB_PRIOR_GENERIC
-        // at most one view with c_i != 0 (always so with two views): the sum has one term.  Bit-identical to the loop, whose other
-        // terms are fmaf(0, x, acc) = acc.  (The generic loop compiles to ~45 instructions of unrolling scaffolding per call.)
-        if (c.oth_n <= 1) return c.oth_c * c.gaf[(size_t)c.oth_i * c.gaf_stride + t];
+#ifdef MVTM_AB_PRIOR_ROLLED
+#pragma unroll 1
 #endif
         for (int i = 0; i < P.M; i++) pri = fmaf(c.cpar[i], c.gaf[(size_t)i * c.gaf_stride + t], pri);
     }
@@ -349,7 +345,6 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         c.pmm = draw_p(P, m, gdoc, p_override);
         for (int k = gl; k < KS / 32; k += G) c.om[k] = 0u;
         float cdoc = 0.f;
-        c.oth_n = 0; c.oth_i = 0; c.oth_c = 0.f;
         for (int i = 0; i < P.M; i++) {                           // uniform trip count; per-group work is predicated
             const long long bi = P.doc_off[i][d];
             const int leni = (int)(P.doc_off[i][d + 1] - bi);
@@ -358,7 +353,6 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
             cdoc += pmi * P.ga_new[i] / denom;                    // W:414-416 (every view, no length test)
             const bool other = (i != m && leni != 0 && len != 0);
             const float ci = other ? pmi / denom : 0.f;           // W:403-404
-            if (ci != 0.f) { c.oth_n++; c.oth_i = i; c.oth_c = ci; }
             __syncwarp();
             if (gl == 0) c.cpar[i] = ci;
             if (other) {                                          // histogram of view i into the empty n_d array

@@ -68,6 +68,7 @@ class FastQMVWVParallelTopicModel:
         self.gammaRoot, self.gammaView, self.pMean, self.inActiveTopicIndex = 10.0, np.zeros(M), np.eye(M), []
         self.sweep_ms = []
         self.saveStateInterval, self.stateFilename = 0, None
+        self.engineFlags = 0      # mvtm_config.flags; setReferenceCompat(True) = the reference's behaviour incl. quirks Q1 and Q5
         self.alphabet = [None] * M      # per view: object with lookup_object(i) (ingest.Alphabet) or None -> the id as text
         self.views, self.present = None, None
 
@@ -76,6 +77,13 @@ class FastQMVWVParallelTopicModel:
     def setBurninPeriod(self, n): self.burninPeriod = int(n)
     def setTopicDisplay(self, interval, n): self.showTopicsInterval, self.wordsPerTopic = int(interval), int(n)
     def setRandomSeed(self, seed): self.randomSeed = int(seed)
+
+    def setReferenceCompat(self, on=True):
+        """Not in the reference (it IS the reference): sample with its dense-index quirk Q1 (W:441-468, W:560-584) and MALLET's
+        Beta law for the view-coupling draw (W:333, Q5) instead of the intended semantics.  Call before addInstances."""
+        from ._lib import FLAG_REFERENCE_COMPAT
+        self.engineFlags = (self.engineFlags | FLAG_REFERENCE_COMPAT) if on else (self.engineFlags & ~FLAG_REFERENCE_COMPAT)
+
     def setOptimizeInterval(self, interval): self.optimizeInterval = int(interval)
     def setNumThreads(self, threads): self.numThreads = int(threads)   # kept for API parity; the GPU bounds asynchrony itself
     def setSymmetricAlpha(self, b): pass
@@ -116,7 +124,8 @@ class FastQMVWVParallelTopicModel:
         for m in range(M):
             self.alphabet[m] = getattr(training[m], "alphabet", None)
         self.views, self.present = views, present
-        self.engine = Engine(K, [max(1, v) for v in self.numTypes], views, seed=seed, device=self.device, present=present)
+        self.engine = Engine(K, [max(1, v) for v in self.numTypes], views, seed=seed, device=self.device, present=present,
+                             flags=self.engineFlags)
         self._push_hyper()
         self.engine.init_assignments()          # M:465-515 + buildInitialTypeTopicCounts M:600-652
 
