@@ -1,5 +1,6 @@
 // Multi-GPU driver for the C ABI WITHOUT torch or Python: N host threads, one handle per GPU, NCCL behind mvtm_comm_init.
-// What a JVM host would do with one Java thread per device.  usage: dist_driver [world=2] [sweeps=6]
+// What a JVM host would do with one Java thread per device.  usage: dist_driver [world=2] [sweeps=6] [views=2]
+// (views = 1: a single-view corpus, whose exchange cannot be hidden and runs on the handle's own stream)
 //
 // Corpus: D two-view documents generated from a fixed LCG; rank r holds documents r, r+N, ... (doc_id_base / doc_id_stride).
 // Checks: (1) after mvtm_sync_counts every rank holds the same n_k, totalling the corpus; (2) after S mvtm_sweep_dist sweeps
@@ -18,17 +19,18 @@
 #include "mvtm.h"
 
 namespace {
-constexpr int K = 64, M = 2;
-const int32_t V[M] = { 700, 90 };
-struct Shard { std::vector<int64_t> off[M]; std::vector<int32_t> word[M]; int64_t D = 0; };
-struct Result { std::vector<int32_t> nk[M], z[M], nwk[M]; double ll0[M], ll1[M]; std::vector<double> alpha; int rc = 0; std::string err; };
+constexpr int K = 64, MMAX = 2;
+int M = 2;                                   // views in use (argv[3])
+const int32_t V[MMAX] = { 700, 90 };
+struct Shard { std::vector<int64_t> off[MMAX]; std::vector<int32_t> word[MMAX]; int64_t D = 0; };
+struct Result { std::vector<int32_t> nk[MMAX], z[MMAX], nwk[MMAX]; double ll0[MMAX], ll1[MMAX]; std::vector<double> alpha; int rc = 0; std::string err; };
 
 uint32_t lcg(uint32_t &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
 Shard make_shard(int D_total, int rank, int world)
 {
     Shard sh;
-    for (int m = 0; m < M; m++) sh.off[m].push_back(0);
+    for (int m = 0; m < MMAX; m++) sh.off[m].push_back(0);
     for (int d = 0; d < D_total; d++) {
         uint32_t s = 12345u + 7919u * (uint32_t)d;            // per-document stream: the shard of a document does not change its words
         const int topic = (int)(lcg(s) % 16);
@@ -63,7 +65,7 @@ void rank_main(int rank, int world, int D_total, int sweeps, const unsigned char
     for (int it = 1; it <= sweeps; it++) CHECK(mvtm_sweep_dist(h, it));
     CHECK(mvtm_comm_drain(h));
     // a stateless host step on every rank, then back to resident sweeps
-    std::vector<int32_t> zh[M]; int32_t *zp[M];
+    std::vector<int32_t> zh[MMAX]; int32_t *zp[MMAX];
     for (int m = 0; m < M; m++) { zh[m].resize(sh.word[m].size() + 1); CHECK(mvtm_get_assignments(h, m, zh[m].data())); zp[m] = zh[m].data(); }
     CHECK(mvtm_sweep_host_dist(h, sweeps + 1, zp));
     if (mvtm_sweep_dist(h, sweeps + 2) != MVTM_ERR_STATE) { res.rc = 100; res.err = "mvtm_sweep_dist accepted local-stale replicas"; mvtm_destroy(h); return; }
@@ -81,7 +83,7 @@ void rank_main(int rank, int world, int D_total, int sweeps, const unsigned char
         res.z[m].resize(sh.word[m].size());
     }
     res.alpha.resize((size_t)M * (K + 1));
-    double asum[M]; int32_t ina[K], nin = 0;
+    double asum[MMAX]; int32_t ina[K], nin = 0;
     CHECK(mvtm_get_hyper(h, res.alpha.data(), asum, ina, &nin));
     int32_t r = -1, w = -1, ver = 0; int64_t bytes = 0;
     CHECK(mvtm_comm_info(h, &r, &w, &ver, &bytes));
@@ -93,6 +95,7 @@ void rank_main(int rank, int world, int D_total, int sweeps, const unsigned char
 int main(int argc, char **argv)
 {
     const int world = argc > 1 ? atoi(argv[1]) : 2, sweeps = argc > 2 ? atoi(argv[2]) : 6, D_total = 6000;
+    M = (argc > 3 && atoi(argv[3]) == 1) ? 1 : 2;
     unsigned char id[MVTM_COMM_ID_BYTES];
     if (mvtm_comm_unique_id(id)) { std::printf("mvtm_comm_unique_id: %s\nFAIL\n", mvtm_last_error(nullptr)); return 2; }
     std::vector<Result> res((size_t)world);
