@@ -165,9 +165,13 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
 {   // sum_i c_i * gamma_i*alpha_i[t] (W:404); c_i = 0 for the own view and for absent views, so no branch is needed
     float pri = 0.f;
     if (MULTI) {
-#ifdef MVTM_AB_PRIOR_ROLLED
-#pragma unroll 1
-#endif
+        // two views: the sum has one term (c of the own view is 0).  Bit-identical to the loop, whose other term is
+        // fmaf(0, x, acc) = acc.  (The generic loop compiles to ~45 instructions of unrolling scaffolding per call.)
+        if (P.M == 2) return c.cpar[1 - P.m] * c.gaf[(size_t)(1 - P.m) * c.gaf_stride + t];
+        if (P.M == 3) {     // the two other views in increasing order, as the loop visits them
+            const int i1 = (P.m == 0) ? 1 : 0, i2 = (P.m == 2) ? 1 : 2;
+            return fmaf(c.cpar[i2], c.gaf[(size_t)i2 * c.gaf_stride + t], c.cpar[i1] * c.gaf[(size_t)i1 * c.gaf_stride + t]);
+        }
         for (int i = 0; i < P.M; i++) pri = fmaf(c.cpar[i], c.gaf[(size_t)i * c.gaf_stride + t], pri);
     }
     return pri;
@@ -274,15 +278,11 @@ __host__ __device__ inline double mallet_next_beta(BetaStream &r, double a, doub
     return v1 / (v1 + v2);
 }
 
-// (kept out of line: the default law's path through draw_p stays as short as it was before this mode existed)
-__device__ __noinline__ double draw_beta_mallet(const SweepParams &P, int i, uint32_t gdoc, uint32_t tag, uint4 x)
-{
-    BetaStream st{ gdoc, P.iteration, tag, P.seed_lo, P.seed_hi, 1u, x, 0 };
-    return mallet_next_beta(st, P.pa[i], P.pb[i]);
-}
-
-// the view-coupling draw p[m][i] of W:327-337 for document gdoc (every lane of the group computes the same value)
-__device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
+// the view-coupling draw p[m][i] of W:327-337 for document gdoc (every lane of the group computes the same value).  Two functions,
+// chosen by a uniform branch at the call site: the default law's has no nested call (putting MALLET's law behind a branch INSIDE it
+// cost the short side-view passes 15 %, measured: profiles/r2_ab_compat_build_vs_round_start.log).
+template <bool MALLET>
+__device__ __noinline__ float draw_p_law(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
 {
     int m = P.m;
     double r;
@@ -294,12 +294,10 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
         const uint32_t tag = ((uint32_t)(lo * P.M + hi) << 8) | PURPOSE_PDRAW;
         uint4 x = philox4x32_10(0u, gdoc, P.iteration, tag, P.seed_lo, P.seed_hi);
         double b;
-#ifndef MVTM_AB_NO_MALLET
-        if (P.beta_mallet) {
-            b = draw_beta_mallet(P, i, gdoc, tag, x);
-        } else
-#endif
-        {
+        if (MALLET) {
+            BetaStream st{ gdoc, P.iteration, tag, P.seed_lo, P.seed_hi, 1u, x, 0 };
+            b = mallet_next_beta(st, P.pa[i], P.pb[i]);
+        } else {
             double u = (double)(x.x >> 8) * (1.0 / 16777216.0);
             b = pow(u, 1.0 / P.pa[i]);                          // Beta(a,1) by inversion (Q5: true law)
         }
@@ -308,6 +306,8 @@ __device__ __noinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc,
     if (!p_override && i != 0 && P.sparse[i]) r = 0.0;          // W:335-336 (column i zeroed, incl. the diagonal)
     return (float)r;
 }
+__device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
+{ return P.beta_mallet ? draw_p_law<true>(P, i, gdoc, p_override) : draw_p_law<false>(P, i, gdoc, p_override); }
 
 // Build n_d, (MULTI: oc/om/cpar), q and beta*sum(q) for document d of view P.m (len == 0: nothing to do, but every
 // lane still walks the same __syncwarp sequence -- the groups of a warp hold different documents).
@@ -619,6 +619,9 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
     // current one is being sampled, so a new document starts with everything in registers (short documents -- side
     // views, SMS-sized corpora -- would otherwise pay three dependent global-memory latencies each).
     auto claim = [&]() { int it = 0; if (lane == 0) it = atomicAdd(P.work_counter, NSUB); return it; };
+    // the row a token's TMA load fetches: its word's, or row 0 for an out-of-vocabulary id (the token is skipped, W:427-428, but
+    // its slot of the ring is still filled and consumed) -- decided once when the word is loaded, not per token
+    auto row_word = [&](int w) { return ((unsigned)w < (unsigned)P.V) ? w : 0; };
     int item0 = __shfl_sync(FULL, claim(), 0);
     int item_next_raw = claim();                                   // lane 0 holds it; broadcast when consumed
     int d = 0, len = 0, wcur = 0, zcur = -1, wnext = 0, wahead = 0;
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
         wcur = (gl < len) ? __ldg(P.word + b + gl) : 0;
         zcur = (gl < len) ? zmv[b + gl] : -1;
         wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
-        wahead = (R + gl < len) ? __ldg(P.word + b + R + gl) : 0;  // word of the token R positions ahead
+        wahead = (R + gl < len) ? row_word(__ldg(P.word + b + R + gl)) : 0;  // word of the token R positions ahead
     }
     while (item0 < P.n_items) {
         const int maxlen = (NSUB == 1) ? len : __reduce_max_sync(FULL, len);
@@ -671,8 +674,12 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
             const int wnext0 = __shfl_sync(FULL, wnext, 0, G);
             const int ot_nextblk = ((unsigned)wnext0 < (unsigned)P.V && base + G < len) ? znext : -1;
             int ot_carry = __shfl_sync(FULL, zeff, 0, G);
+            {   // tokens this block resamples (counted once per block, not once per token)
+                const unsigned live = __ballot_sync(FULL, gl < nblk && zeff != -2);
+                n_tok += (unsigned)__popc((live >> (lane - gl)) & ((G == 32) ? FULL : ((1u << (G & 31)) - 1u)));
+            }
             for (int i = 0; i < nblk_max; i++) {
-                const bool act = i < nblk;
+                const bool act = (NSUB == 1) || (i < nblk);            // one document per warp: the trip count is its own
                 const int w = __shfl_sync(FULL, wcur, i, G);
                 const int ot = ot_carry;                                       // = zeff of token i (shuffled one step earlier)
                 const float u = __shfl_sync(FULL, umine, i, G);
@@ -691,8 +698,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                 else nt = ot;
                 __syncwarp();
                 // slot consumed: refill it with the row of token base+i+R
-                if (act && gl == 0 && base + i + R < len) {
-                    if ((unsigned)wa >= (unsigned)P.V) wa = 0;
+                if (act && gl == 0 && base + i + R < len) {                  // (wahead holds in-vocabulary ids only: see row_word)
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
@@ -706,7 +712,6 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                         }
                     }
                     n_changed += (nt != ot);
-                    n_tok++;
                     if (gl == i) znew = nt;
                 }
                 __syncwarp();
@@ -717,21 +722,21 @@ __global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_vi
                 if (P.z_host) P.z_host[b + base + gl] = znew;       // posted write over PCIe, one 4*G-byte run per block
             }
             wcur = wnext;
-            wahead = (base + G + R + gl < len) ? __ldg(P.word + b + base + G + R + gl) : 0;
+            wahead = (base + G + R + gl < len) ? row_word(__ldg(P.word + b + base + G + R + gl)) : 0;
             zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;
             wnext = (base + 2 * G + gl < len) ? __ldg(P.word + b + base + 2 * G + gl) : 0;
             if (base == 0) {   // pipeline stage 3: the next document's first tokens (its offsets arrived long ago)
                 wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
                 zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
                 wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
-                wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
+                wahead_n = (R + gl < len_n) ? row_word(__ldg(P.word + b_n + R + gl)) : 0;
             }
         }
         if (maxlen == 0) {     // (cannot happen: the work list holds non-empty documents only; keeps the pipeline total)
             wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
             zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
             wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
-            wahead_n = (R + gl < len_n) ? __ldg(P.word + b_n + R + gl) : 0;
+            wahead_n = (R + gl < len_n) ? row_word(__ldg(P.word + b_n + R + gl)) : 0;
         }
         item0 = item_n; d = d_n; b = b_n; len = len_n;
         wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n;
