@@ -273,7 +273,7 @@ int mvtm_optimize_hyper(mvtm_handle *h, int32_t iteration, uint32_t which);
  * return 0 on success.  With an all-reduce behind `fn`, the same seed and the same iteration every rank installs identical
  * hyper-parameters.  optimizeBeta needs no reduction: it reads the (already global) count tables.  fn = NULL (default): single handle. */
 /* Activation of inactive topics that received tokens (U:263-270: alpha[m][t] = alpha[m][K], topic leaves inActiveTopicIndex).
- * A single handle does this at the end of every sweep.  With a statistics reducer installed (multi-rank) the sweep leaves it to
+ * A single handle does this after every view pass of mvtm_sweep (the reference: per delta).  With a statistics reducer installed (multi-rank) the sweep leaves it to
  * the caller, who calls mvtm_activate_topics AFTER the count exchange so that every rank decides on the same global counts. */
 int mvtm_activate_topics(mvtm_handle *h);
 typedef int (*mvtm_stat_reducer)(void *ctx, int32_t op, int64_t *ints, int64_t n_ints, double *reals, int64_t n_reals);

@@ -12,7 +12,9 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "mvtm_kernels.cuh"), os.path.join(HERE, 
 OUT = os.path.join(HERE, "libmvtm.so")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-ldl", "-split-compile", "0"]
+              "-I" + os.path.join(ROOT, "include"), "-shared", "-Xcompiler", "-fPIC", "-ldl"]
+# NOT -split-compile: with it ptxas' code for the sweep kernel changes from build to build of the SAME source (three variants were
+# seen, one 27 % slower: profiles/r2_ab_codegen_variants.log); the single-threaded compile is deterministic (~110 s).
 
 
 def needs_build():

@@ -566,7 +566,7 @@ static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
     }
     if (docs < NSUB) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
     int W = docs / NSUB;
-    W = std::min(W, sweep_max_threads(JG) / 32);
+    W = std::min(W, sweep_max_threads(KS, G, multi) / 32);
     if (h->cfg_warps > 0) W = std::min(W, h->cfg_warps);
     if (const char *e = getenv("MVTM_WARPS")) W = std::max(1, std::min(W, atoi(e)));
     int grid = h->num_sms;
@@ -751,8 +751,16 @@ static int sweep_impl(mvtm_handle *h, int iteration, int update_global, bool syn
 {
     if (h->sweep_open) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep: passes queued by mvtm_sweep_view_async are still open (call mvtm_sweep_finish)");
     if (int rc = open_sweep(h)) return rc;
-    for (int m = 0; m < h->M; m++)
+    for (int m = 0; m < h->M; m++) {
         if (int rc = enqueue_view_pass(h, iteration, update_global, m, &h->open_launches)) { h->sweep_open = false; return rc; }
+        // The reference's updater activates a sampled inactive topic per delta (U:263-270).  The blocking single-handle sweep does
+        // it after every VIEW PASS rather than once per sweep, so the following views of the same sweep already see the topic as
+        // active (one host synchronisation per view, paid only while some topic is inactive, i.e. after an optimizeDP step).
+        if (update_global == 1 && sync_stats && m + 1 < h->M && !h->inactive.empty() && !h->reducer && !h->comm) {
+            if (int rc = activate_sampled_topics(h)) { h->sweep_open = false; return rc; }
+            if (int rc = upload_hyper(h)) { h->sweep_open = false; return rc; }
+        }
+    }
     if (sync_stats) return close_sweep(h, update_global);
     h->sweep_open = false;
     CK(h, cudaEventRecord(h->ev[1], h->stream));

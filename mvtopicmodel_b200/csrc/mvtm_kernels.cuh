@@ -565,10 +565,23 @@ __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bo
 // ------------------------------------------------------------------------------------------------
 // THE sweep kernel: one launch = one view pass over all documents of the shard  (W:186-233, W:301-597, U:197-218)
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int sweep_max_threads(int JG) { return JG <= 8 ? 768 : 512; }
+// Threads per CTA the kernel is compiled for.  Shared memory, not the register file, limits how many documents an SM holds (one
+// CTA per SM, smem_doc_bytes each), so the launch bound is the largest warp count the shared-memory budget admits for this
+// (KS, G, >= 2 views if MULTI) at ring depth 1 -- and ptxas may use 65536 / bound registers per thread: 96 instead of 80 at
+// K = 1024.  With the flat 768-thread bound of round 1 the K = 1024 kernel sat at the 80-register cap and its quality depended on
+// the build (spilled loop-carried values in some, profiles/r2_ab_codegen_variants*.log).
+__host__ __device__ constexpr int sweep_max_threads(int KS, int G, bool multi)
+{
+    const size_t cta = (size_t)KS * 12 + (multi ? (size_t)2 * KS * 4 : 0);
+    const size_t doc = ((size_t)KS * 6u + (multi ? 320u : 0u) + 128u + (size_t)KS * 4 + 127) & ~(size_t)127;      // smem_doc_bytes(KS, 1, multi)
+    const int docs = (int)((227 * 1024 - 1024 - cta) / doc);
+    int W = docs / (32 / G);
+    W = W > 24 ? 24 : (W < 1 ? 1 : W);
+    return 32 * W;
+}
 
 template <int KS, int G, bool MULTI, bool Q1>
-__global__ void __launch_bounds__(sweep_max_threads(KS / (4 * G)), 1) k_sweep_view(const SweepParams P)
+__global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_view(const SweepParams P)
 {
     constexpr int JG = KS / (4 * G), NSUB = 32 / G;
     extern __shared__ __align__(128) unsigned char smem[];

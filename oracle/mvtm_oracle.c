@@ -792,6 +792,7 @@ int orc_sweep(orc_t *o, int iteration, unsigned flags)
                 memcpy(nk_frozen, o->n_k[m], (size_t)K * 4);
                 recount_nk_hist(o, m);           /* local doc-topic histogram (and a local n_k, replaced below)  */
                 for (int t = 0; t < K; t++) o->n_k[m][t] = nk_frozen[t] + dnk[t];
+                if (m + 1 < o->M) activate_sampled_topics(o);    /* the engine activates after every view pass (mvtm.cu sweep_impl) */
             }
         }
         free(nk_frozen); free(dnk); free(order);
