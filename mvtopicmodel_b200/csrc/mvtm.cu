@@ -47,6 +47,7 @@ struct CommState;                                   // NCCL communicators and ex
 struct mvtm_handle {
     CommState *comm = nullptr;                      // multi-GPU inside the library (mvtm_comm_init)
     int K = 0, M = 0, Kp = 0, J = 0, KS = 0, G = 32;
+    bool direct = false;                            // DIRECT sweep kernel: n_wk rows in registers instead of the TMA ring (mvtm_kernels.cuh)
     long long D = 0;
     int device = 0, num_sms = 0;
     unsigned flags = 0;
@@ -110,10 +111,26 @@ static int pick_J(int K)
 }
 // lanes per document-view (the lane group G of mvtm_kernels.cuh) for a slot size KS = 128 * J.
 // Compiled combinations: (128,8) (256,8) (384,16) (512,8) (512,16) (512,32) (768,16) (1024,16) (1024,32) (1536,32) (2048,32).
-static int pick_G(int KS, bool multi)
+// DIRECT kernels compiled (mvtm_kernels.cuh): rows in registers cost KS/G registers per thread, so only combinations with
+// KS/G <= 64; not in reference-compat (Q1) mode, whose kernels stay on the TMA ring.
+// Measured on B200 (profiles/r2_ab_direct*.log), DIRECT vs TMA ring: K = 1000 two views (acm_2v) 2.14 vs 1.66 G tok/s, K = 1000 one
+// view 2.62 vs 1.97, K = 1000 uniform words (HBM-bound) 1.67 vs 1.50, three views (pubmed_3v) 1.93 vs 1.59; K = 500 (four
+// documents per warp) 3.19 vs 3.26: no gain, stays on the ring; K = 2000 four views (stress_4v, one document per warp, 12 instead
+// of 8 warps per SM) 0.877 vs 0.671 at 200 K documents.
+static bool direct_compiled(int KS, int G) { return (KS == 1024 && G == 16) || (KS == 2048 && G == 32); }
+static bool pick_direct(int KS, bool multi, unsigned flags)
+{
+    (void)multi;
+    if (flags & MVTM_FLAG_Q1_COMPAT) return false;
+    bool d = (KS == 1024 || KS == 2048);
+    if (const char *e = getenv("MVTM_DIRECT")) d = atoi(e) != 0;
+    return d;
+}
+static int pick_G(int KS, bool multi, bool direct = false)
 {
     int g = KS <= 256 ? 8 : (KS <= 1024 ? 16 : 32);       // measured on B200: lda_100k 3.4 (G=16) vs 2.6 G tok/s (G=32)
     if (multi && KS >= 1024) g = 32;                      // measured: acm_2v 1.43 (G=32) vs 1.30 G tok/s (G=16)
+    if (direct && KS == 1024) g = 16;                     // DIRECT: 6.5 KB of shared memory per document leave room for two per warp
     if (const char *e = getenv("MVTM_GROUP")) {
         int want = atoi(e);
         if (want == 32 && (KS == 512 || KS == 1024)) g = 32;
@@ -154,7 +171,9 @@ extern "C" int mvtm_create(const mvtm_config *cfg, mvtm_handle **out)
     h->Kp = (h->K + 31) / 32 * 32;
     h->J = pick_J(h->K);
     h->KS = h->J * 128;
-    h->G = pick_G(h->KS, h->M > 1);
+    h->direct = pick_direct(h->KS, h->M > 1, h->flags);
+    h->G = pick_G(h->KS, h->M > 1, h->direct);
+    if (h->direct && !direct_compiled(h->KS, h->G)) { h->direct = false; h->G = pick_G(h->KS, h->M > 1, false); }
     memset(&h->stats, 0, sizeof(h->stats));
     h->alpha.assign((size_t)h->M * (h->K + 1), 0.1);                    // S:149-159, M:195-239
     for (int m = 0; m < h->M; m++) {
@@ -275,7 +294,8 @@ extern "C" int mvtm_add_view(mvtm_handle *h, int32_t m, const int64_t *doc_off, 
     CK(h, cudaMalloc(&v.z, (size_t)std::max<long long>(N, 1) * 4));
     CK(h, cudaMalloc(&v.present, pres.size()));
     CK(h, cudaMalloc(&v.order, (size_t)std::max<int>(v.n_items, 1) * 4));
-    CK(h, cudaMalloc(&v.nwk, ((size_t)v.V + 1) * Kp * 4));
+    // + KS ints of tail padding: the DIRECT kernel reads KS (>= Kp) ints per row, whatever follows the row weighs 0
+    CK(h, cudaMalloc(&v.nwk, (((size_t)v.V + 1) * Kp + (size_t)h->KS) * 4));
     v.nk = v.nwk + (size_t)v.V * Kp;
     CK(h, cudaMalloc(&v.nk_snap, Kp * 4));
     CK(h, cudaMalloc(&v.ga_tree, Kp * 4));
@@ -518,7 +538,7 @@ static int ensure_oc_scratch(mvtm_handle *h, size_t doc_slots)
     return MVTM_OK;
 }
 
-struct LaunchCfg { int R, W, grid, oc_smem; size_t smem; };
+struct LaunchCfg { int R, W, grid, oc_smem; size_t smem; bool direct; };
 
 // Ring depth of view m.  Unless fixed by the caller (mvtm_config.ring_depth / MVTM_RING), the first 2*RING_SAMPLES timed
 // passes of the view alternate R = 1, 2, 1, 2, ... and the depth with the smaller MEDIAN pass time is kept (one sample per depth
@@ -555,25 +575,25 @@ static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
     // pubmed_3v / acm_2v: the extra 4*KS bytes per document cost more resident documents than the faster reads give
     // back, even for the side views (5.7 vs 4.8 ms), so the default keeps it in global memory for every view.
     (void)m;
-    const bool oc_smem = multi && getenv("MVTM_OC_SMEM") && atoi(getenv("MVTM_OC_SMEM")) != 0;
-    R = std::max(1, std::min(R, 8));
+    const bool oc_smem = multi && !h->direct && getenv("MVTM_OC_SMEM") && atoi(getenv("MVTM_OC_SMEM")) != 0;
+    R = h->direct ? 0 : std::max(1, std::min(R, 8));
     const size_t budget = 227 * 1024 - 1024;
     int docs;
     for (;;) {
         docs = (int)((budget - smem_cta_bytes(KS, multi ? h->M : 0)) / smem_doc_bytes(KS, R, multi, oc_smem));
-        if (docs >= NSUB || R == 1) break;
+        if (docs >= NSUB || R <= 1) break;
         R--;
     }
     if (docs < NSUB) FAIL(h, MVTM_ERR_LIMIT, "shared memory cannot hold one warp's state for K=%d", h->K);
     int W = docs / NSUB;
-    W = std::min(W, sweep_max_threads(KS, G, multi) / 32);
+    W = std::min(W, sweep_max_threads(KS, G, multi, h->direct) / 32);
     if (h->cfg_warps > 0) W = std::min(W, h->cfg_warps);
     if (const char *e = getenv("MVTM_WARPS")) W = std::max(1, std::min(W, atoi(e)));
     int grid = h->num_sms;
     if (h->cfg_ctas > 0) grid = std::min(grid, h->cfg_ctas);
     if (const char *e = getenv("MVTM_CTAS")) grid = std::max(1, std::min(grid, atoi(e)));
     if (h->flags & MVTM_FLAG_SINGLE_WARP) { W = 1; grid = 1; }
-    lc.R = R; lc.W = W; lc.grid = grid; lc.oc_smem = oc_smem ? 1 : 0;
+    lc.R = R; lc.W = W; lc.grid = grid; lc.oc_smem = oc_smem ? 1 : 0; lc.direct = h->direct;
     lc.smem = smem_cta_bytes(KS, multi ? h->M : 0) + (size_t)W * NSUB * smem_doc_bytes(KS, R, multi, oc_smem);
     return MVTM_OK;
 }
@@ -587,6 +607,10 @@ static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cud
         kernel<<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
         return cudaGetLastError();
     };
+    if constexpr ((KS == 1024 && G == 16) || (KS == 2048 && G == 32)) {   // = direct_compiled
+        if (lc.direct && !q1) return go(k_sweep_view_direct<KS, G, MULTI>);
+    }
+    if (lc.direct) return cudaErrorInvalidValue;
     return q1 ? go(k_sweep_view<KS, G, MULTI, true>) : go(k_sweep_view<KS, G, MULTI, false>);
 }
 template <int KS, int G, bool MULTI>

@@ -25,6 +25,9 @@
 #include <stdint.h>
 
 #define MVTM_MAXM 8
+#ifndef MVTM_DIRECT_REGS
+#define MVTM_DIRECT_REGS 168         // registers per thread the DIRECT sweep kernels are compiled for (__maxnreg__): 12 warps per SM
+#endif
 
 struct SweepParams {
     int M, K, Kp, m, V;
@@ -534,6 +537,92 @@ __device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa
     return newbucket ? -1 : sel;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// DIRECT mode: the n_wk row of a token lives in REGISTERS (JG 128-bit words per lane, loaded straight from global memory / L2
+// with ld.global.cg one token ahead) instead of a shared-memory ring filled by the TMA engine.  A document then needs only
+// q + n_d in shared memory (6 KS bytes instead of 10 KS), so an SM holds ~1.6x the documents, which is what lets a warp host
+// two (or four) document-views at K = 1024 (K = 512) without running out of warps.  Same arithmetic, same scan order.
+// ------------------------------------------------------------------------------------------------
+template <int JG, int G>
+__device__ __forceinline__ void load_row_regs(int4 (&row)[JG], const int *rowp, int gl)
+{   // .cg: L2 only -- the rows are modified by other SMs' RED atomics during the pass, an L1 copy could be arbitrarily stale.
+    // Chunks beyond the row (KS > Kp) read the following row or the table's tail padding; their q is 0, so they weigh nothing
+    const int4 *p = reinterpret_cast<const int4 *>(rowp) + gl;
+#pragma unroll
+    for (int j = 0; j < JG; j++) row[j] = __ldcg(p + G * j);
+}
+
+template <int JG, int G>
+__device__ __forceinline__ float lane_weights_regs(const int4 (&row)[JG], uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG])
+{   // lane_weights with the row in registers (bit-identical arithmetic)
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < JG; j++) {
+        const int4 r = row[j];
+        const float4 qq = lds_f4(q_gl_sa + 16u * G * j);
+        float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
+        a = fmaf(__int2float_rn(r.y), qq.y, a);
+        a = fmaf(__int2float_rn(r.z), qq.z, a);
+        a = fmaf(__int2float_rn(r.w), qq.w, a);
+        tot += a;
+        cum[j] = tot;
+    }
+    return tot;
+}
+
+// group_select over a register-resident row.  The chunk is found by bisection over the running sums and the row's 128-bit word of
+// that chunk is carried along by selects (registers cannot be indexed); everything else as group_select.
+template <int JG, int G>
+__device__ __forceinline__ int group_select_regs(const int4 (&row)[JG], uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
+{
+    float cum[JG];
+    const float lane_total = lane_weights_regs<JG, G>(row, q_gl_sa, bsq, cum);
+    float incl = lane_total;
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
+    const float total = __shfl_sync(FULL, incl, G - 1, G);
+    float target = u * (total + C);
+    const bool newbucket = (C > 0.f) && (target < C);
+    target -= C;
+    target = fminf(target, next_below(total));
+    const unsigned sh = (unsigned)(lane - gl);
+    const unsigned gmask = (G == 32) ? FULL : ((1u << (G & 31)) - 1u);
+    const unsigned hit = (__ballot_sync(FULL, incl > target) >> sh) & gmask;
+    const int L = __ffs(hit) - 1;
+    const float r = fminf(target - (incl - lane_total), next_below(lane_total));
+    int jsel = 0; float base = 0.f;
+    constexpr int P2 = (JG <= 1) ? 1 : (JG <= 2) ? 2 : (JG <= 4) ? 4 : (JG <= 8) ? 8 : (JG <= 16) ? 16 : 32;
+    float win[P2]; int4 rw[P2];
+#pragma unroll
+    for (int j = 0; j < P2; j++) { win[j] = (j < JG - 1) ? cum[j] : __int_as_float(0x7f800000); rw[j] = row[j < JG ? j : JG - 1]; }
+#pragma unroll
+    for (int half = P2 / 2; half >= 1; half >>= 1) {
+        const float t = win[half - 1];
+        const bool ge = (r >= t);
+        base = ge ? t : base;
+        jsel += ge ? half : 0;
+#pragma unroll
+        for (int j = 0; j + 1 < half; j++) win[j] = ge ? win[half + j] : win[j];
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+            rw[j].x = ge ? rw[half + j].x : rw[j].x; rw[j].y = ge ? rw[half + j].y : rw[j].y;
+            rw[j].z = ge ? rw[half + j].z : rw[j].z; rw[j].w = ge ? rw[half + j].w : rw[j].w;
+        }
+    }
+    const int cidx = gl + G * jsel;
+    const int4 rr = rw[0];
+    const float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
+    const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
+    const float w2 = topic_weight(rr.z, qq.z, beta), w3 = topic_weight(rr.w, qq.w, beta);
+    const float c1 = w0 + w1, c2 = c1 + w2, c3 = c2 + w3;
+    const float r2 = fminf(r - base, next_below(c3));
+    const int e = (r2 >= w0 ? 1 : 0) + (r2 >= c1 ? 1 : 0) + (r2 >= c2 ? 1 : 0);
+    const int mine = 4 * cidx + e;
+    const int sel = __shfl_sync(FULL, mine, L, G);
+    return newbucket ? -1 : sel;
+}
+
 // shared-memory carve-up -------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_cta_bytes(int KS, int M_multi) { return (size_t)KS * 8 + (size_t)KS * 4 + (size_t)M_multi * KS * 4; }
 // per-document area: [q KS*4][n_d KS*2][om 256 + cpar 64 (multi)][mbarriers 128][ring R*KS*4][oc KS*4 (multi, optional)]
@@ -544,6 +633,7 @@ __host__ __device__ constexpr uint32_t doc_off_ring(int KS, bool multi) { return
 __host__ __device__ inline size_t smem_doc_bytes(int KS, int R, bool multi, bool oc_smem = false)
 {
     size_t b = doc_off_ring(KS, multi) + (size_t)R * KS * 4;
+    if (R == 0) b = doc_off_mbar(KS, multi);                      // DIRECT mode: rows in registers, no mbarriers and no ring
     if (multi && oc_smem) b += (size_t)KS * 4;                    // oc in shared memory
     return (b + 127) & ~(size_t)127;
 }
@@ -570,24 +660,29 @@ __device__ __forceinline__ void carve_doc(unsigned char *base, int KS, int R, bo
 // (KS, G, >= 2 views if MULTI) at ring depth 1 -- and ptxas may use 65536 / bound registers per thread: 96 instead of 80 at
 // K = 1024.  With the flat 768-thread bound of round 1 the K = 1024 kernel sat at the 80-register cap and its quality depended on
 // the build (spilled loop-carried values in some, profiles/r2_ab_codegen_variants*.log).
-__host__ __device__ constexpr int sweep_max_threads(int KS, int G, bool multi)
+__host__ __device__ constexpr int sweep_max_threads(int KS, int G, bool multi, bool direct = false)
 {
     const size_t cta = (size_t)KS * 12 + (multi ? (size_t)2 * KS * 4 : 0);
-    const size_t doc = ((size_t)KS * 6u + (multi ? 320u : 0u) + 128u + (size_t)KS * 4 + 127) & ~(size_t)127;      // smem_doc_bytes(KS, 1, multi)
+    const size_t doc = direct ? (((size_t)KS * 6u + (multi ? 320u : 0u) + 127) & ~(size_t)127)                       // smem_doc_bytes(KS, 0, multi)
+                              : (((size_t)KS * 6u + (multi ? 320u : 0u) + 128u + (size_t)KS * 4 + 127) & ~(size_t)127);  // smem_doc_bytes(KS, 1, multi)
     const int docs = (int)((227 * 1024 - 1024 - cta) / doc);
     int W = docs / (32 / G);
+    // DIRECT: the row costs KS/G registers per thread on top of ~100, so the register file (64 K), not shared memory, is the bound
+    const int wreg = direct ? (65536 / 32) / MVTM_DIRECT_REGS : 24;
+    W = W > wreg ? wreg : W;
     W = W > 24 ? 24 : (W < 1 ? 1 : W);
     return 32 * W;
 }
 
-template <int KS, int G, bool MULTI, bool Q1>
-__global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_view(const SweepParams P)
+template <int KS, int G, bool MULTI, bool Q1, bool DIRECT>
+__device__ __forceinline__ void sweep_view_body(const SweepParams &P)
 {
     constexpr int JG = KS / (4 * G), NSUB = 32 / G;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / G, gl = lane % G;
-    const int R = P.R;
+    const int R = DIRECT ? 0 : P.R;               // ring depth (DIRECT: no ring, the row is loaded into registers one token ahead)
+    const int RA = DIRECT ? 1 : P.R;              // how many tokens ahead the row fetch runs
 
     {
         float2 *ginv = reinterpret_cast<float2 *>(smem);
@@ -613,9 +708,11 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
     asm volatile("" : "+r"(cta_sa));                              // opaque: hold the base in a register
     c.ginv_sa = cta_sa;
     const uint32_t dnk_sa = cta_sa + (uint32_t)KS * 8u;
-    if (gl == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
-    for (int k = gl; k < R * KS; k += G) ring[k] = 0;
-    fence_proxy_async();
+    if (!DIRECT) {
+        if (gl == 0) { for (int s = 0; s < R; s++) mbar_init(smem_u32(mbar + s), 1); fence_mbar_init(); }
+        for (int k = gl; k < R * KS; k += G) ring[k] = 0;
+        fence_proxy_async();
+    }
     __syncthreads();
 
     const uint32_t row_bytes = (uint32_t)P.Kp * 4u;
@@ -627,6 +724,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
     const int m = P.m;
     int *zmv = P.zv[m];
     float bsq[JG];
+    int4 row[DIRECT ? JG : 1];                                    // DIRECT: the current token's n_wk row (this lane's chunks)
 
     // Work items are claimed two documents ahead and the next document's offsets and first tokens are loaded while the
     // current one is being sampled, so a new document starts with everything in registers (short documents -- side
@@ -647,7 +745,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
         wcur = (gl < len) ? __ldg(P.word + b + gl) : 0;
         zcur = (gl < len) ? zmv[b + gl] : -1;
         wnext = (G + gl < len) ? __ldg(P.word + b + G + gl) : 0;
-        wahead = (R + gl < len) ? row_word(__ldg(P.word + b + R + gl)) : 0;  // word of the token R positions ahead
+        wahead = (RA + gl < len) ? row_word(__ldg(P.word + b + RA + gl)) : 0;  // word of the token RA positions ahead
     }
     while (item0 < P.n_items) {
         const int maxlen = (NSUB == 1) ? len : __reduce_max_sync(FULL, len);
@@ -665,6 +763,10 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
             if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
         doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, nullptr, true, bsq);
+        if constexpr (DIRECT) {     // row of the document's first token (after the setup: JG 128-bit registers are not worth carrying through it)
+            const int w0 = row_word(__shfl_sync(FULL, wcur, 0, G));
+            if (len > 0) load_row_regs<JG, G>(row, P.nwk + (size_t)w0 * P.Kp, gl);
+        }
         // pipeline stage 2 (d_n has arrived during the setup): next document's extent and first tokens
         const long long b_n = P.doc_off[m][d_n];
         const int len_n = have_n ? (int)(P.doc_off[m][d_n + 1] - b_n) : 0;
@@ -701,17 +803,24 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
                 if (i + 1 == G) otn = ot_nextblk;
                 int wa = __shfl_sync(FULL, wahead, i, G);                      // word of token base+i+R (ring refill)
                 const bool valid = act && (ot != -2);
-                if (act) {
-                    mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
-                    phasebits ^= 1u << slot;
+                int nt;
+                if constexpr (DIRECT) {
+                    nt = group_select_regs<JG, G>(row, q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
+                    // row consumed: fetch the next token's (wahead holds in-vocabulary ids only: see row_word)
+                    if (act && base + i + 1 < len) load_row_regs<JG, G>(row, P.nwk + (size_t)wa * P.Kp, gl);
+                } else {
+                    if (act) {
+                        mbar_wait(mbar_u32 + 8u * slot, (phasebits >> slot) & 1u);
+                        phasebits ^= 1u << slot;
+                    }
+                    __syncwarp();
+                    nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
                 }
-                __syncwarp();
-                int nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
                 if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
                 else nt = ot;
                 __syncwarp();
                 // slot consumed: refill it with the row of token base+i+R
-                if (act && gl == 0 && base + i + R < len) {                  // (wahead holds in-vocabulary ids only: see row_word)
+                if (!DIRECT && act && gl == 0 && base + i + R < len) {       // (wahead holds in-vocabulary ids only: see row_word)
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
@@ -728,28 +837,28 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
                     if (gl == i) znew = nt;
                 }
                 __syncwarp();
-                if (act) slot = (slot + 1 == R) ? 0 : slot + 1;
+                if (!DIRECT && act) slot = (slot + 1 == R) ? 0 : slot + 1;
             }
             if (gl < nblk) {
                 zmv[b + base + gl] = znew;
                 if (P.z_host) P.z_host[b + base + gl] = znew;       // posted write over PCIe, one 4*G-byte run per block
             }
             wcur = wnext;
-            wahead = (base + G + R + gl < len) ? row_word(__ldg(P.word + b + base + G + R + gl)) : 0;
+            wahead = (base + G + RA + gl < len) ? row_word(__ldg(P.word + b + base + G + RA + gl)) : 0;
             zcur = (base + G + gl < len) ? zmv[b + base + G + gl] : -1;
             wnext = (base + 2 * G + gl < len) ? __ldg(P.word + b + base + 2 * G + gl) : 0;
             if (base == 0) {   // pipeline stage 3: the next document's first tokens (its offsets arrived long ago)
                 wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
                 zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
                 wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
-                wahead_n = (R + gl < len_n) ? row_word(__ldg(P.word + b_n + R + gl)) : 0;
+                wahead_n = (RA + gl < len_n) ? row_word(__ldg(P.word + b_n + RA + gl)) : 0;
             }
         }
         if (maxlen == 0) {     // (cannot happen: the work list holds non-empty documents only; keeps the pipeline total)
             wcur_n = (gl < len_n) ? __ldg(P.word + b_n + gl) : 0;
             zcur_n = (gl < len_n) ? zmv[b_n + gl] : -1;
             wnext_n = (G + gl < len_n) ? __ldg(P.word + b_n + G + gl) : 0;
-            wahead_n = (R + gl < len_n) ? row_word(__ldg(P.word + b_n + R + gl)) : 0;
+            wahead_n = (RA + gl < len_n) ? row_word(__ldg(P.word + b_n + RA + gl)) : 0;
         }
         item0 = item_n; d = d_n; b = b_n; len = len_n;
         wcur = wcur_n; zcur = zcur_n; wnext = wnext_n; wahead = wahead_n;
@@ -765,6 +874,17 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
         for (int t = threadIdx.x; t < P.K; t += blockDim.x) { int v = dnk[t]; if (v) atomicAdd(P.nk_live + t, v); }
     }
 }
+
+// entry points: the TMA-ring kernel is bounded by its launch shape (the shared-memory budget decides the warps), the DIRECT kernel
+// by an explicit register count (ptxas rounds a launch bound's thread count up to a multiple of 128 before it derives the
+// register cap, which would leave 13..16-warp shapes with 128 registers and spills in the token loop)
+template <int KS, int G, bool MULTI, bool Q1>
+__global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_view(const SweepParams P)
+{ sweep_view_body<KS, G, MULTI, Q1, false>(P); }
+
+template <int KS, int G, bool MULTI>
+__global__ void __maxnreg__(MVTM_DIRECT_REGS) k_sweep_view_direct(const SweepParams P)
+{ sweep_view_body<KS, G, MULTI, false, true>(P); }
 
 // ------------------------------------------------------------------------------------------------
 // parity probe: conditional of one token on frozen counts, same device functions as the sweep.  One warp; every lane

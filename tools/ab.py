@@ -1,4 +1,4 @@
-"""A/B two builds of libmvtm.so on the same box: python tools/ab.py libA.so libB.so [workload[:docs] ...]
+"""A/B two builds of libmvtm.so on the same box: python tools/ab.py libA.so[@ENV=VAL,...] libB.so [workload[:docs] ...]
 Each (library, workload) runs in its own process; prints the mean device ms per view pass of sweeps 5..12."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,9 @@ _so = ctypes.CDLL(L.SO_PATH)          # an older build may lack entry points add
 L.SIGNATURES = {k: v for k, v in L.SIGNATURES.items() if hasattr(_so, k)}
 from mvtopicmodel_b200 import Engine, corpus
 wl, docs = sys.argv[2], (int(sys.argv[3]) if sys.argv[3] != "0" else None)
-K, Vs, views = corpus.generate(wl, docs=docs)
+if wl == "uniform_k1000": K, Vs, views = corpus.generate_uniform(docs or 100_000, 1000, 400_000, 200)     # HBM-bound: no word reuse
+elif wl == "acmtext": K, Vs, views = corpus.generate(dict(D=docs or 200_000, K=1000, views=[(100_000, 120, 0.5, 1.0, 1024)]))   # single view, K = 1000
+else: K, Vs, views = corpus.generate(wl, docs=docs)
 e = Engine(K, Vs, views, seed=1); e.init_assignments()
 acc = [0.0] * len(views); n = 0
 for it in range(1, 13):
@@ -23,11 +25,15 @@ assert e.check_invariants() == 0
 tok = sum(e.ntok)
 print("%%s %%s ms/view %%s  total %%.3f ms  %%.3f Gtok/s" %% (os.path.basename(sys.argv[1]), wl, [round(a / n, 3) for a in acc], sum(acc) / n, tok / (sum(acc) / n) / 1e6))
 ''' % ROOT
-libs = [a for a in sys.argv[1:] if a.endswith(".so")]
-wls = [a for a in sys.argv[1:] if not a.endswith(".so")] or ["lda_100k"]
+libs = [a for a in sys.argv[1:] if ".so" in a]
+wls = [a for a in sys.argv[1:] if ".so" not in a] or ["lda_100k"]
 for wl in wls:
     name, _, docs = wl.partition(":")
-    for rep in range(2):
+    for rep in range(int(os.environ.get("AB_REPS", "2"))):
         for lib in libs:
-            out = subprocess.run([sys.executable, "-c", CHILD, os.path.abspath(lib), name, docs or "0"], capture_output=True, text=True)
-            print(out.stdout.strip() or out.stderr[-400:], flush=True)
+            path, _, envs = lib.partition("@")
+            env = dict(os.environ)
+            for kv in filter(None, envs.split(",")):
+                k, _, v = kv.partition("="); env[k] = v
+            out = subprocess.run([sys.executable, "-c", CHILD, os.path.abspath(path), name, docs or "0"], capture_output=True, text=True, env=env)
+            print((envs + " " if envs else "") + (out.stdout.strip() or out.stderr[-400:]), flush=True)
