@@ -129,6 +129,10 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t a)
 { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u16(uint32_t a, unsigned v)
 { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{ float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ unsigned lds_u32(uint32_t a)
+{ unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v)
 { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
@@ -180,6 +184,24 @@ __device__ __forceinline__ float prior_other(const SweepParams &P, const DocCtx 
     return pri;
 }
 
+// prior_other for the token loop: same sums, addressed from the two .shared bases held in registers (c.sa: cpar at +6 KS + 256;
+// c.ginv_sa: gaf at +12 KS) -- through the generic pointers ptxas rebuilds both addresses from %tid on every call (~25 instructions)
+template <int KS, bool MULTI>
+__device__ __forceinline__ float prior_other_sa(const SweepParams &P, const DocCtx &c, int t)
+{
+    float pri = 0.f;
+    if (MULTI) {
+        const uint32_t cp = c.sa + (uint32_t)KS * 6u + 256u, ga = c.ginv_sa + (uint32_t)KS * 12u + 4u * (uint32_t)t;
+        if (P.M == 2) return lds_f32(cp + 4u * (uint32_t)(1 - P.m)) * lds_f32(ga + (uint32_t)(1 - P.m) * (KS * 4u));
+        if (P.M == 3) {
+            const int i1 = (P.m == 0) ? 1 : 0, i2 = (P.m == 2) ? 1 : 2;
+            return fmaf(lds_f32(cp + 4u * (uint32_t)i2), lds_f32(ga + (uint32_t)i2 * (KS * 4u)), lds_f32(cp + 4u * (uint32_t)i1) * lds_f32(ga + (uint32_t)i1 * (KS * 4u)));
+        }
+        for (int i = 0; i < P.M; i++) pri = fmaf(lds_f32(cp + 4u * (uint32_t)i), lds_f32(ga + (uint32_t)i * (KS * 4u)), pri);
+    }
+    return pri;
+}
+
 // n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over the chunk).  Executed by the lane that
 // owns topic t (gl == (t >> 2) % G), W:434-471 / W:557-584.
 // Q1 (reference-exact dense index, MVTM_FLAG_Q1_COMPAT): bit 15 of n_d[t] flags "t is not in S for the rest of the sweep".  The
@@ -196,7 +218,7 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
     const unsigned before = Q1 ? (raw & 0x7fffu) : raw;
     const unsigned ndv_i = (unsigned)((int)before + dl);
     bool oth = false;
-    if (MULTI) oth = (c.om[t >> 5] >> (t & 31)) & 1u;
+    if (MULTI) oth = (lds_u32(c.sa + (uint32_t)KS * 6u + 4u * (uint32_t)(t >> 5)) >> (t & 31)) & 1u;      // c.om[t >> 5]
     if (Q1) {
         const bool leaves = (dl < 0) && (ndv_i == 0u) && !oth;
         const bool gained_absent = (dl > 0) && (before == 0u) && !oth;
@@ -211,7 +233,7 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
     if (MULTI) {
         // branch-light on purpose: the lane groups of a warp hold different documents and would serialise on branches
         inS = ((ndv_i > 0u) || oth) && !(Q1 && flag);
-        pri = prior_other<MULTI>(P, c, t);
+        pri = prior_other_sa<KS, MULTI>(P, c, t);
         if (oth) ocv = c.oc[t];
     }
     sts_f32(c.sa + 4u * (uint32_t)t, q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t)));
@@ -818,7 +840,7 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
                 }
                 if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
                 else nt = ot;
-                __syncwarp();
+                if (!DIRECT) __syncwarp();
                 // slot consumed: refill it with the row of token base+i+R
                 if (!DIRECT && act && gl == 0 && base + i + R < len) {       // (wahead holds in-vocabulary ids only: see row_word)
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
@@ -836,7 +858,9 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
                     n_changed += (nt != ot);
                     if (gl == i) znew = nt;
                 }
-                __syncwarp();
+                // (DIRECT: nothing in the token loop passes through shared memory between lanes -- q, n_d and the row are private to
+                // their owner lane -- and the full-mask shuffles at the top of the next token reconverge the warp)
+                if (!DIRECT) __syncwarp();
                 if (!DIRECT && act) slot = (slot + 1 == R) ? 0 : slot + 1;
             }
             if (gl < nblk) {
