@@ -48,6 +48,11 @@ typedef enum {
                                       reference calls at W:333, instead of the true Beta(p_a, 1): for p_a > 1 that is a truncated normal
                                       N(1, 0.25/(p_a - 1)) on [0, 1] (quirk Q5: its rejection test compares against NaN).  Same law for
                                       p_a <= 1. */
+#define MVTM_FLAG_TMA_RING   16u   /* stage n_wk rows through the shared-memory ring filled by the TMA engine for every K.  Default (flag clear):
+                                      for K in (768, 1024] and (1536, 2048] the DIRECT kernel keeps the row of a token in registers
+                                      (ld.global.cg one token ahead), which leaves room for more documents per SM -- measured faster
+                                      there; compat mode (Q1) always uses the ring.  Same arithmetic and scan order for a given
+                                      lane-group size, so frozen sweeps of the two kernels agree token for token. */
 #define MVTM_FLAG_REFERENCE_COMPAT (MVTM_FLAG_Q1_COMPAT | MVTM_FLAG_BETA_MALLET)   /* both: the reference's behaviour, quirks included */
 
 typedef struct mvtm_config {
@@ -61,7 +66,7 @@ typedef struct mvtm_config {
     int64_t doc_id_base;             /* global id of local document d is doc_id_base + d * doc_id_stride;     */
     int64_t doc_id_stride;           /*   it keys the RNG, so a sharded run draws what the unsharded one does */
     int32_t warps_per_cta;           /* 0 = auto                                                             */
-    int32_t ring_depth;              /* n_wk rows in flight per warp (TMA ring), 0 = auto                    */
+    int32_t ring_depth;              /* n_wk rows in flight per warp (TMA ring kernel only), 0 = auto        */
     int32_t max_ctas;                /* 0 = one persistent CTA per SM; smaller values bound the number of documents
                                         sampled concurrently (the asynchrony the reference bounds by numThreads, M:1036) */
 } mvtm_config;
@@ -73,7 +78,7 @@ typedef struct mvtm_sweep_stats {
     double ms_total;                 /* device time of the last sweep, CUDA events                           */
     double ms_view[MVTM_MAX_VIEWS];  /* device time of each view's sampling kernel                           */
     int32_t kernel_launches;         /* kernels launched by the last sweep                                   */
-    int32_t ring_depth[MVTM_MAX_VIEWS];  /* TMA ring depth each view's last pass ran with                       */
+    int32_t ring_depth[MVTM_MAX_VIEWS];  /* TMA ring depth each view's last pass ran with; 0 = DIRECT kernel     */
     int32_t ring_locked[MVTM_MAX_VIEWS]; /* the depth the autotune settled on (0 = still sampling; = the configured depth when fixed) */
 } mvtm_sweep_stats;
 

@@ -121,7 +121,7 @@ static bool direct_compiled(int KS, int G) { return (KS == 1024 && G == 16) || (
 static bool pick_direct(int KS, bool multi, unsigned flags)
 {
     (void)multi;
-    if (flags & MVTM_FLAG_Q1_COMPAT) return false;
+    if (flags & (MVTM_FLAG_Q1_COMPAT | MVTM_FLAG_TMA_RING)) return false;
     bool d = (KS == 1024 || KS == 2048);
     if (const char *e = getenv("MVTM_DIRECT")) d = atoi(e) != 0;
     return d;
@@ -143,7 +143,8 @@ static int pick_G(int KS, bool multi, bool direct = false)
 // ------------------------------------------------------------------------------------------------
 extern "C" const char *mvtm_build_info(void)
 {
-    return "mvtm-b200 sm_100a; k_sweep_view<KS in {128..2048}, lanes per document G in {8,16,32}, single|multi view>; TMA 1-D bulk ring; Philox4x32-10";
+    return "mvtm-b200 sm_100a; k_sweep_view<KS in {128..2048}, lanes per document G in {8,16,32}, single|multi view>: TMA 1-D bulk ring; "
+           "k_sweep_view_direct<KS in {1024,2048}>: rows in registers; Philox4x32-10";
 }
 
 extern "C" const char *mvtm_last_error(const mvtm_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }

@@ -202,16 +202,15 @@ __device__ __forceinline__ float prior_other_sa(const SweepParams &P, const DocC
     return pri;
 }
 
-// n_d[t] += dl, then recompute q[t] and the owner lane's beta * (sum of q over the chunk).  Executed by the lane that
+// n_d[t] += dl, then recompute q[t].  Executed by the lane that
 // owns topic t (gl == (t >> 2) % G), W:434-471 / W:557-584.
 // Q1 (reference-exact dense index, MVTM_FLAG_Q1_COMPAT): bit 15 of n_d[t] flags "t is not in S for the rest of the sweep".  The
 // reference removes a topic from S when no view of the document holds it any more (W:441-468) and never inserts one (W:563-584 is
 // dead code), so S = {held and not flagged} with the flag set when the topic leaves or is gained while absent
 // (tests/test_reference_vectors.py::test_flag_rule_equals_reference_dense_index).  A flagged topic keeps only its tree mass.
 template <int KS, int G, bool MULTI, bool Q1>
-__device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl, int gl, float (&bsq)[KS / (4 * G)])
+__device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &c, int t, int dl)
 {
-    constexpr int JG = KS / (4 * G);
     const uint32_t nd_a = c.sa + (uint32_t)KS * 4u + 2u * (uint32_t)t;
     const unsigned raw = lds_u16(nd_a);
     unsigned flag = Q1 ? (raw >> 15) : 0u;
@@ -237,19 +236,13 @@ __device__ __forceinline__ void apply_count_delta(const SweepParams &P, DocCtx &
         if (oth) ocv = c.oc[t];
     }
     sts_f32(c.sa + 4u * (uint32_t)t, q_value<MULTI>(ndv, inS, ocv, pri, c.coefm, c.pmm, lds_f2(c.ginv_sa + 8u * (uint32_t)t)));
-    constexpr int LG = ilog2(G);
-    const int j = t >> (2 + LG);
-    const float4 qq = lds_f4(c.sa + 16u * (uint32_t)(gl + G * j));      // own store is visible in program order
-    const float v = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
-#pragma unroll
-    for (int jj = 0; jj < JG; jj++) if (jj == j) bsq[jj] = v;
 }
 
 // one step: n_d[tinc]++ and n_d[tdec]-- (either may be -1 = none) by their owner lanes, in parallel when the owners
 // differ (a second pass runs only when one lane owns both).  No warp-level synchronisation inside: the lane groups of a
 // warp may diverge here.
 template <int KS, int G, bool MULTI, bool Q1>
-__device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int tinc, int tdec, int gl, float (&bsq)[KS / (4 * G)])
+__device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int tinc, int tdec, int gl)
 {
     if (tinc == tdec) return;                                   // same topic: the two changes cancel
     const int own_i = tinc >= 0 ? ((tinc >> 2) & (G - 1)) : -1, own_d = tdec >= 0 ? ((tdec >> 2) & (G - 1)) : -2;
@@ -257,7 +250,7 @@ __device__ __forceinline__ void apply_pair(const SweepParams &P, DocCtx &c, int 
     if (gl == own_i) { t = tinc; dl = 1; if (own_i == own_d) t2 = tdec; } else if (gl == own_d) { t = tdec; dl = -1; }
 #pragma unroll 1
     while (t >= 0) {
-        apply_count_delta<KS, G, MULTI, Q1>(P, c, t, dl, gl, bsq);
+        apply_count_delta<KS, G, MULTI, Q1>(P, c, t, dl);
         t = t2; t2 = -1; dl = -1;
     }
 }
@@ -334,7 +327,7 @@ __device__ __noinline__ float draw_p_law(const SweepParams &P, int i, uint32_t g
 __device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gdoc, const double *p_override)
 { return P.beta_mallet ? draw_p_law<true>(P, i, gdoc, p_override) : draw_p_law<false>(P, i, gdoc, p_override); }
 
-// Build n_d, (MULTI: oc/om/cpar), q and beta*sum(q) for document d of view P.m (len == 0: nothing to do, but every
+// Build n_d, (MULTI: oc/om/cpar) and q for document d of view P.m (len == 0: nothing to do, but every
 // lane still walks the same __syncwarp sequence -- the groups of a warp hold different documents).
 //
 // Cost is O(KS/G) cheap vector work + O(tokens of the document, all views): q starts as the document-independent vector
@@ -345,7 +338,7 @@ __device__ __forceinline__ float draw_p(const SweepParams &P, int i, uint32_t gd
 // K = 1000 -- more than sampling the 6-12 tokens of a side view.)
 template <int KS, int G, bool MULTI, bool Q1>
 __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d, int len, int gl, const double *p_override,
-                                          bool skip_first, float (&bsq)[KS / (4 * G)])
+                                          bool skip_first)
 {
     constexpr int JG = KS / (4 * G);
     const int m = P.m;
@@ -467,32 +460,40 @@ __device__ __forceinline__ void doc_setup(const SweepParams &P, DocCtx &c, int d
         }
     }
     __syncwarp();
-#pragma unroll
-    for (int j = 0; j < JG; j++) {
-        const float4 qq = reinterpret_cast<const float4 *>(c.q)[gl + G * j];
-        bsq[j] = P.beta * ((qq.x + qq.y) + (qq.z + qq.w));
-    }
-    __syncwarp();
 }
 
 // weight of one topic: (n + beta) * q evaluated as n*q + beta*q
 __device__ __forceinline__ float topic_weight(int n, float q, float beta) { return fmaf(__int2float_rn(n), q, beta * q); }
 
-// per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, each topic weighted (n + beta) * q,
-// evaluated as beta*sum(q) (registers, bsq) + sum n*q.  Returns the lane total (= cum[JG-1]).
+// packed fp32 pairs (sm_100: add/mul/fma.f32x2 -- one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b)
+{ unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b))); return *reinterpret_cast<float2 *>(&d); }
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b)
+{ unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b))); return *reinterpret_cast<float2 *>(&d); }
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c)
+{ unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)), "l"(*reinterpret_cast<unsigned long long *>(&c))); return *reinterpret_cast<float2 *>(&d); }
+
+// weight of one 4-topic chunk, sum_e (n_e + beta) * q_e, evaluated as beta * (q0 + q2, q1 + q3) + n * q on packed pairs: 4 packed
+// instructions + 1 add for 4 topics, and nothing to maintain per chunk when a q changes (the first kernels kept beta * sum(q) of every
+// chunk in registers: 2 JG instructions of select chain per n_d update, JG registers)
+__device__ __forceinline__ float chunk_weight(const int4 r, const float4 qq, const float2 bb)
+{
+    float2 acc = f2_mul(f2_add(make_float2(qq.x, qq.y), make_float2(qq.z, qq.w)), bb);
+    acc = f2_fma(make_float2(__int2float_rn(r.x), __int2float_rn(r.y)), make_float2(qq.x, qq.y), acc);
+    acc = f2_fma(make_float2(__int2float_rn(r.z), __int2float_rn(r.w)), make_float2(qq.z, qq.w), acc);
+    return acc.x + acc.y;
+}
+
+// per-lane weights of one row: cum[j] = running sum over the lane's chunks 0..j, each topic weighted (n + beta) * q.
+// Returns the lane total (= cum[JG-1]).
 template <int JG, int G>
-__device__ __forceinline__ float lane_weights(uint32_t row_gl_sa, uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG])
+__device__ __forceinline__ float lane_weights(uint32_t row_gl_sa, uint32_t q_gl_sa, float beta, float (&cum)[JG])
 {   // row_gl_sa / q_gl_sa: .shared address of the lane's first chunk (base + 16*gl); chunk j sits 16*G*j bytes further
     float tot = 0.f;
+    const float2 bb = make_float2(beta, beta);
 #pragma unroll
     for (int j = 0; j < JG; j++) {
-        const int4 r = lds_i4(row_gl_sa + 16u * G * j);
-        const float4 qq = lds_f4(q_gl_sa + 16u * G * j);
-        float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
-        a = fmaf(__int2float_rn(r.y), qq.y, a);
-        a = fmaf(__int2float_rn(r.z), qq.z, a);
-        a = fmaf(__int2float_rn(r.w), qq.w, a);
-        tot += a;
+        tot += chunk_weight(lds_i4(row_gl_sa + 16u * G * j), lds_f4(q_gl_sa + 16u * G * j), bb);
         cum[j] = tot;
     }
     return tot;
@@ -505,10 +506,10 @@ __device__ __forceinline__ float next_below(float x) { return __int_as_float(__f
 // exceeds target = u*(total + C) - C; -1 if the draw fell into the new-topic bucket (W:522).  Every lane of the warp
 // must call it (full-mask shuffles); groups whose document is exhausted compute on stale data and ignore the result.
 template <int JG, int G>
-__device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
+__device__ __forceinline__ int group_select(uint32_t row_gl_sa, uint32_t q_gl_sa, int lane, int gl, float beta, float u, float C)
 {
     float cum[JG];
-    const float lane_total = lane_weights<JG, G>(row_gl_sa, q_gl_sa, bsq, cum);
+    const float lane_total = lane_weights<JG, G>(row_gl_sa, q_gl_sa, beta, cum);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
@@ -576,18 +577,13 @@ __device__ __forceinline__ void load_row_regs(int4 (&row)[JG], const int *rowp, 
 }
 
 template <int JG, int G>
-__device__ __forceinline__ float lane_weights_regs(const int4 (&row)[JG], uint32_t q_gl_sa, const float (&bsq)[JG], float (&cum)[JG])
+__device__ __forceinline__ float lane_weights_regs(const int4 (&row)[JG], uint32_t q_gl_sa, float beta, float (&cum)[JG])
 {   // lane_weights with the row in registers (bit-identical arithmetic)
     float tot = 0.f;
+    const float2 bb = make_float2(beta, beta);
 #pragma unroll
     for (int j = 0; j < JG; j++) {
-        const int4 r = row[j];
-        const float4 qq = lds_f4(q_gl_sa + 16u * G * j);
-        float a = fmaf(__int2float_rn(r.x), qq.x, bsq[j]);
-        a = fmaf(__int2float_rn(r.y), qq.y, a);
-        a = fmaf(__int2float_rn(r.z), qq.z, a);
-        a = fmaf(__int2float_rn(r.w), qq.w, a);
-        tot += a;
+        tot += chunk_weight(row[j], lds_f4(q_gl_sa + 16u * G * j), bb);
         cum[j] = tot;
     }
     return tot;
@@ -596,10 +592,10 @@ __device__ __forceinline__ float lane_weights_regs(const int4 (&row)[JG], uint32
 // group_select over a register-resident row.  The chunk is found by bisection over the running sums and the row's 128-bit word of
 // that chunk is carried along by selects (registers cannot be indexed); everything else as group_select.
 template <int JG, int G>
-__device__ __forceinline__ int group_select_regs(const int4 (&row)[JG], uint32_t q_gl_sa, int lane, int gl, float beta, const float (&bsq)[JG], float u, float C)
+__device__ __forceinline__ int group_select_regs(const int4 (&row)[JG], uint32_t q_gl_sa, int lane, int gl, float beta, float u, float C)
 {
     float cum[JG];
-    const float lane_total = lane_weights_regs<JG, G>(row, q_gl_sa, bsq, cum);
+    const float lane_total = lane_weights_regs<JG, G>(row, q_gl_sa, beta, cum);
     float incl = lane_total;
 #pragma unroll
     for (int off = 1; off < G; off <<= 1) { float v = __shfl_up_sync(FULL, incl, off, G); if (gl >= off) incl += v; }
@@ -633,6 +629,8 @@ __device__ __forceinline__ int group_select_regs(const int4 (&row)[JG], uint32_t
         }
     }
     const int cidx = gl + G * jsel;
+    // (a branch on the selected lane's chunk index -- a switch over the JG registers, <= 32/G targets per warp -- instead of the
+    // 4 (P2 - 1) selects was measured 5 % slower: the taken branches cost more than the selects they save)
     const int4 rr = rw[0];
     const float4 qq = lds_f4(q_gl_sa + 16u * G * (uint32_t)jsel);
     const float w0 = topic_weight(rr.x, qq.x, beta), w1 = topic_weight(rr.y, qq.y, beta);
@@ -745,7 +743,6 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
     unsigned n_tok = 0, n_changed = 0, n_new = 0;                 // per lane group: far below 2^32 per launch
     const int m = P.m;
     int *zmv = P.zv[m];
-    float bsq[JG];
     int4 row[DIRECT ? JG : 1];                                    // DIRECT: the current token's n_wk row (this lane's chunks)
 
     // Work items are claimed two documents ahead and the next document's offsets and first tokens are loaded while the
@@ -784,7 +781,7 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
             if ((unsigned)w >= (unsigned)P.V) w = 0;
             if (gl == 0 && i < len) tma_row_load(ring_u32 + (uint32_t)i * KS * 4u, P.nwk + (size_t)w * P.Kp, row_bytes, mbar_u32 + 8u * i);
         }
-        doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, nullptr, true, bsq);
+        doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, nullptr, true);
         if constexpr (DIRECT) {     // row of the document's first token (after the setup: JG 128-bit registers are not worth carrying through it)
             const int w0 = row_word(__shfl_sync(FULL, wcur, 0, G));
             if (len > 0) load_row_regs<JG, G>(row, P.nwk + (size_t)w0 * P.Kp, gl);
@@ -827,7 +824,7 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
                 const bool valid = act && (ot != -2);
                 int nt;
                 if constexpr (DIRECT) {
-                    nt = group_select_regs<JG, G>(row, q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
+                    nt = group_select_regs<JG, G>(row, q_gl_sa, lane, gl, P.beta, u, c.C);
                     // row consumed: fetch the next token's (wahead holds in-vocabulary ids only: see row_word)
                     if (act && base + i + 1 < len) load_row_regs<JG, G>(row, P.nwk + (size_t)wa * P.Kp, gl);
                 } else {
@@ -836,7 +833,7 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
                         phasebits ^= 1u << slot;
                     }
                     __syncwarp();
-                    nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, bsq, u, c.C);
+                    nt = group_select<JG, G>(q_gl_sa + doc_off_ring(KS, MULTI) + (uint32_t)slot * (KS * 4u), q_gl_sa, lane, gl, P.beta, u, c.C);
                 }
                 if (valid) { if (nt < 0) { nt = P.first_inactive; n_new++; } }   // W:522-526
                 else nt = ot;
@@ -846,7 +843,7 @@ __device__ __forceinline__ void sweep_view_body(const SweepParams &P)
                     tma_row_load(ring_u32 + (uint32_t)slot * KS * 4u, P.nwk + (size_t)wa * P.Kp, row_bytes, mbar_u32 + 8u * slot);
                 }
                 // this token joins its new topic (W:557-560) while the next token of the block leaves its old one
-                apply_pair<KS, G, MULTI, Q1>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl, bsq);
+                apply_pair<KS, G, MULTI, Q1>(P, c, valid ? nt : -1, (act && (i + 1 < nblk || i + 1 == G) && otn >= 0) ? otn : -1, gl);
                 if (valid) {
                     if (nt != ot && P.update_global) {                       // U:197-218
                         const int tsel = (gl & 1) ? ot : nt, v = (gl & 1) ? -1 : 1;
@@ -937,16 +934,15 @@ __global__ void __launch_bounds__(32, 1) k_cond_probe(const SweepParams P, int d
     c.ginv_sa = smem_u32(smem);
     if (MULTI) c.oc = P.oc_scratch + (size_t)sub * P.Kp;
     __syncwarp();
-    float bsq[JG];
     const long long b = P.doc_off[P.m][d];
     const int len = (int)(P.doc_off[P.m][d + 1] - b);
-    doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, p_row, false, bsq);
+    doc_setup<KS, G, MULTI, Q1>(P, c, d, len, gl, p_row, false);
     const int w = P.word[b + pos], ot = P.zv[P.m][b + pos];
-    apply_pair<KS, G, MULTI, Q1>(P, c, -1, ot, gl, bsq);
+    apply_pair<KS, G, MULTI, Q1>(P, c, -1, ot, gl);
     for (int t = gl; t < KS; t += G) ring[t] = (t < P.Kp) ? P.nwk[(size_t)w * P.Kp + t] : 0;
     __syncwarp();
     float cum[JG];
-    float lt = lane_weights<JG, G>(smem_u32(ring) + 16u * (uint32_t)gl, c.sa + 16u * (uint32_t)gl, bsq, cum);
+    float lt = lane_weights<JG, G>(smem_u32(ring) + 16u * (uint32_t)gl, c.sa + 16u * (uint32_t)gl, P.beta, cum);
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) lt += __shfl_xor_sync(FULL, lt, off, G);
     const float total = lt + c.C;
