@@ -236,9 +236,16 @@ int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size
  *       communicator.  Returns when the PASSES are done (mvtm_stats valid); the exchanges are ordered on the device before
  *       anything that touches the view again.  Inactive topics sampled by a sweep are activated (U:263-270) at the start of
  *       the next one, on the global counts.  mvtm_comm_drain waits for everything.
- *   mvtm_sweep_host_dist(h, it, z) the stateless step through HOST buffers on every rank: upload + local recount, ONE all-reduce
- *       per view (overlapped with the next view's upload), the passes, new z written to the caller's arrays.  No exchange
- *       follows (the next stateless step recounts anyway): call mvtm_sync_counts(h, 1) before going back to mvtm_sweep_dist.
+ *   mvtm_sweep_host_dist(h, it, z) the step of a host whose only state are its assignment arrays (the reference's topicSequence),
+ *       on every rank: assignments in, assignments out.  The first call -- and any call after something else wrote the handle's
+ *       assignments or tables, or after the caller changed its arrays -- uploads, recounts locally, makes the counts global with
+ *       ONE all-reduce per view (overlapped with the next view's upload) and takes the exchange snapshot.  Otherwise the upload
+ *       is only COMPARED with the resident assignments (one 4-byte all-reduce tells every rank whether all shards are intact)
+ *       and the resident global counts are used as they are; a difference on any rank sends all ranks down the recount path, so
+ *       the result never depends on which path ran.  Then the passes with their overlapped exchanges as in mvtm_sweep_dist; new z
+ *       is written to the caller's arrays (by the sweep kernel itself when they are pinned + mapped).  The replicas hold global
+ *       counts afterwards (mvtm_sweep_dist / mvtm_loglik_dist may follow).  mvtm_comm_last_host_step tells which path ran;
+ *       MVTM_HOST_COMPARE=0 in the environment forces the recount path.
  *   mvtm_loglik_dist(h, ll, q)     modelLogLikelihood of the whole corpus (document parts summed over ranks).
  * With a communicator and no mvtm_set_stat_reducer callback, mvtm_optimize_hyper reduces its statistics over the communicator
  * itself, so every rank installs identical hyper-parameters. */
@@ -251,6 +258,7 @@ int mvtm_sync_counts(mvtm_handle *h, int32_t rebuild_from_assignments);
 int mvtm_sweep_dist(mvtm_handle *h, int32_t iteration);
 int mvtm_comm_drain(mvtm_handle *h);
 int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout);
+int mvtm_comm_last_host_step(mvtm_handle *h, int32_t *resident_counts_used);
 int mvtm_loglik_dist(mvtm_handle *h, double *ll_out, int32_t quirk_len2);
 
 /* Scan layout of the sampler (for order-exact checkers): a document-view is sampled by `lanes_per_doc` lanes (8, 16 or

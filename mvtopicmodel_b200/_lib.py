@@ -78,6 +78,7 @@ SIGNATURES = {
     "mvtm_sweep_dist": (_i32, [_vp, _i32]),
     "mvtm_comm_drain": (_i32, [_vp]),
     "mvtm_sweep_host_dist": (_i32, [_vp, _i32, C.POINTER(_vp)]),
+    "mvtm_comm_last_host_step": (_i32, [_vp, C.POINTER(_i32)]),
     "mvtm_loglik_dist": (_i32, [_vp, _vp, _i32]),
     "mvtm_scan_layout": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "mvtm_optimize_hyper": (_i32, [_vp, _i32, C.c_uint32]),

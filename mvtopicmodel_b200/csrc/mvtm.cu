@@ -31,6 +31,8 @@ struct ViewDev {
     int *nwk = nullptr, *nk = nullptr, *nk_snap = nullptr;
     int *order = nullptr;
     int *z_mirror = nullptr;                        // device alias of a caller-owned pinned array that mirrors z (mvtm_set_host_mirror)
+    int *z_host_once = nullptr;                     // the same for the passes of ONE call (mvtm_sweep_host_dist), wins over z_mirror
+    int *z_stage = nullptr;                         // mvtm_sweep_host_dist: the uploaded assignments before they are compared with z
     std::vector<long long> chunk_tok_off;           // mvtm_sweep_host: HOST_CHUNKS + 1 token offsets of contiguous document ranges
     float *ga_tree = nullptr, *ga_full = nullptr, *ga_one = nullptr;   // ga_one: all ones, the inferencer's bare trees (Q13)
     int *snap_nwk = nullptr, *snap_nk = nullptr;    // multi-GPU delta snapshots
@@ -47,6 +49,7 @@ struct CommState;                                   // NCCL communicators and ex
 struct mvtm_handle {
     CommState *comm = nullptr;                      // multi-GPU inside the library (mvtm_comm_init)
     int K = 0, M = 0, Kp = 0, J = 0, KS = 0, G = 32;
+    unsigned long long mut_epoch = 1;               // bumped by everything that writes assignments or count tables on the device
     bool direct = false;                            // DIRECT sweep kernel: n_wk rows in registers instead of the TMA ring (mvtm_kernels.cuh)
     long long D = 0;
     int device = 0, num_sms = 0;
@@ -207,7 +210,7 @@ static void free_view(ViewDev &v)
 {
     // nk / snap_nk are row V of the nwk / snap_nwk allocations (one all-reduce covers table and totals)
     cudaFree(v.doc_off); cudaFree(v.word); cudaFree(v.z); cudaFree(v.present); cudaFree(v.nwk);
-    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk);
+    cudaFree(v.nk_snap); cudaFree(v.order); cudaFree(v.ga_tree); cudaFree(v.ga_full); cudaFree(v.ga_one); cudaFree(v.snap_nwk); cudaFree(v.z_stage);
     v = ViewDev();
 }
 
@@ -326,6 +329,7 @@ static int rebuild_counts_view(mvtm_handle *h, int m)
 {
     ViewDev &v = h->v[m];
     const size_t Kp = (size_t)h->Kp;
+    h->mut_epoch++;
     if (int rc = wait_view_ready(h, m)) return rc;
     CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * Kp * 4, h->stream));
     CK(h, cudaMemsetAsync(v.nk, 0, Kp * 4, h->stream));
@@ -380,6 +384,7 @@ extern "C" int mvtm_set_counts(mvtm_handle *h, int32_t m, const int32_t *n_wk, c
     if (m < 0 || m >= h->M || !h->v[m].added || !n_wk || !n_k) FAIL(h, MVTM_ERR_ARG, "mvtm_set_counts: bad argument");
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
+    h->mut_epoch++;
     ViewDev &v = h->v[m];
     for (int t = 0; t < h->K; t++) if (n_k[t] < 0) FAIL(h, MVTM_ERR_CORRUPT, "mvtm_set_counts: negative n_k[%d]", t);
     CK(h, cudaMemsetAsync(v.nwk, 0, (size_t)v.V * h->Kp * 4, h->stream));
@@ -396,6 +401,7 @@ extern "C" int mvtm_init_assignments_from_counts(mvtm_handle *h)
     if (int rc = require_views(h, "mvtm_init_assignments_from_counts")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
+    h->mut_epoch++;
     const int K = h->K;
     int P2 = 1; while (P2 * 2 <= 2 * K - 1) P2 *= 2;                  // 2^floor(log2(2K-1)): first index of the deepest tree level
     const int rot = P2 - K;
@@ -641,6 +647,7 @@ static cudaError_t launch_probe_t(const SweepParams &P, int d, int pos, const do
 static cudaError_t launch_sweep(mvtm_handle *h, const SweepParams &P, const LaunchCfg &lc)
 {
     cudaError_t e = cudaErrorInvalidValue;
+    h->mut_epoch++;
 #define CALL_SWEEP(KS_, G_, MU_) e = launch_sweep_t<KS_, G_, MU_>(P, lc, h->stream, (h->flags & MVTM_FLAG_Q1_COMPAT) != 0)
     if (h->M > 1) { DISPATCH_KG(h->KS, h->G, true, CALL_SWEEP) } else { DISPATCH_KG(h->KS, h->G, false, CALL_SWEEP) }
 #undef CALL_SWEEP
@@ -712,7 +719,7 @@ static int enqueue_view_pass(mvtm_handle *h, int iteration, int update_global, i
         fill_params(h, m, iteration, update_global, P);
         P.R = lc.R; P.oc_smem = lc.oc_smem;
         h->stats.ring_depth[m] = lc.R;
-        P.z_host = v.z_mirror;
+        P.z_host = v.z_host_once ? v.z_host_once : v.z_mirror;
         CK(h, launch_sweep(h, P, lc));
         (*launches)++;
     }
@@ -1238,6 +1245,7 @@ extern "C" int mvtm_heldout_loglik(mvtm_handle *h, int32_t m, const int64_t *eva
 extern "C" int mvtm_delta_begin(mvtm_handle *h)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (int rc = require_views(h, "mvtm_delta_begin")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
@@ -1255,6 +1263,7 @@ extern "C" int mvtm_delta_begin(mvtm_handle *h)
 extern "C" int mvtm_delta_reset(mvtm_handle *h)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (int rc = require_views(h, "mvtm_delta_reset")) return rc;
     CK(h, cudaSetDevice(h->device));
     if (int rc = wait_all_ready(h)) return rc;
@@ -1272,6 +1281,7 @@ extern "C" int mvtm_delta_reset(mvtm_handle *h)
 extern "C" int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_delta_export: bad view %d", m);
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_export: call mvtm_delta_begin first");
@@ -1292,6 +1302,7 @@ extern "C" int mvtm_delta_export(mvtm_handle *h, int32_t m, void **n_wk_dev, int
 extern "C" int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_dev, int64_t *n_wk_elems, void **n_k_dev, int64_t *n_k_elems)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_buffers: bad view %d", m);
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_buffers: call mvtm_delta_begin first");
@@ -1308,6 +1319,7 @@ extern "C" int mvtm_sum_exchange_buffers(mvtm_handle *h, int32_t m, void **n_wk_
 extern "C" int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world_size)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (m < 0 || m >= h->M || !h->v[m].added || world_size < 1) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_finish: bad argument");
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_finish: call mvtm_delta_begin first");
@@ -1326,6 +1338,7 @@ extern "C" int mvtm_sum_exchange_finish(mvtm_handle *h, int32_t m, int32_t world
 extern "C" int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size, void *stream, int32_t max_ctas)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (m < 0 || m >= h->M || !h->v[m].added || world_size < 1) FAIL(h, MVTM_ERR_ARG, "mvtm_sum_exchange_finish_async: bad argument");
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_sum_exchange_finish_async: call mvtm_delta_begin first");
@@ -1340,6 +1353,7 @@ extern "C" int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t
 extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
 {
     if (!h) return MVTM_ERR_ARG;
+    h->mut_epoch++;
     if (m < 0 || m >= h->M || !h->v[m].added) FAIL(h, MVTM_ERR_ARG, "mvtm_delta_import: bad view %d", m);
     ViewDev &v = h->v[m];
     if (!v.snap_nwk) FAIL(h, MVTM_ERR_STATE, "mvtm_delta_import: call mvtm_delta_begin first");

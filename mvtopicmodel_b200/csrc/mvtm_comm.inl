@@ -44,6 +44,9 @@ struct CommState {
     int rank = 0, world = 1, hidden_ctas = 0;
     cudaStream_t stream = nullptr;                  // the collectives and their finishing passes
     bool counts_global = false;                     // replicas hold global counts and snapshots of them (sum-form exchange valid)
+    unsigned long long host_epoch = 0;              // mvtm_handle::mut_epoch at the end of the last mvtm_sweep_host_dist (0: none)
+    int *d_flag = nullptr;                          // mvtm_sweep_host_dist: differences between the uploaded and the resident assignments
+    int host_fast_last = 0;                         // 1: the last mvtm_sweep_host_dist found its state intact and skipped the count rebuild
     long long bytes_last = 0;                       // bytes all-reduced by the last sweep
     int64_t *d_i = nullptr; double *d_r = nullptr; size_t cap_i = 0, cap_r = 0;   // staging of reduced statistics
 };
@@ -62,7 +65,7 @@ static void comm_teardown(mvtm_handle *h)
     if (c->narrow) g_nccl.CommDestroy(c->narrow);
     if (c->wide) g_nccl.CommDestroy(c->wide);
     if (c->stream) cudaStreamDestroy(c->stream);
-    cudaFree(c->d_i); cudaFree(c->d_r);
+    cudaFree(c->d_i); cudaFree(c->d_r); cudaFree(c->d_flag);
     delete c;
     h->comm = nullptr;
 }
@@ -126,6 +129,14 @@ extern "C" int mvtm_comm_info(mvtm_handle *h, int32_t *rank, int32_t *world, int
     return MVTM_OK;
 }
 
+extern "C" int mvtm_comm_last_host_step(mvtm_handle *h, int32_t *resident_counts_used)
+{
+    if (!h || !resident_counts_used) return MVTM_ERR_ARG;
+    if (!h->comm) FAIL(h, MVTM_ERR_STATE, "mvtm_comm_last_host_step: no communicator (mvtm_comm_init)");
+    *resident_counts_used = h->comm->host_fast_last;
+    return MVTM_OK;
+}
+
 static int require_comm(mvtm_handle *h, const char *who)
 {
     if (!h->comm) FAIL(h, MVTM_ERR_STATE, "%s: no communicator (call mvtm_comm_init first)", who);
@@ -165,6 +176,7 @@ extern "C" int mvtm_sync_counts(mvtm_handle *h, int32_t rebuild_from_assignments
     }
     CK(h, cudaStreamSynchronize(h->stream));
     c->counts_global = true;
+    h->mut_epoch++;
     return MVTM_OK;
 }
 
@@ -198,24 +210,19 @@ static int critical_view(mvtm_handle *h)
     return best;
 }
 
-extern "C" int mvtm_sweep_dist(mvtm_handle *h, int32_t iteration)
+// the passes of one sweep with their exchanges (replicas hold global counts + snapshots on entry and again when the exchanges end).
+// z_pageable != NULL: host arrays that are not pinned + mapped get a copy of the view's new assignments behind its pass.
+static int dist_passes(mvtm_handle *h, int iteration, int32_t *const *z_pageable)
 {
-    if (!h) return MVTM_ERR_ARG;
-    if (int rc = require_comm(h, "mvtm_sweep_dist")) return rc;
     CommState *c = h->comm;
-    if (!c->counts_global) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep_dist: the replicas do not hold global counts (call mvtm_sync_counts)");
-    if (h->sweep_open) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep_dist: passes queued by mvtm_sweep_view_async are still open");
-    CK(h, cudaSetDevice(h->device));
-    // activation of inactive topics that the PREVIOUS sweep sampled, on the global counts its exchanges produced (U:263-270):
-    // every rank takes the same decision.  Waits for those exchanges; skipped (no wait) while no topic is inactive.
-    if (!h->inactive.empty()) if (int rc = mvtm_activate_topics(h)) return rc;
     if (int rc = open_sweep(h)) return rc;
     h->open_mode = 1;
-    c->bytes_last = 0;
     const bool overlap = h->M > 1 && c->world > 1;
     const int crit = critical_view(h);
     for (int m = 0; m < h->M; m++) {
         if (int rc = enqueue_view_pass(h, iteration, 1, m, &h->open_launches)) { h->sweep_open = false; return rc; }
+        if (z_pageable && z_pageable[m] && h->v[m].n_tok > 0)
+            CK(h, cudaMemcpyAsync(z_pageable[m], h->v[m].z, (size_t)h->v[m].n_tok * 4, cudaMemcpyDeviceToHost, h->stream));
         if (c->world == 1) continue;
         int rc;
         if (overlap) {
@@ -230,6 +237,21 @@ extern "C" int mvtm_sweep_dist(mvtm_handle *h, int32_t iteration)
     return close_sweep(h, 1);                                           // host side of the barrier M:1231: the PASSES only
 }
 
+extern "C" int mvtm_sweep_dist(mvtm_handle *h, int32_t iteration)
+{
+    if (!h) return MVTM_ERR_ARG;
+    if (int rc = require_comm(h, "mvtm_sweep_dist")) return rc;
+    CommState *c = h->comm;
+    if (!c->counts_global) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep_dist: the replicas do not hold global counts (call mvtm_sync_counts)");
+    if (h->sweep_open) FAIL(h, MVTM_ERR_STATE, "mvtm_sweep_dist: passes queued by mvtm_sweep_view_async are still open");
+    CK(h, cudaSetDevice(h->device));
+    // activation of inactive topics that the PREVIOUS sweep sampled, on the global counts its exchanges produced (U:263-270):
+    // every rank takes the same decision.  Waits for those exchanges; skipped (no wait) while no topic is inactive.
+    if (!h->inactive.empty()) if (int rc = mvtm_activate_topics(h)) return rc;
+    c->bytes_last = 0;
+    return dist_passes(h, iteration, nullptr);
+}
+
 extern "C" int mvtm_comm_drain(mvtm_handle *h)
 {
     if (!h) return MVTM_ERR_ARG;
@@ -240,11 +262,17 @@ extern "C" int mvtm_comm_drain(mvtm_handle *h)
     return MVTM_OK;
 }
 
-// The stateless multi-rank step: every rank uploads its shard's assignments, rebuilds its LOCAL counts from them, ONE all-reduce
-// per view makes them global (view m's runs while the next view's upload travels), the passes run, and the new assignments land
-// in the caller's arrays (written by the sweep kernel itself when they are pinned + mapped).  No exchange follows the passes: a
-// stateless caller's next step rebuilds the counts from its assignments anyway, so the replicas are left LOCAL-stale and
-// mvtm_sweep_dist refuses to run until mvtm_sync_counts has been called.
+// The multi-rank step of a host that keeps the assignments (`topicSequence` arrays) as its only state: assignments in, assignments
+// out, counts consistent over all ranks in between.
+//  * First call, or anything else touched the handle's assignments / tables since the last one, or the caller changed its arrays:
+//    every rank uploads its shard, rebuilds its LOCAL counts from it, ONE all-reduce per view makes them global (view m's runs
+//    while the next view's upload travels) and the snapshot of the sum-form exchange is taken.
+//  * Otherwise (the usual case: the arrays come back exactly as the previous call returned them) the upload is COMPARED with the
+//    resident assignments while the previous sweep's last exchange is still finishing; one 4-byte all-reduce tells every rank
+//    whether all shards are intact, and if so the resident global counts are used as they are.  Any difference anywhere sends all
+//    ranks down the rebuild path with the uploaded data, so the result never depends on which path ran.
+// Then the passes run with their overlapped exchanges exactly as in mvtm_sweep_dist, and the new assignments land in the caller's
+// arrays (written by the sweep kernel itself when they are pinned + mapped).  The replicas hold global counts afterwards.
 extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *const *z_inout)
 {
     if (!h) return MVTM_ERR_ARG;
@@ -254,87 +282,106 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
     if (int rc = require_views(h, "mvtm_sweep_host_dist")) return rc;
     CK(h, cudaSetDevice(h->device));
     CommState *c = h->comm;
-    if (int rc = wait_all_ready(h)) return rc;
     if (!h->copy_stream) CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     const size_t n_ev = (size_t)MVTM_MAX_VIEWS * HOST_CHUNKS;
     while (h->host_ev.size() < n_ev) { cudaEvent_t e; CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->host_ev.push_back(e); }
     auto ev_up = [&](int m, int cidx) { return h->host_ev[(size_t)(m * HOST_CHUNKS + cidx)]; };
     const size_t Kp = (size_t)h->Kp;
     int *alias[MVTM_MAX_VIEWS];
+    int32_t *pageable[MVTM_MAX_VIEWS];
     for (int m = 0; m < h->M; m++) {
         if (h->v[m].n_tok > 0 && !z_inout[m]) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: NULL z for view %d", m);
         alias[m] = h->v[m].n_tok > 0 ? mapped_alias(z_inout[m]) : nullptr;
+        pageable[m] = alias[m] ? nullptr : z_inout[m];
     }
-    if (int rc = upload_hyper(h)) return rc;
-    c->counts_global = false;
+    if (int rc = ensure_snapshots(h)) return rc;
+    if (!c->d_flag) CK(h, cudaMalloc(&c->d_flag, sizeof(int)));
     c->bytes_last = 0;
-    // neither the copy stream nor the collective stream may overtake earlier work on the handle's stream
-    CK(h, cudaEventRecord(h->ev_done[0], h->stream));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
-    CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
-    for (int m = 0; m < h->M; m++) {
-        ViewDev &v = h->v[m];
-        CK(h, cudaMemsetAsync(v.nwk, 0, ((size_t)v.V + 1) * Kp * 4, h->stream));
-        for (int cidx = 0; cidx < HOST_CHUNKS; cidx++) {
-            const long long t0 = v.chunk_tok_off[cidx], n = v.chunk_tok_off[cidx + 1] - t0;
-            if (n <= 0) continue;
-            CK(h, cudaMemcpyAsync(v.z + t0, z_inout[m] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, h->copy_stream));
-            CK(h, cudaEventRecord(ev_up(m, cidx), h->copy_stream));
-            CK(h, cudaStreamWaitEvent(h->stream, ev_up(m, cidx), 0));
-            int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
-            k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(n, v.word + t0, v.z + t0, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad, 1);
-            CK(h, cudaGetLastError());
+    c->host_fast_last = 0;
+    const bool compare = c->counts_global && c->host_epoch != 0 && c->host_epoch == h->mut_epoch &&
+                         !(getenv("MVTM_HOST_COMPARE") && atoi(getenv("MVTM_HOST_COMPARE")) == 0);
+    bool intact = false;
+    // activation of inactive topics the previous sweep sampled, on the global counts its exchanges produced (as mvtm_sweep_dist does)
+    if (compare && !h->inactive.empty()) if (int rc = mvtm_activate_topics(h)) return rc;
+    if (compare) {
+        // the uploads go to a staging buffer and the comparisons only read z: neither waits for the exchanges the previous call
+        // left running on the collective stream
+        for (int m = 0; m < h->M; m++)
+            if (h->v[m].n_tok > 0 && !h->v[m].z_stage) CK(h, cudaMalloc(&h->v[m].z_stage, (size_t)h->v[m].n_tok * 4));
+        CK(h, cudaEventRecord(h->ev_done[0], h->stream));
+        CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+        CK(h, cudaMemsetAsync(c->d_flag, 0, sizeof(int), h->stream));
+        for (int m = 0; m < h->M; m++) {
+            ViewDev &v = h->v[m];
+            for (int cidx = 0; cidx < HOST_CHUNKS; cidx++) {
+                const long long t0 = v.chunk_tok_off[cidx], n = v.chunk_tok_off[cidx + 1] - t0;
+                if (n <= 0) continue;
+                CK(h, cudaMemcpyAsync(v.z_stage + t0, z_inout[m] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(h, cudaEventRecord(ev_up(m, cidx), h->copy_stream));
+                CK(h, cudaStreamWaitEvent(h->stream, ev_up(m, cidx), 0));
+                int blocks = (int)std::min<long long>((n + 1023) / 1024, (long long)h->num_sms * 4);
+                k_diff_assign<<<blocks, 256, 0, h->stream>>>(n, v.z_stage + t0, v.z + t0, c->d_flag);
+                CK(h, cudaGetLastError());
+            }
         }
-        if (c->world > 1) {      // local -> global, on the collective stream while the next view's chunks travel and are counted
-            CK(h, cudaEventRecord(h->ev_done[m], h->stream));
-            CK(h, cudaStreamWaitEvent(c->stream, h->ev_done[m], 0));
-            NCK(h, g_nccl.AllReduce(v.nwk, v.nwk, ((size_t)v.V + 1) * Kp, ncclInt32, ncclSum, c->wide, c->stream));
-            CK(h, cudaEventRecord(h->ev_ready[m], c->stream));
-            h->ready_pending[m] = true;
-            c->bytes_last += (long long)(((size_t)v.V + 1) * Kp * 4);
+        // the verdict travels on the COLLECTIVE stream, behind the exchanges the previous call queued there (one communicator is
+        // never used from two streams at once); those have to end before the first pass anyway
+        CK(h, cudaEventRecord(h->ev_done[0], h->stream));
+        CK(h, cudaStreamWaitEvent(c->stream, h->ev_done[0], 0));
+        if (c->world > 1) NCK(h, g_nccl.AllReduce(c->d_flag, c->d_flag, 1, ncclInt32, ncclSum, c->wide, c->stream));
+        int ndiff = 0;
+        CK(h, cudaMemcpyAsync(&ndiff, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(h, cudaStreamSynchronize(c->stream));
+        intact = (ndiff == 0);
+    }
+    if (!intact) {
+        if (int rc = wait_all_ready(h)) return rc;
+        c->counts_global = false; c->host_epoch = 0;
+        h->mut_epoch++;
+        // neither the copy stream nor the collective stream may overtake earlier work on the handle's stream
+        CK(h, cudaEventRecord(h->ev_done[0], h->stream));
+        CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+        CK(h, cudaMemsetAsync(h->d_bad, 0, sizeof(int), h->stream));
+        for (int m = 0; m < h->M; m++) {
+            ViewDev &v = h->v[m];
+            const size_t n_tab = ((size_t)v.V + 1) * Kp;
+            CK(h, cudaMemsetAsync(v.nwk, 0, n_tab * 4, h->stream));
+            for (int cidx = 0; cidx < HOST_CHUNKS; cidx++) {
+                const long long t0 = v.chunk_tok_off[cidx], n = v.chunk_tok_off[cidx + 1] - t0;
+                if (n <= 0) continue;
+                if (compare) {      // already on the device
+                    CK(h, cudaMemcpyAsync(v.z + t0, v.z_stage + t0, (size_t)n * 4, cudaMemcpyDeviceToDevice, h->stream));
+                } else {
+                    CK(h, cudaMemcpyAsync(v.z + t0, z_inout[m] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+                    CK(h, cudaEventRecord(ev_up(m, cidx), h->copy_stream));
+                    CK(h, cudaStreamWaitEvent(h->stream, ev_up(m, cidx), 0));
+                }
+                int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->num_sms * 8);
+                k_build_counts<<<blocks, 256, (size_t)h->K * 4, h->stream>>>(n, v.word + t0, v.z + t0, v.V, h->K, h->Kp, v.nwk, v.nk, h->d_bad, 1);
+                CK(h, cudaGetLastError());
+            }
+            if (c->world > 1) {      // local -> global + snapshot, on the collective stream while the next view's chunks travel and are counted
+                CK(h, cudaEventRecord(h->ev_done[m], h->stream));
+                CK(h, cudaStreamWaitEvent(c->stream, h->ev_done[m], 0));
+                NCK(h, g_nccl.AllReduce(v.nwk, v.nwk, n_tab, ncclInt32, ncclSum, c->wide, c->stream));
+                CK(h, cudaMemcpyAsync(v.snap_nwk, v.nwk, n_tab * 4, cudaMemcpyDeviceToDevice, c->stream));
+                CK(h, cudaEventRecord(h->ev_ready[m], c->stream));
+                h->ready_pending[m] = true;
+                c->bytes_last += (long long)(n_tab * 4);
+            }
         }
+        int bad = 0;
+        CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (bad) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: the assignments hold %d topic ids >= K", bad);   // (rewritten to UNASSIGNED on the device)
+        c->counts_global = true;
     }
-    CK(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
-    CK(h, cudaEventRecord(h->ev[0], h->stream));
-    int launches = 0;
-    for (int m = 0; m < h->M; m++) {
-        ViewDev &v = h->v[m];
-        LaunchCfg lc;
-        if (int rc = choose_launch(h, m, ring_for_view(h, m), lc)) return rc;
-        if (int rc = ensure_oc_scratch(h, (size_t)lc.grid * lc.W * (32 / h->G))) return rc;
-        if (int rc = wait_view_ready(h, m)) return rc;                  // the view's global counts
-        CK(h, cudaEventRecord(h->ev[2 + 2 * m], h->stream));
-        if (v.n_items > 0) {
-            CK(h, cudaMemcpyAsync(v.nk_snap, v.nk, Kp * 4, cudaMemcpyDeviceToDevice, h->stream));
-            CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
-            SweepParams P;
-            fill_params(h, m, iteration, 1, P);
-            P.R = lc.R; P.oc_smem = lc.oc_smem;
-            h->stats.ring_depth[m] = lc.R;
-            P.z_host = alias[m];
-            CK(h, launch_sweep(h, P, lc));
-            launches++;
-        }
-        CK(h, cudaEventRecord(h->ev[3 + 2 * m], h->stream));
-        if (v.n_tok > 0 && !alias[m])
-            CK(h, cudaMemcpyAsync(z_inout[m], v.z, (size_t)v.n_tok * 4, cudaMemcpyDeviceToHost, h->stream));
-    }
-    CK(h, cudaEventRecord(h->ev[1], h->stream));
-    unsigned long long st[4];
-    int bad = 0;
-    CK(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    if (bad) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: the assignments hold %d topic ids >= K", bad);
-    h->stats.tokens = (long long)st[0]; h->stats.changed = (long long)st[1]; h->stats.new_topic = (long long)st[2];
-    float ms = 0.f;
-    CK(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    h->stats.ms_total = ms;
-    for (int m = 0; m < h->M; m++) {
-        CK(h, cudaEventElapsedTime(&ms, h->ev[2 + 2 * m], h->ev[3 + 2 * m]));
-        h->stats.ms_view[m] = ms;
-    }
-    h->stats.kernel_launches = launches;
+    c->host_fast_last = intact ? 1 : 0;
+    for (int m = 0; m < h->M; m++) h->v[m].z_host_once = alias[m];
+    const int rc = dist_passes(h, iteration, pageable);
+    for (int m = 0; m < h->M; m++) h->v[m].z_host_once = nullptr;
+    if (rc) { c->counts_global = false; c->host_epoch = 0; return rc; }
+    c->host_epoch = h->mut_epoch;
     return MVTM_OK;
 }
 

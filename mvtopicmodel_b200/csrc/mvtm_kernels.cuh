@@ -1017,6 +1017,15 @@ __global__ void k_init_from_phi(int m, int K, int Kp, int V, long long n_docs, c
     }
 }
 
+// mvtm_sweep_host_dist: does the caller's array still hold what the device holds?  *ndiff receives the number of blocks that saw
+// a difference (0 = identical)
+__global__ void k_diff_assign(long long n, const int *a, const int *b, int *ndiff)
+{
+    int d = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) d |= (a[i] != b[i]);
+    if (__syncthreads_or(d) && threadIdx.x == 0) atomicAdd(ndiff, 1);
+}
+
 // buildInitialTypeTopicCounts M:600-652: n_wk / n_k from (word, z); n_k through a shared-memory histogram
 // fix != 0: an id >= K is rewritten to UNASSIGNED_TOPIC so that no sweep can index with it; fix == 0 (mvtm_check_invariants): the
 // assignments are only read

@@ -204,6 +204,12 @@ class Engine:
             ptrs[m] = z.ctypes.data
         self._ck(self.L.mvtm_sweep_host_dist(self.h, int(iteration), ptrs))
 
+    def last_host_step_used_resident_counts(self):
+        """True if the last sweep_host_dist found the caller's arrays equal to the resident assignments on every rank and skipped the recount."""
+        f = C.c_int32()
+        self._ck(self.L.mvtm_comm_last_host_step(self.h, C.byref(f)))
+        return bool(f.value)
+
     def loglik_dist(self, quirk_len2=False):
         out = np.empty(self.M, dtype=np.float64)
         self._ck(self.L.mvtm_loglik_dist(self.h, _ptr(out), int(bool(quirk_len2))))

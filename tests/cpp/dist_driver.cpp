@@ -5,8 +5,9 @@
 // Corpus: D two-view documents generated from a fixed LCG; rank r holds documents r, r+N, ... (doc_id_base / doc_id_stride).
 // Checks: (1) after mvtm_sync_counts every rank holds the same n_k, totalling the corpus; (2) after S mvtm_sweep_dist sweeps
 // (overlapped exchange) the same again, and each rank's replica equals the histogram of ALL ranks' assignments (cell by cell, on
-// the host); (3) the global log-likelihood is the same number on every rank and improved; (4) a stateless mvtm_sweep_host_dist
-// step followed by mvtm_sync_counts(rebuild) leaves consistent global tables; (5) mvtm_optimize_hyper installs identical
+// the host); (3) the global log-likelihood is the same number on every rank and improved; (4) mvtm_sweep_host_dist
+// steps through host arrays -- recounting on the first call, keeping the resident counts when no rank's arrays changed, recounting
+// on EVERY rank when one rank edits one token -- leave consistent global tables that mvtm_sweep_dist continues from; (5) mvtm_optimize_hyper installs identical
 // hyper-parameters on every rank (statistics reduced inside the library).
 #include <cstdint>
 #include <cstdio>
@@ -67,10 +68,18 @@ void rank_main(int rank, int world, int D_total, int sweeps, const unsigned char
     // a stateless host step on every rank, then back to resident sweeps
     std::vector<int32_t> zh[MMAX]; int32_t *zp[MMAX];
     for (int m = 0; m < M; m++) { zh[m].resize(sh.word[m].size() + 1); CHECK(mvtm_get_assignments(h, m, zh[m].data())); zp[m] = zh[m].data(); }
+    int32_t kept = -1;
+    CHECK(mvtm_sweep_host_dist(h, sweeps + 1, zp));                      // first host step: recount + all-reduce
+    CHECK(mvtm_comm_last_host_step(h, &kept));
+    if (kept != 0) { res.rc = 100; res.err = "first mvtm_sweep_host_dist did not recount"; mvtm_destroy(h); return; }
+    CHECK(mvtm_sweep_host_dist(h, sweeps + 1, zp));                      // arrays unchanged on every rank: resident counts kept
+    CHECK(mvtm_comm_last_host_step(h, &kept));
+    if (kept != 1) { res.rc = 101; res.err = "second mvtm_sweep_host_dist recounted although nothing changed"; mvtm_destroy(h); return; }
+    if (rank == world - 1 && !zh[0].empty()) zh[0][0] = (zh[0][0] + 1) % K;   // ONE rank edits ONE token: every rank must recount
     CHECK(mvtm_sweep_host_dist(h, sweeps + 1, zp));
-    if (mvtm_sweep_dist(h, sweeps + 2) != MVTM_ERR_STATE) { res.rc = 100; res.err = "mvtm_sweep_dist accepted local-stale replicas"; mvtm_destroy(h); return; }
-    CHECK(mvtm_sync_counts(h, 1));
-    CHECK(mvtm_sweep_dist(h, sweeps + 2));
+    CHECK(mvtm_comm_last_host_step(h, &kept));
+    if (kept != 0) { res.rc = 102; res.err = "mvtm_sweep_host_dist missed an edit made on another rank"; mvtm_destroy(h); return; }
+    CHECK(mvtm_sweep_dist(h, sweeps + 2));                               // global counts were left behind
     CHECK(mvtm_comm_drain(h));
     CHECK(mvtm_optimize_hyper(h, 50, MVTM_OPT_ALL));
     CHECK(mvtm_sweep_dist(h, sweeps + 3));
