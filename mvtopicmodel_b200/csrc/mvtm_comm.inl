@@ -46,6 +46,8 @@ struct CommState {
     bool counts_global = false;                     // replicas hold global counts and snapshots of them (sum-form exchange valid)
     unsigned long long host_epoch = 0;              // mvtm_handle::mut_epoch at the end of the last mvtm_sweep_host_dist (0: none)
     int *d_flag = nullptr;                          // mvtm_sweep_host_dist: differences between the uploaded and the resident assignments
+    cudaEvent_t ev_wide = nullptr;                  // end of the last exchange that used the WIDE communicator on the collective stream
+    bool wide_pending = false;
     int host_fast_last = 0;                         // 1: the last mvtm_sweep_host_dist found its state intact and skipped the count rebuild
     long long bytes_last = 0;                       // bytes all-reduced by the last sweep
     int64_t *d_i = nullptr; double *d_r = nullptr; size_t cap_i = 0, cap_r = 0;   // staging of reduced statistics
@@ -65,6 +67,7 @@ static void comm_teardown(mvtm_handle *h)
     if (c->narrow) g_nccl.CommDestroy(c->narrow);
     if (c->wide) g_nccl.CommDestroy(c->wide);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->ev_wide) cudaEventDestroy(c->ev_wide);
     cudaFree(c->d_i); cudaFree(c->d_r); cudaFree(c->d_flag);
     delete c;
     h->comm = nullptr;
@@ -102,6 +105,7 @@ extern "C" int mvtm_comm_init(mvtm_handle *h, const void *unique_id, int32_t ran
     }
     cudaError_t e = cudaSuccess;
     if (r == ncclSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (r == ncclSuccess && e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_wide, cudaEventDisableTiming);
     if (r != ncclSuccess || e != cudaSuccess) {
         std::string msg = r != ncclSuccess ? std::string("NCCL: ") + g_nccl.GetErrorString(r) : std::string("CUDA: ") + cudaGetErrorString(e);
         comm_teardown(h);
@@ -198,6 +202,7 @@ static int enqueue_exchange(mvtm_handle *h, int m, cudaStream_t s, ncclComm_t co
     if (s != h->stream) {
         CK(h, cudaEventRecord(h->ev_ready[m], s));
         h->ready_pending[m] = true;
+        if (comm == c->wide) { CK(h, cudaEventRecord(c->ev_wide, s)); c->wide_pending = true; }
     }
     c->bytes_last += (long long)n * 4;
     return MVTM_OK;
@@ -324,14 +329,15 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
                 CK(h, cudaGetLastError());
             }
         }
-        // the verdict travels on the COLLECTIVE stream, behind the exchanges the previous call queued there (one communicator is
-        // never used from two streams at once); those have to end before the first pass anyway
-        CK(h, cudaEventRecord(h->ev_done[0], h->stream));
-        CK(h, cudaStreamWaitEvent(c->stream, h->ev_done[0], 0));
-        if (c->world > 1) NCK(h, g_nccl.AllReduce(c->d_flag, c->d_flag, 1, ncclInt32, ncclSum, c->wide, c->stream));
+        // the verdict travels on the WIDE communicator from the handle's stream, ordered (by an event) behind the last exchange that
+        // used that communicator on the collective stream -- the longest view's, which has to end before the first pass anyway --
+        // but NOT behind the CTA-limited exchanges of the other views still queued there: those keep running under the passes, and
+        // one communicator is never used from two streams at once
+        if (c->wide_pending) CK(h, cudaStreamWaitEvent(h->stream, c->ev_wide, 0));
+        if (c->world > 1) NCK(h, g_nccl.AllReduce(c->d_flag, c->d_flag, 1, ncclInt32, ncclSum, c->wide, h->stream));
         int ndiff = 0;
-        CK(h, cudaMemcpyAsync(&ndiff, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(h, cudaStreamSynchronize(c->stream));
+        CK(h, cudaMemcpyAsync(&ndiff, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
         intact = (ndiff == 0);
     }
     if (!intact) {
@@ -391,6 +397,7 @@ static int comm_reduce_stats(mvtm_handle *h, int op, long long *ints, long long 
     CommState *c = h->comm;
     if (c->world == 1) return MVTM_OK;
     const ncclRedOp_t rop = op == 0 ? ncclSum : ncclMax;
+    if (c->wide_pending) CK(h, cudaStreamWaitEvent(h->stream, c->ev_wide, 0));   // the wide communicator is never used from two streams at once
     if ((size_t)n_ints > c->cap_i) { cudaFree(c->d_i); c->d_i = nullptr; c->cap_i = 0; CK(h, cudaMalloc(&c->d_i, (size_t)n_ints * 8)); c->cap_i = (size_t)n_ints; }
     if ((size_t)n_reals > c->cap_r) { cudaFree(c->d_r); c->d_r = nullptr; c->cap_r = 0; CK(h, cudaMalloc(&c->d_r, (size_t)n_reals * 8)); c->cap_r = (size_t)n_reals; }
     if (n_ints > 0 && ints) {
