@@ -322,7 +322,7 @@ def main():
 
         def e2e_step(i):
             if world > 1:
-                eng.sweep_host_dist(i, zn)                 # upload + local recount, ONE all-reduce per view, passes, z written back
+                eng.sweep_host_dist(i, zn)                 # upload + compare (or recount + all-reduce), passes + exchanges, z written back
             else:
                 eng.sweep_host(i, zn)
         e2e_steps = max(3, min(args.steps, 10))
@@ -344,7 +344,9 @@ def main():
         e2e = {"value": ntok_global * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * ntok_local,
                "d2h_bytes_per_step": 4 * ntok_local, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                "call": "mvtm_sweep_host (pinned host z in/out: chunked upload + count rebuild, sweep, new z stored to the pinned arrays by the kernel)" if world == 1 else
-                       "mvtm_sweep_host_dist (per rank: pinned host z in/out, chunked upload + local count rebuild, one NCCL all-reduce per view inside the library, sweep, new z stored to the pinned arrays by the kernel)"}
+                       "mvtm_sweep_host_dist (per rank: pinned host z in/out; the upload is compared with the resident assignments, a 4-byte all-reduce tells every rank "
+                       "whether all shards came back unchanged -- they do here -- so the resident global counts are kept (any difference: recount + one all-reduce per view); "
+                       "passes with overlapped exchanges; new z stored to the pinned arrays by the kernel)"}
         for m in range(M):
             assert np.array_equal(zn[m], eng.get_assignments(m)), "host arrays differ from the device assignments"
 
@@ -383,7 +385,7 @@ def main():
             # on Zipf corpora the hot rows are served from L2 and DRAM moves only `traffic` bytes per launch (dram_frac of peak)
             "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "dram_frac": dram_frac, "l2_hit": l2_hit, "traffic": traffic,
-                         "kernel": f"k_sweep_view (view {dom})", "bytes_per_token": btok_dom, "tokens_per_launch": eng.ntok[dom],
+                         "kernel": ("k_sweep_view_direct (n_wk rows in registers)" if ring[dom] == 0 else "k_sweep_view (TMA ring)") + f", view {dom}", "bytes_per_token": btok_dom, "tokens_per_launch": eng.ntok[dom],
                          "avg_launch_ms": launch_ms, "bytes_per_token_all_views": btok_all,
                          "whole_job_frac": btok_all * value / 1e9 / (peak * world),
                          "peak_source": peak_src, "traffic_source": ent.get("source") if ent else None},

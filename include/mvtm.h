@@ -79,7 +79,7 @@ typedef struct mvtm_sweep_stats {
     double ms_view[MVTM_MAX_VIEWS];  /* device time of each view's sampling kernel                           */
     int32_t kernel_launches;         /* kernels launched by the last sweep                                   */
     int32_t ring_depth[MVTM_MAX_VIEWS];  /* TMA ring depth each view's last pass ran with; 0 = DIRECT kernel     */
-    int32_t ring_locked[MVTM_MAX_VIEWS]; /* the depth the autotune settled on (0 = still sampling; = the configured depth when fixed) */
+    int32_t ring_locked[MVTM_MAX_VIEWS]; /* the depth the autotune settled on (0 = still sampling, or DIRECT kernel; = the configured depth when fixed) */
 } mvtm_sweep_stats;
 
 typedef struct mvtm_handle mvtm_handle;

@@ -564,7 +564,7 @@ static int ring_for_view(mvtm_handle *h, int m)
 static void ring_record(mvtm_handle *h, int m, float ms)
 {
     ViewDev &v = h->v[m];
-    if (h->cfg_ring > 0 || getenv("MVTM_RING") || v.ring_locked) return;
+    if (h->direct || h->cfg_ring > 0 || getenv("MVTM_RING") || v.ring_locked) return;
     v.tune_ms[v.tune_step] = ms;
     if (++v.tune_step == 2 * RING_SAMPLES) {
         float a[RING_SAMPLES], b[RING_SAMPLES];
@@ -961,7 +961,7 @@ extern "C" int mvtm_stats(mvtm_handle *h, mvtm_sweep_stats *out)
     if (!h || !out) return MVTM_ERR_ARG;
     for (int m = 0; m < h->M; m++) {
         const char *e = getenv("MVTM_RING");
-        h->stats.ring_locked[m] = h->cfg_ring > 0 ? h->cfg_ring : (e ? atoi(e) : h->v[m].ring_locked);
+        h->stats.ring_locked[m] = h->direct ? 0 : (h->cfg_ring > 0 ? h->cfg_ring : (e ? atoi(e) : h->v[m].ring_locked));   // DIRECT kernel: no ring
     }
     *out = h->stats;
     return MVTM_OK;
