@@ -118,9 +118,10 @@ static int pick_J(int K)
 // KS/G <= 64; not in reference-compat (Q1) mode, whose kernels stay on the TMA ring.
 // Measured on B200 (profiles/r2_ab_direct*.log), DIRECT vs TMA ring: K = 1000 two views (acm_2v) 2.14 vs 1.66 G tok/s, K = 1000 one
 // view 2.62 vs 1.97, K = 1000 uniform words (HBM-bound) 1.67 vs 1.50, three views (pubmed_3v) 1.93 vs 1.59; K = 500 (four
-// documents per warp) 3.19 vs 3.26: no gain, stays on the ring; K = 2000 four views (stress_4v, one document per warp, 12 instead
+// documents per warp at 168 registers) 3.19 vs 3.26, (two per warp at 128 registers, 16 warps per SM; compiled, MVTM_DIRECT=1 selects it)
+// 3.24 vs 3.18: within 2 %, K <= 512 stays on the ring by default; K = 2000 four views (stress_4v, one document per warp, 12 instead
 // of 8 warps per SM) 0.877 vs 0.671 at 200 K documents.
-static bool direct_compiled(int KS, int G) { return (KS == 1024 && G == 16) || (KS == 2048 && G == 32); }
+static bool direct_compiled(int KS, int G) { return (KS == 512 && G == 16) || (KS == 1024 && G == 16) || (KS == 2048 && G == 32); }
 static bool pick_direct(int KS, bool multi, unsigned flags)
 {
     (void)multi;
@@ -614,7 +615,7 @@ static cudaError_t launch_sweep_t(const SweepParams &P, const LaunchCfg &lc, cud
         kernel<<<lc.grid, lc.W * 32, lc.smem, s>>>(P);
         return cudaGetLastError();
     };
-    if constexpr ((KS == 1024 && G == 16) || (KS == 2048 && G == 32)) {   // = direct_compiled
+    if constexpr ((KS == 512 && G == 16) || (KS == 1024 && G == 16) || (KS == 2048 && G == 32)) {   // = direct_compiled
         if (lc.direct && !q1) return go(k_sweep_view_direct<KS, G, MULTI>);
     }
     if (lc.direct) return cudaErrorInvalidValue;

@@ -25,9 +25,10 @@
 #include <stdint.h>
 
 #define MVTM_MAXM 8
-#ifndef MVTM_DIRECT_REGS
-#define MVTM_DIRECT_REGS 168         // registers per thread the DIRECT sweep kernels are compiled for (__maxnreg__): 12 warps per SM
-#endif
+// registers per thread the DIRECT sweep kernels are compiled for (__maxnreg__).  The register file is split per SM sub-partition
+// (16 K registers each): 168 registers = 3 warps per sub-partition (12 per SM), 128 = 4 (16 per SM); nothing in between launches.
+// The row costs KS/G registers: 64 at (1024, 16) and (2048, 32) -> 168; 32 at (512, 16) -> 128.
+__host__ __device__ constexpr int direct_regs(int KS, int G) { return (KS / G <= 32) ? 128 : 168; }
 
 struct SweepParams {
     int M, K, Kp, m, V;
@@ -688,7 +689,7 @@ __host__ __device__ constexpr int sweep_max_threads(int KS, int G, bool multi, b
     const int docs = (int)((227 * 1024 - 1024 - cta) / doc);
     int W = docs / (32 / G);
     // DIRECT: the row costs KS/G registers per thread on top of ~100, so the register file (64 K), not shared memory, is the bound
-    const int wreg = direct ? (65536 / 32) / MVTM_DIRECT_REGS : 24;
+    const int wreg = direct ? (65536 / 32) / direct_regs(KS, G) : 24;
     W = W > wreg ? wreg : W;
     W = W > 24 ? 24 : (W < 1 ? 1 : W);
     return 32 * W;
@@ -904,7 +905,7 @@ __global__ void __launch_bounds__(sweep_max_threads(KS, G, MULTI), 1) k_sweep_vi
 { sweep_view_body<KS, G, MULTI, Q1, false>(P); }
 
 template <int KS, int G, bool MULTI>
-__global__ void __maxnreg__(MVTM_DIRECT_REGS) k_sweep_view_direct(const SweepParams P)
+__global__ void __maxnreg__(direct_regs(KS, G)) k_sweep_view_direct(const SweepParams P)
 { sweep_view_body<KS, G, MULTI, false, true>(P); }
 
 // ------------------------------------------------------------------------------------------------
