@@ -35,6 +35,20 @@ def test_library_is_sm100a_native(engine_lib):
     assert "UBLKCP" in sass                 # TMA 1-D bulk copies of the n_wk rows
     assert "SYNCS.ARRIVE.TRANS64" in sass   # mbarrier expect_tx
     assert "REDG" in sass or "RED." in sass # count deltas as reductions
+    # the DIRECT kernel (n_wk rows in registers): coherent 128-bit row loads and packed fp32 pairs
+    direct = [b for b in sass.split("Function : ") if b.startswith("_Z19k_sweep_view_direct")]
+    assert len(direct) >= 4                 # (1024,16) and (2048,32), single and multi view
+    for b in direct:
+        assert "LDG.E.128.STRONG.GPU" in b and "FFMA2" in b and "UBLKCP" not in b
+
+
+def test_flag_constants_match_the_header():
+    """The flag values the Python tests and tools pass as plain integers are the header's."""
+    src = open(os.path.join(ROOT, "include", "mvtm.h")).read()
+    flags = {k: int(v) for k, v in re.findall(r"#define\s+(MVTM_FLAG_[A-Z0-9_]+)\s+(\d+)u", src)}
+    assert flags["MVTM_FLAG_DOC_ORDER"] == 1 and flags["MVTM_FLAG_SINGLE_WARP"] == 2
+    assert flags["MVTM_FLAG_Q1_COMPAT"] == 4 and flags["MVTM_FLAG_BETA_MALLET"] == 8 and flags["MVTM_FLAG_TMA_RING"] == 16
+    assert len(set(flags.values())) == len(flags) and all(v & (v - 1) == 0 for v in flags.values())
 
 
 def test_no_cpu_fallback_without_device(engine_lib):
