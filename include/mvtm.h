@@ -306,6 +306,12 @@ double mvtm_test_learn_symmetric_concentration(const int64_t *count_hist, int32_
  * hist[m]: K x stride[m] bins of topicDocCounts; lencnt[m]: n_len[m] bins of docLengthCounts; alpha: M x (K+1);
  * scal = { gammaRoot, rootTablesCnt } (in/out); script: one value per draw in call order (Gamma(a,1), Beta, Bernoulli, Antoniak);
  * arg_log: 3 doubles (kind 1..4, a, b) per consumed draw; *n_used: draws consumed.  MVTM_ERR_ARG when the script is too short. */
+/* The launch shape a handle with these parameters would give a view pass, computed without a device (148 SMs assumed): lanes per
+ * document, ring depth (0 = DIRECT kernel), warps per CTA, dynamic shared memory per CTA, and the register count the kernel is
+ * compiled for (0 = bounded by its launch shape).  A CPU test checks every K against the SM's limits (227 KB of shared memory,
+ * 16 K registers per sub-partition) together with the register counts of the compiled kernels. */
+int mvtm_test_launch_shape(int32_t num_topics, int32_t num_views, uint32_t flags, int32_t *lanes_per_doc, int32_t *ring_depth,
+                           int32_t *warps_per_cta, int64_t *smem_bytes, int32_t *maxnreg);
 int mvtm_test_hyper_core(int32_t M, int32_t K, uint32_t which, const int64_t *const *hist, const int32_t *stride,
                          const int64_t *const *lencnt, const int32_t *n_len, double *alpha, double *alpha_sum, double *gamma,
                          double *gamma_view, double *tables_cnt, double *scal, int32_t *inactive, int32_t *n_inactive,

@@ -89,6 +89,7 @@ SIGNATURES = {
     "mvtm_test_sampler": (_i32, [C.c_uint64, _i32, C.c_double, C.c_double, _i32, _vp]),
     "mvtm_test_learn_symmetric_concentration": (C.c_double, [_vp, _i32, _vp, _i32, _i32, C.c_double]),
     "mvtm_test_hyper_core": (_i32, [_i32, _i32, C.c_uint32] + [_vp] * 13 + [C.c_int64, _vp, _vp]),
+    "mvtm_test_launch_shape": (_i32, [_i32, _i32, C.c_uint32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)]),
     "mvtm_build_info": (C.c_char_p, []),
 }
 

@@ -1369,4 +1369,23 @@ extern "C" int mvtm_delta_import(mvtm_handle *h, int32_t m)
 }
 
 #include "mvtm_optim.inl"
+// test hook: the launch shape of a view pass for (K, M, flags), no device needed
+extern "C" int mvtm_test_launch_shape(int32_t num_topics, int32_t num_views, uint32_t flags, int32_t *lanes_per_doc, int32_t *ring_depth,
+                                      int32_t *warps_per_cta, int64_t *smem_bytes, int32_t *maxnreg)
+{
+    if (num_topics < 1 || pick_J(num_topics) == 0 || num_views < 1 || num_views > MVTM_MAX_VIEWS) return MVTM_ERR_ARG;
+    if (!lanes_per_doc || !ring_depth || !warps_per_cta || !smem_bytes || !maxnreg) return MVTM_ERR_ARG;
+    mvtm_handle h;
+    h.K = num_topics; h.M = num_views; h.flags = flags; h.num_sms = 148;
+    h.Kp = (h.K + 31) / 32 * 32; h.J = pick_J(h.K); h.KS = h.J * 128;
+    h.direct = pick_direct(h.KS, h.M > 1, h.flags);
+    h.G = pick_G(h.KS, h.M > 1, h.direct);
+    if (h.direct && !direct_compiled(h.KS, h.G)) { h.direct = false; h.G = pick_G(h.KS, h.M > 1, false); }
+    LaunchCfg lc;
+    if (int rc = choose_launch(&h, 0, 1, lc)) return rc;
+    *lanes_per_doc = h.G; *ring_depth = lc.R; *warps_per_cta = lc.W; *smem_bytes = (int64_t)lc.smem;
+    *maxnreg = h.direct ? direct_regs(h.KS, h.G) : 0;
+    return MVTM_OK;
+}
+
 #include "mvtm_comm.inl"

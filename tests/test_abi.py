@@ -117,3 +117,42 @@ def test_bench_reference_arm_json_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_launch_shapes_fit_the_sm(engine_lib):
+    """Every launch shape the library would choose -- each K, 1..8 views, default / ring / compat kernels -- fits an SM of a B200:
+    dynamic + static shared memory within 227 KB, and the warps of a CTA times the registers the chosen kernel was COMPILED with
+    (cuobjdump -res-usage of the in-tree library) within the 16 K registers of each of the four sub-partitions.  (A 13-warp
+    152-register shape fits the SM's 64 K registers on paper and still cannot launch: found on the GPU, now a CPU test.)"""
+    from mvtopicmodel_b200 import _lib
+    res = subprocess.run(["cuobjdump", "-res-usage", _lib.SO_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    for name, r, shared in re.findall(r"Function (_Z\d+k_sweep_view\w+):\s*\n\s*REG:(\d+) STACK:\d+ SHARED:(\d+)", res):
+        m = re.match(r"_Z\d+k_sweep_view(_direct)?ILi(\d+)ELi(\d+)ELb(\d)(?:ELb(\d))?", name)
+        direct, KS, G, multi, q1 = bool(m.group(1)), int(m.group(2)), int(m.group(3)), m.group(4) == "1", m.group(5) == "1"
+        regs[(direct, KS, G, multi, q1)] = (int(r), int(shared))
+    assert len(regs) >= 48
+    FLAG_Q1, FLAG_RING = 4, 16
+    seen_direct = set()
+    for K in list(range(1, 2049, 7)) + [128, 129, 256, 257, 384, 385, 500, 512, 513, 768, 769, 1000, 1024, 1025, 1536, 1537, 2000, 2048]:
+        KS = next(128 * j for j in (1, 2, 3, 4, 6, 8, 12, 16) if 128 * j >= K)
+        for M in (1, 2, 3, 4, 8):
+            for flags in (0, FLAG_RING, FLAG_Q1):
+                g, ring, warps, nreg = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+                smem = C.c_int64()
+                rc = engine_lib.mvtm_test_launch_shape(K, M, flags, C.byref(g), C.byref(ring), C.byref(warps), C.byref(smem), C.byref(nreg))
+                assert rc == 0, (K, M, flags, rc)
+                direct = ring.value == 0
+                assert not (direct and flags), (K, M, flags)                       # ring / compat requests never get the DIRECT kernel
+                key = (direct, KS, g.value, M > 1, bool(flags & FLAG_Q1))
+                assert key in regs, f"no compiled kernel for {key} (K={K}, M={M}, flags={flags})"
+                r, static = regs[key]
+                if direct:
+                    assert r <= nreg.value
+                    seen_direct.add((KS, g.value))
+                assert 1 <= warps.value <= 32
+                assert smem.value + static <= 227 * 1024, (K, M, flags, smem.value)
+                per_partition = -(-warps.value // 4)                                # warps of the CTA on the fullest sub-partition
+                assert per_partition * 32 * (-(-r // 8) * 8) <= 16384, (K, M, flags, warps.value, r)
+    assert seen_direct == {(1024, 16), (2048, 32)}                                  # the shapes DIRECT is the default for
+    assert engine_lib.mvtm_test_launch_shape(2049, 1, 0, C.byref(g), C.byref(ring), C.byref(warps), C.byref(smem), C.byref(nreg)) == 1
