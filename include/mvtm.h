@@ -242,7 +242,9 @@ int mvtm_sum_exchange_finish_async(mvtm_handle *h, int32_t m, int32_t world_size
  *       ONE all-reduce per view (overlapped with the next view's upload) and takes the exchange snapshot.  Otherwise the upload
  *       is only COMPARED with the resident assignments (one 4-byte all-reduce tells every rank whether all shards are intact)
  *       and the resident global counts are used as they are; a difference on any rank sends all ranks down the recount path, so
- *       the result never depends on which path ran.  Then the passes with their overlapped exchanges as in mvtm_sweep_dist; new z
+ *       the result never depends on which path ran.  Every rank takes part in that 4-byte verdict on EVERY call (a rank that cannot
+ *       compare reports "changed"), so the ranks always agree on the collectives that follow; topic ids >= K in the arrays are treated
+ *       as unassigned, the step still completes on every rank and the call then returns MVTM_ERR_ARG.  Then the passes with their overlapped exchanges as in mvtm_sweep_dist; new z
  *       is written to the caller's arrays (by the sweep kernel itself when they are pinned + mapped).  The replicas hold global
  *       counts afterwards (mvtm_sweep_dist / mvtm_loglik_dist may follow).  mvtm_comm_last_host_step tells which path ran;
  *       MVTM_HOST_COMPARE=0 in the environment forces the recount path.

@@ -308,6 +308,11 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
     bool intact = false;
     // activation of inactive topics the previous sweep sampled, on the global counts its exchanges produced (as mvtm_sweep_dist does)
     if (compare && !h->inactive.empty()) if (int rc = mvtm_activate_topics(h)) return rc;
+    // EVERY rank takes part in the verdict, whether or not it can compare (a rank whose state was touched reports "changed"): the
+    // ranks must agree on the sequence of collectives that follows, and only the reduced verdict is the same everywhere
+    static const int k_one = 1;
+    if (compare) CK(h, cudaMemsetAsync(c->d_flag, 0, sizeof(int), h->stream));
+    else CK(h, cudaMemcpyAsync(c->d_flag, &k_one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (compare) {
         // the uploads go to a staging buffer and the comparisons only read z: neither waits for the exchanges the previous call
         // left running on the collective stream
@@ -315,7 +320,6 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
             if (h->v[m].n_tok > 0 && !h->v[m].z_stage) CK(h, cudaMalloc(&h->v[m].z_stage, (size_t)h->v[m].n_tok * 4));
         CK(h, cudaEventRecord(h->ev_done[0], h->stream));
         CK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
-        CK(h, cudaMemsetAsync(c->d_flag, 0, sizeof(int), h->stream));
         for (int m = 0; m < h->M; m++) {
             ViewDev &v = h->v[m];
             for (int cidx = 0; cidx < HOST_CHUNKS; cidx++) {
@@ -329,6 +333,8 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
                 CK(h, cudaGetLastError());
             }
         }
+    }
+    {
         // the verdict travels on the WIDE communicator from the handle's stream, ordered (by an event) behind the last exchange that
         // used that communicator on the collective stream -- the longest view's, which has to end before the first pass anyway --
         // but NOT behind the CTA-limited exchanges of the other views still queued there: those keep running under the passes, and
@@ -338,8 +344,9 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
         int ndiff = 0;
         CK(h, cudaMemcpyAsync(&ndiff, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
-        intact = (ndiff == 0);
+        intact = (ndiff == 0);                       // every rank compared, no rank found a difference
     }
+    int bad = 0;
     if (!intact) {
         if (int rc = wait_all_ready(h)) return rc;
         c->counts_global = false; c->host_epoch = 0;
@@ -376,10 +383,10 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
                 c->bytes_last += (long long)(n_tab * 4);
             }
         }
-        int bad = 0;
         CK(h, cudaMemcpyAsync(&bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
-        if (bad) FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: the assignments hold %d topic ids >= K", bad);   // (rewritten to UNASSIGNED on the device)
+        // topic ids >= K were rewritten to UNASSIGNED_TOPIC on the device: the step still runs (a rank that left here would leave
+        // its peers waiting in the exchanges) and reports the error at the end
         c->counts_global = true;
     }
     c->host_fast_last = intact ? 1 : 0;
@@ -387,6 +394,10 @@ extern "C" int mvtm_sweep_host_dist(mvtm_handle *h, int32_t iteration, int32_t *
     const int rc = dist_passes(h, iteration, pageable);
     for (int m = 0; m < h->M; m++) h->v[m].z_host_once = nullptr;
     if (rc) { c->counts_global = false; c->host_epoch = 0; return rc; }
+    if (bad) {
+        c->host_epoch = 0;
+        FAIL(h, MVTM_ERR_ARG, "mvtm_sweep_host_dist: the assignments hold %d topic ids >= K (treated as unassigned)", bad);
+    }
     c->host_epoch = h->mut_epoch;
     return MVTM_OK;
 }
