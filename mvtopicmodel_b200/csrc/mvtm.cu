@@ -577,7 +577,7 @@ static void ring_record(mvtm_handle *h, int m, float ms)
 
 static int choose_launch(mvtm_handle *h, int m, int R, LaunchCfg &lc)
 {
-    const int KS = h->KS, G = h->G, NSUB = 32 / G, JG = KS / (4 * G);
+    const int KS = h->KS, G = h->G, NSUB = 32 / G;
     const bool multi = h->M > 1;
     // The other-view mass can live in shared memory instead of the global scratch (MVTM_OC_SMEM=1).  Measured on
     // pubmed_3v / acm_2v: the extra 4*KS bytes per document cost more resident documents than the faster reads give
